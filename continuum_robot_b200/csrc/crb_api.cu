@@ -1,0 +1,402 @@
+// crb_api.cu -- kernels + C ABI of libcrb.so (see include/crb.h).  sm_100a only.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "crb.h"
+#include "crb_assemble.cuh"
+#include "crb_device.cuh"
+#include "crb_rk45.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error handling (thread-local string; no other global mutable state)
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CRB_E_ARG (-1)
+#define CRB_E_CUDA (-2)
+#define CRB_E_LIMIT (-3)
+
+static KPlan kplan_of(const crb_plan_t* p) {
+  KPlan k;
+  k.N = p->n_elements;
+  k.n_free = p->n_free;
+  k.n0 = p->n0;
+  k.p_act = p->p_act;
+  k.m = p->m;
+  k.g = p->g;
+  k.p = p->p;
+  k.levels = p->levels;
+  k.contiguous = p->contiguous;
+  k.has_mask = p->has_mask;
+  k.mfac_doubles = p->mfac_doubles;
+  return k;
+}
+
+extern "C" int crb_version(void) { return CRB_VERSION; }
+extern "C" const char* crb_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// crb_plan (host)
+// ------------------------------------------------------------------------------------------
+extern "C" int crb_plan(int32_t n_elements, const uint8_t* bc, int32_t max_slots_per_lane, crb_plan_t* out) {
+  if (!bc || !out) return fail(CRB_E_ARG, "crb_plan: null argument");
+  if (n_elements < 1) return fail(CRB_E_ARG, "crb_plan: n_elements must be >= 1, got %d", n_elements);
+  const int N = n_elements;
+  for (int i = 0; i <= N; ++i)
+    if (bc[i] > CRB_BC_PINNED) return fail(CRB_E_ARG, "crb_plan: bad boundary condition code %d at node %d", bc[i], i);
+  memset(out, 0, sizeof(*out));
+  const int mmax = max_slots_per_lane > 0 ? (max_slots_per_lane > 4 ? 4 : max_slots_per_lane) : 4;
+  const int n0 = bc[0] == CRB_BC_FIXED ? 1 : 0;
+  const int p_act = N + 1 - n0;
+  int g = 1;
+  while ((p_act + g - 1) / g > mmax && g < 32) g *= 2;
+  const int m = (p_act + g - 1) / g;
+  if (m > 4 || m * g > CRB_MAX_SLOTS)
+    return fail(CRB_E_LIMIT, "crb_plan: %d active nodes exceed the %d-slot limit of one lane group", p_act, 32 * 4);
+  int levels = 0;
+  while ((1 << levels) < g) ++levels;
+  out->n_elements = N;
+  out->n0 = n0;
+  out->p_act = p_act;
+  out->m = m;
+  out->g = g;
+  out->p = m * g;
+  out->levels = levels;
+  int r = 0, contiguous = 1;
+  for (int s = 0; s < out->p; ++s) {
+    for (int d = 0; d < 3; ++d) {
+      int idx = -1;
+      if (s < p_act) {
+        const int node = s + n0;
+        const bool constrained = bc[node] == CRB_BC_FIXED || (bc[node] == CRB_BC_PINNED && d < 2);
+        if (!constrained) idx = r++;
+        else contiguous = 0;
+      }
+      out->red_index[3 * s + d] = idx;
+    }
+  }
+  if (r == 0) return fail(CRB_E_ARG, "crb_plan: cannot constrain all degrees of freedom");
+  out->n_free = r;
+  out->contiguous = contiguous;
+  out->has_mask = !contiguous;
+  out->mfac_doubles = 2ll * CRB_SLOT_PAIRS * out->p + 2ll * CRB_SCAN_PAIRS * (levels > 0 ? levels : 1) * g;
+  out->kcoef_doubles = 4ll * out->p;
+  return 0;
+}
+
+static int fill_topo(const crb_plan_t* plan, const uint8_t* elem_type_host, AsmTopo* T) {
+  memset(T, 0, sizeof(*T));
+  for (int s = 0; s < plan->p; ++s) {
+    uint8_t fb = 0;
+    for (int d = 0; d < 3; ++d)
+      if (plan->red_index[3 * s + d] >= 0) fb |= (1u << d);
+    T->free_bits[s] = fb;
+    const int e = plan->n0 + s - 1;
+    uint8_t et = CRB_ELEM_ABSENT;
+    if (s < plan->p_act && e >= 0 && e < plan->n_elements) {
+      et = elem_type_host[e];
+      if (et > CRB_ELEM_NONLINEAR) return fail(CRB_E_ARG, "crb_assemble: bad element type %d at element %d", et, e);
+    }
+    T->etype[s] = et;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// crb_assemble
+// ------------------------------------------------------------------------------------------
+extern "C" int crb_assemble(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
+                            const uint8_t* elem_type_host, const uint8_t* bc_host, int32_t n_mass,
+                            int32_t n_stiff, int32_t n_force, double fluid_density, double* mfac,
+                            double* kcoef, uint8_t* elem_type_slots, double* drag, double* grav,
+                            double* seg_half_mass, void* stream) {
+  (void)bc_host;
+  if (!plan || !params || !elem_type_host || !mfac || !kcoef || !elem_type_slots)
+    return fail(CRB_E_ARG, "crb_assemble: null argument");
+  if (n_param_sets < 1) return fail(CRB_E_ARG, "crb_assemble: n_param_sets must be >= 1");
+  for (int v : {n_mass, n_stiff, n_force})
+    if (v != 1 && v != n_param_sets) return fail(CRB_E_ARG, "crb_assemble: set counts must be 1 or n_param_sets");
+  AsmTopo T;
+  if (int rc = fill_topo(plan, elem_type_host, &T)) return rc;
+  const int nthreads = std::max(std::max(n_mass, n_stiff), n_force);
+  const int block = 128;
+  const int grid = (nthreads + block - 1) / block;
+  crb_assemble_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(kplan_of(plan), T, params, n_param_sets, n_mass,
+                                                               n_stiff, n_force, fluid_density, mfac, kcoef,
+                                                               elem_type_slots, drag, grav, seg_half_mass);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_assemble: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels: RHS and fused RK4
+// ------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(CRB_THREADS)
+crb_rhs_kernel(KPlan P, crb_system_t S, SmemLayout SL, const double* __restrict__ X, double t,
+               double* __restrict__ dX) {
+  extern __shared__ __align__(16) double smem[];
+  const double* mf = stage_mfac(S, P, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mpw = 32 / P.g;
+  const int mloc = warp * mpw + lane / P.g;
+  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  LaneCtx<M> L;
+  load_lane_ctx<M>(L, P, S, member, lane % P.g, mf,
+                   SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  const RhsFlags F = make_flags(S, P);
+  double q[M][3], v[M][3], a[M][3];
+  load_state<M>(L, X, q, v);
+  beam_accel<M>(L, S, F, q, v, t, a);
+  store_state<M>(L, dX, v, a);
+}
+
+// Classical RK4, nsteps fused: state, stage state and the running combination stay in registers.
+template <int M>
+__global__ void __launch_bounds__(CRB_THREADS)
+crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
+               int nsteps, double* __restrict__ Y, int save_every) {
+  extern __shared__ __align__(16) double smem[];
+  const double* mf = stage_mfac(S, P, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mpw = 32 / P.g;
+  const int mloc = warp * mpw + lane / P.g;
+  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  LaneCtx<M> L;
+  load_lane_ctx<M>(L, P, S, member, lane % P.g, mf,
+                   SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  const RhsFlags F = make_flags(S, P);
+  double q[M][3], v[M][3];
+  load_state<M>(L, X, q, v);
+  const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
+  for (int k = 0; k < nsteps; ++k) {
+    const double t = t0 + k * h;
+    double qs[M][3], vs[M][3], aq[M][3], av[M][3], a[M][3];
+    // stage 1
+    beam_accel<M>(L, S, F, q, v, t, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        aq[j][d] = fma(h6, v[j][d], q[j][d]);
+        av[j][d] = fma(h6, a[j][d], v[j][d]);
+        qs[j][d] = fma(hh, v[j][d], q[j][d]);
+        vs[j][d] = fma(hh, a[j][d], v[j][d]);
+      }
+    // stage 2
+    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
+        av[j][d] = fma(h3, a[j][d], av[j][d]);
+        qs[j][d] = fma(hh, vs[j][d], q[j][d]);
+        vs[j][d] = fma(hh, a[j][d], v[j][d]);
+      }
+    // stage 3
+    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
+        av[j][d] = fma(h3, a[j][d], av[j][d]);
+        qs[j][d] = fma(h, vs[j][d], q[j][d]);
+        vs[j][d] = fma(h, a[j][d], v[j][d]);
+      }
+    // stage 4
+    beam_accel<M>(L, S, F, qs, vs, t + h, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        q[j][d] = fma(h6, vs[j][d], aq[j][d]);
+        v[j][d] = fma(h6, a[j][d], av[j][d]);
+      }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) {
+      const long long frame = (k + 1) / save_every - 1;
+      store_state<M>(L, Y + frame * (long long)S.n_members * 2 * L.n, q, v);
+    }
+  }
+  store_state<M>(L, X, q, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static int check_system(const char* who, const crb_plan_t* plan, const crb_system_t* sys) {
+  if (!plan || !sys) return fail(CRB_E_ARG, "%s: null plan/system", who);
+  if (sys->n_members < 1) return fail(CRB_E_ARG, "%s: n_members must be >= 1, got %d", who, sys->n_members);
+  if (!sys->mfac || !sys->kcoef || !sys->elem_type || !sys->red_index)
+    return fail(CRB_E_ARG, "%s: system not assembled (mfac/kcoef/elem_type/red_index missing)", who);
+  if (sys->grav_mode < 0 || sys->grav_mode > 2) return fail(CRB_E_ARG, "%s: bad grav_mode %d", who, sys->grav_mode);
+  if (sys->grav_mode == 1 && (!sys->grav || !plan->contiguous))
+    return fail(CRB_E_ARG, "%s: slot-space gravity needs grav[] and a contiguous plan", who);
+  if (sys->grav_mode == 2 && !sys->seg_half_mass)
+    return fail(CRB_E_ARG, "%s: generic gravity needs seg_half_mass[]", who);
+  if (sys->imp_amp && (sys->imp_dof < 0 || sys->imp_dof >= plan->n_free))
+    return fail(CRB_E_ARG, "%s: imp_dof %d outside [0,%d)", who, sys->imp_dof, plan->n_free);
+  return 0;
+}
+
+static SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
+  SmemLayout SL;
+  SL.mfac_doubles = sys->mass_shared ? (int)plan->mfac_doubles : 0;
+  SL.scratch_doubles = (sys->gain || sys->grav_mode == 2) ? 2 * plan->n_free : 0;
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
+  return SL;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes, const char* who) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 227 * 1024) return fail(CRB_E_LIMIT, "%s: needs %zu bytes of shared memory (> 227 KB)", who, bytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(CRB_E_CUDA, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+#define CRB_DISPATCH_M(mval, ...)                                  \
+  switch (mval) {                                                    \
+    case 1: { constexpr int M = 1; __VA_ARGS__; } break;                    \
+    case 2: { constexpr int M = 2; __VA_ARGS__; } break;                    \
+    case 3: { constexpr int M = 3; __VA_ARGS__; } break;                    \
+    case 4: { constexpr int M = 4; __VA_ARGS__; } break;                    \
+    default: return fail(CRB_E_LIMIT, "unsupported slots per lane %d", mval); \
+  }
+
+extern "C" int crb_rhs(const crb_plan_t* plan, const crb_system_t* sys, const double* X, double t, double* dX,
+                       void* stream) {
+  if (int rc = check_system("crb_rhs", plan, sys)) return rc;
+  if (!X || !dX) return fail(CRB_E_ARG, "crb_rhs: null state pointer");
+  size_t bytes;
+  const SmemLayout SL = smem_layout(plan, sys, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  CRB_DISPATCH_M(plan->m, {
+    if (int rc = set_smem(crb_rhs_kernel<M>, bytes, "crb_rhs")) return rc;
+    crb_rhs_kernel<M><<<grid, CRB_THREADS, bytes, (cudaStream_t)stream>>>(P, *sys, SL, X, t, dX);
+  });
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rhs: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
+                       int32_t nsteps, double* Y_out, int32_t save_every, void* stream) {
+  if (int rc = check_system("crb_rk4", plan, sys)) return rc;
+  if (!X) return fail(CRB_E_ARG, "crb_rk4: null state pointer");
+  if (nsteps < 0) return fail(CRB_E_ARG, "crb_rk4: nsteps must be >= 0");
+  if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_rk4: step h must be positive and finite");
+  if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_rk4: save_every must be >= 1 when Y_out is given");
+  if (nsteps == 0) return 0;
+  size_t bytes;
+  const SmemLayout SL = smem_layout(plan, sys, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  CRB_DISPATCH_M(plan->m, {
+    if (int rc = set_smem(crb_rk4_kernel<M>, bytes, "crb_rk4")) return rc;
+    crb_rk4_kernel<M><<<grid, CRB_THREADS, bytes, (cudaStream_t)stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out,
+                                                                         save_every);
+  });
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// crb_rk45
+// ------------------------------------------------------------------------------------------
+extern "C" int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t, double* h_abs,
+                        double t_bound, double rtol, double atol, const double* t_eval, int32_t n_eval,
+                        double* Y_eval, int32_t* status, int64_t* counters, int32_t max_attempts, void* stream) {
+  if (int rc = check_system("crb_rk45", plan, sys)) return rc;
+  if (!X || !t || !h_abs || !status || !counters) return fail(CRB_E_ARG, "crb_rk45: null argument");
+  if (n_eval < 0 || (n_eval > 0 && (!t_eval || !Y_eval))) return fail(CRB_E_ARG, "crb_rk45: bad t_eval / Y_eval");
+  if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(CRB_E_ARG, "crb_rk45: rtol must be > 0 and atol >= 0");
+  if (max_attempts < 1) return fail(CRB_E_ARG, "crb_rk45: max_attempts must be >= 1");
+  size_t bytes;
+  const SmemLayout SL = smem_layout(plan, sys, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  Rk45Args A;
+  A.X = X; A.t = t; A.h_abs = h_abs; A.t_bound = t_bound; A.rtol = rtol; A.atol = atol;
+  A.t_eval = t_eval; A.n_eval = n_eval; A.Y_eval = Y_eval; A.status = status; A.counters = reinterpret_cast<long long*>(counters);
+  A.max_attempts = max_attempts;
+  const DpTab T = make_dp_tab();
+  CRB_DISPATCH_M(plan->m, {
+    const size_t total = bytes + sizeof(double) * 21 * M * CRB_THREADS;  // kv stage storage
+    if (int rc = set_smem(crb_rk45_kernel<M>, total, "crb_rk45")) return rc;
+    crb_rk45_kernel<M><<<grid, CRB_THREADS, total, (cudaStream_t)stream>>>(P, *sys, SL, A, T);
+  });
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk45: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// crb_dense_matrices (host): BC-reduced M and K of one design, for LQR synthesis on the host.
+// models/segments.py:32-78, euler_bernoulli_beam.py:139-161, 265, 422-511.
+// ------------------------------------------------------------------------------------------
+extern "C" int crb_dense_matrices(const crb_plan_t* plan, const double* par, const uint8_t* elem_type_host,
+                                  const uint8_t* bc_host, double* M_out, double* K_out) {
+  if (!plan || !par || !elem_type_host || !bc_host || !M_out) return fail(CRB_E_ARG, "crb_dense_matrices: null argument");
+  const int N = plan->n_elements, nf = 3 * (N + 1), n = plan->n_free;
+  if (K_out)
+    for (int e = 0; e < N; ++e)
+      if (elem_type_host[e] != CRB_ELEM_LINEAR)
+        return fail(CRB_E_ARG, "Cannot extract stiffness matrix from beam with nonlinear segments. Segment %d is nonlinear.", e);
+  std::vector<int> red(nf, -1);
+  int r = 0;
+  for (int node = 0; node <= N; ++node)
+    for (int d = 0; d < 3; ++d) {
+      const bool c = bc_host[node] == CRB_BC_FIXED || (bc_host[node] == CRB_BC_PINNED && d < 2);
+      if (!c) red[3 * node + d] = r++;
+    }
+  if (r != n) return fail(CRB_E_ARG, "crb_dense_matrices: plan / bc mismatch (%d vs %d free DOFs)", r, n);
+  for (long long k = 0; k < (long long)n * n; ++k) M_out[k] = 0.0;
+  if (K_out)
+    for (long long k = 0; k < (long long)n * n; ++k) K_out[k] = 0.0;
+  static const double mi[6][6] = {{140, 0, 0, 70, 0, 0},   {0, 156, -22, 0, 54, 13}, {0, -22, 4, 0, -13, -3},
+                                  {70, 0, 0, 140, 0, 0},   {0, 54, -13, 0, 156, 22}, {0, 13, -3, 0, 22, 4}};
+  static const int mp[6][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 1}, {0, 1, 2, 0, 1, 2},
+                               {0, 0, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 1}, {0, 1, 2, 0, 1, 2}};
+  for (int e = 0; e < N; ++e) {
+    const double* q = par + e * CRB_NPARAM;
+    const double L = q[CRB_P_LENGTH], mu = q[CRB_P_RHO] * q[CRB_P_AREA] * L / 420;
+    const double EI = q[CRB_P_E] * q[CRB_P_I], EA = q[CRB_P_E] * q[CRB_P_AREA];
+    const double a = EA / L, c1 = EI / L, c2 = EI / (L * L), c3 = EI / (L * L * L);
+    const double ke[6][6] = {{a, 0, 0, -a, 0, 0},
+                             {0, 12 * c3, -6 * c2, 0, -12 * c3, -6 * c2},
+                             {0, -6 * c2, 4 * c1, 0, 6 * c2, 2 * c1},
+                             {-a, 0, 0, a, 0, 0},
+                             {0, -12 * c3, 6 * c2, 0, 12 * c3, 6 * c2},
+                             {0, -6 * c2, 2 * c1, 0, 6 * c2, 4 * c1}};
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        const int ri = red[3 * e + i], rj = red[3 * e + j];
+        if (ri < 0 || rj < 0) continue;
+        M_out[(long long)ri * n + rj] += mi[i][j] * std::pow(L, mp[i][j]) * mu;
+        if (K_out) K_out[(long long)ri * n + rj] += ke[i][j];
+      }
+  }
+  return 0;
+}

@@ -1,0 +1,513 @@
+// crb_device.cuh -- device-side building blocks of the batched beam RHS (sm_100a).
+//
+// Work decomposition ("lane group"): one ensemble member is owned by G lanes of a warp; lane g
+// owns M consecutive node slots (slot s = g*M + j) and the element LEFT of each of its slots.
+// State, stage vectors and accumulators live in registers; neighbouring lanes exchange one
+// node of halo by warp shuffles; the banded mass solve is a partitioned (SPIKE-type) block
+// LDL^T whose constants are precomputed by crb_assemble (see crb_assemble.cuh).
+//
+// Reference behaviour restated here (paths under /root/reference/src/continuum_robot/):
+//   element forces     models/segments.py:32-62 (linear), :121-472 (nonlinear polynomials)
+//   scatter / BCs      models/euler_bernoulli_beam.py:163-219, 221-298
+//   drag, gravity      models/fluid_forces.py:103-142, models/gravity_forces.py:66-148
+//   RHS composition    models/dynamic_beam_model.py:256-272, 294-328, 343-362
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "crb.h"
+
+#define CRB_FULL_MASK 0xffffffffu
+#define CRB_SLOT_PAIRS 13  // 26 doubles of mass-solve constants per slot (as double2 pairs)
+#define CRB_SCAN_PAIRS 6   // 12 doubles of scan constants per lane per level
+
+// Scalars of crb_plan_t that kernels need (the red_index table travels as a device array).
+struct KPlan {
+  int N, n_free, n0, p_act, m, g, p, levels, contiguous, has_mask;
+  long long mfac_doubles;
+};
+
+__device__ __forceinline__ double shfl_up_d(double v, int d, int w) {
+  return __shfl_up_sync(CRB_FULL_MASK, v, d, w);
+}
+__device__ __forceinline__ double shfl_down_d(double v, int d, int w) {
+  return __shfl_down_sync(CRB_FULL_MASK, v, d, w);
+}
+
+// ------------------------------------------------------------------------------------------
+// Mass-solve constants: layout [pair][j][g] of double2 so the G lanes of a member read one
+// contiguous 16*G-byte run (conflict-free LDS.128 when staged in shared memory).
+//   pairs 0,1 Lm | 2,3 Sinv | 4,5 U | 6,7 Phi | 8,9 Psi | 10 (lu, sinv_u) | 11 (uu, phi_u) | 12 (psi_u, -)
+// ------------------------------------------------------------------------------------------
+template <int M>
+struct MassConsts {
+  const double* slot;  // base of the slot part
+  const double* scan;  // base of the scan part
+  int G, g;
+  __device__ __forceinline__ double2 ld(int pair, int j) const {
+    return *reinterpret_cast<const double2*>(slot + ((((pair * M) + j) * G + g) << 1));
+  }
+  __device__ __forceinline__ double2 lds(int level, int pair) const {
+    return *reinterpret_cast<const double2*>(scan + (((level * CRB_SCAN_PAIRS + pair) * G + g) << 1));
+  }
+};
+
+__device__ __forceinline__ void mv2(const double2 r0, const double2 r1, double x0, double x1,
+                                    double& y0, double& y1) {
+  // y += [r0; r1] * x
+  y0 = fma(r0.x, x0, fma(r0.y, x1, y0));
+  y1 = fma(r1.x, x0, fma(r1.y, x1, y1));
+}
+
+// Solve M a = b in place (b[j][d], d = u,w,phi).  Algebraically exact partitioned solve:
+//   local forward  y~_s = b_s - Lm_s y~_{s-1}          (incoming boundary value ignored)
+//   forward scan   z_g  = y~_last(g) + Tl_g z_{g-1}     (Kogge-Stone with precomputed products)
+//   local backward x~_s = Sinv_s y~_s - U_s x~_{s+1}
+//   backward scan  w_g  = x~_first(g) + Phi_first y_in + Psi_first w_{g+1}
+//   correction     x_s  = x~_s + Phi_s y_in(g) + Psi_s x_in(g)
+template <int M>
+__device__ __forceinline__ void mass_solve(double (&b)[M][3], const MassConsts<M>& C, int levels) {
+  const int G = C.G;
+  // ---- local forward ----
+#pragma unroll
+  for (int j = 1; j < M; ++j) {
+    const double2 l0 = C.ld(0, j), l1 = C.ld(1, j);
+    const double lu = C.ld(10, j).x;
+    b[j][0] = fma(-lu, b[j - 1][0], b[j][0]);
+    const double p0 = b[j - 1][1], p1 = b[j - 1][2];
+    b[j][1] = fma(-l0.x, p0, fma(-l0.y, p1, b[j][1]));
+    b[j][2] = fma(-l1.x, p0, fma(-l1.y, p1, b[j][2]));
+  }
+  double yin0 = 0.0, yin1 = 0.0, yin2 = 0.0;
+  if (G > 1) {
+    double z0 = b[M - 1][0], z1 = b[M - 1][1], z2 = b[M - 1][2];
+    for (int l = 0; l < levels; ++l) {
+      const int d = 1 << l;
+      const double s0 = shfl_up_d(z0, d, G), s1 = shfl_up_d(z1, d, G), s2 = shfl_up_d(z2, d, G);
+      const double2 c0 = C.lds(l, 0), c1 = C.lds(l, 1), cu = C.lds(l, 2);
+      z0 = fma(cu.x, s0, z0);
+      mv2(c0, c1, s1, s2, z1, z2);
+    }
+    yin0 = shfl_up_d(z0, 1, G);
+    yin1 = shfl_up_d(z1, 1, G);
+    yin2 = shfl_up_d(z2, 1, G);
+    if (C.g == 0) { yin0 = 0.0; yin1 = 0.0; yin2 = 0.0; }
+  }
+  // ---- local backward on the uncorrected y~ ----
+  {
+    const double2 s0 = C.ld(2, M - 1), s1 = C.ld(3, M - 1);
+    const double su = C.ld(10, M - 1).y;
+    const double y1 = b[M - 1][1], y2 = b[M - 1][2];
+    b[M - 1][0] *= su;
+    b[M - 1][1] = fma(s0.x, y1, s0.y * y2);
+    b[M - 1][2] = fma(s1.x, y1, s1.y * y2);
+  }
+#pragma unroll
+  for (int j = M - 2; j >= 0; --j) {
+    const double2 s0 = C.ld(2, j), s1 = C.ld(3, j), u0 = C.ld(4, j), u1 = C.ld(5, j);
+    const double2 cu = C.ld(10, j);
+    const double uu = C.ld(11, j).x;
+    const double y1 = b[j][1], y2 = b[j][2];
+    const double n1 = b[j + 1][1], n2 = b[j + 1][2];
+    b[j][0] = fma(cu.y, b[j][0], -uu * b[j + 1][0]);
+    b[j][1] = fma(s0.x, y1, fma(s0.y, y2, -fma(u0.x, n1, u0.y * n2)));
+    b[j][2] = fma(s1.x, y1, fma(s1.y, y2, -fma(u1.x, n1, u1.y * n2)));
+  }
+  if (G > 1) {
+    // ---- backward scan on the first slot of every chunk ----
+    double w0, w1, w2;
+    {
+      const double2 f0 = C.ld(6, 0), f1 = C.ld(7, 0);
+      const double fu = C.ld(11, 0).y;
+      w0 = fma(fu, yin0, b[0][0]);
+      w1 = b[0][1];
+      w2 = b[0][2];
+      mv2(f0, f1, yin1, yin2, w1, w2);
+    }
+    for (int l = 0; l < levels; ++l) {
+      const int d = 1 << l;
+      const double s0 = shfl_down_d(w0, d, G), s1 = shfl_down_d(w1, d, G), s2 = shfl_down_d(w2, d, G);
+      const double2 c0 = C.lds(l, 3), c1 = C.lds(l, 4), cu = C.lds(l, 5);
+      w0 = fma(cu.x, s0, w0);
+      mv2(c0, c1, s1, s2, w1, w2);
+    }
+    double xin0 = shfl_down_d(w0, 1, G), xin1 = shfl_down_d(w1, 1, G), xin2 = shfl_down_d(w2, 1, G);
+    if (C.g == G - 1) { xin0 = 0.0; xin1 = 0.0; xin2 = 0.0; }
+    // ---- correction ----
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double2 f0 = C.ld(6, j), f1 = C.ld(7, j), p0 = C.ld(8, j), p1 = C.ld(9, j);
+      const double fu = C.ld(11, j).y, pu = C.ld(12, j).x;
+      b[j][0] = fma(fu, yin0, fma(pu, xin0, b[j][0]));
+      mv2(f0, f1, yin1, yin2, b[j][1], b[j][2]);
+      mv2(p0, p1, xin1, xin2, b[j][1], b[j][2]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Element forces.  `c` = 4 coefficients written by crb_assemble for the element's type.
+// Both accumulate  bA -= f[0:3]  (node 1) and  bB -= f[3:6]  (node 2).
+// ------------------------------------------------------------------------------------------
+
+// linear: c = (EA/L, 12EI/L^3, 6EI/L^2, 2EI/L)   (models/segments.py:32-62)
+__device__ __forceinline__ void elem_linear(const double4 c, const double (&qa)[3], const double (&qb)[3],
+                                            double (&bA)[3], double (&bB)[3]) {
+  const double du = qa[0] - qb[0];
+  const double d = qa[1] - qb[1];
+  const double s = qa[2] + qb[2];
+  const double fu = c.x * du;                 // axial force on node 1 (node 2: -fu)
+  const double V = fma(c.y, d, -c.z * s);     // shear on node 1 (node 2: -V)
+  const double R = fma(c.w, s, -c.z * d);     // common part of both end moments
+  bA[0] -= fu;
+  bB[0] += fu;
+  bA[1] -= V;
+  bB[1] += V;
+  bA[2] -= fma(c.w, qa[2], R);
+  bB[2] -= fma(c.w, qb[2], R);
+}
+
+// nonlinear: c = (EA/L^2, EI/L^2, L, 1/L).  The six polynomials of models/segments.py:159-472
+// rewritten in the scaled variables a = theta1*L, b = theta2*L, d = w1-w2, e = u1-u2 (the
+// monomials group exactly; decimal literals are the reference's).  Node order
+// [f1,f3,f4 | f2,f5,f6] (segments.py:146-155); f5 = -f3; f1 keeps the one-sided axial term of
+// segments.py:197-205.
+__device__ __forceinline__ void elem_nonlinear(const double4 c, const double (&qa)[3], const double (&qb)[3],
+                                               double (&bA)[3], double (&bB)[3]) {
+  const double al = c.x, de = c.y, L = c.z, iL = c.w;
+  const double u1 = qa[0], u2 = qb[0];
+  const double a = qa[2] * L, b = qb[2] * L;
+  const double d = qa[1] - qb[1];
+  const double e = u1 - u2;
+  const double Le = L * e;
+  const double a2 = a * a, b2 = b * b, d2 = d * d, ab = a * b;
+  // axial pair f1 / f2
+  const double g1 = fma(0.0666666666666665, a, fma(-0.0166666666666667, b, -0.05 * d));
+  const double g2 = fma(0.0166666666666667, a, fma(-0.0666666666666667, b, 0.05 * d));
+  const double g3 = fma(-0.05, a + b, 0.6 * d);
+  const double T = fma(a, g1, -b * g2);
+  const double f1 = al * (fma(L, u1, -T) - (u2 + d) * g3);
+  const double f2 = al * (fma(d, g3, T) - Le);
+  // transverse force f3 (= -f5)
+  const double apb = a + b;
+  double A3 = 0.0357142857143344 * fma(a2, a, b2 * b);
+  A3 = fma(-0.107142857143003 * ab, apb, A3);
+  A3 = fma(1.28571428571433 * d, a2 + b2, A3);
+  A3 = fma(Le, apb, A3);
+  A3 = fma(-d2, fma(3.8571428571413, a, 3.857142857143 * b), A3);
+  A3 = fma(-12.0 * Le, d, A3);
+  A3 = fma(10.2857142857147 * d2, d, A3);
+  const double D3 = fma(120.0, d, -60.0 * apb);
+  const double f3 = (0.1 * iL) * fma(al, A3, de * D3);
+  // moment f4 (node 1)
+  double A4 = 0.0285714285714391 * a2 * a;
+  A4 = fma(-0.0107142857142861 * a2, b, A4);
+  A4 = fma(0.0107142857142719 * d, a2 - b2, A4);
+  A4 = fma(0.00714285714286444 * a, b2, A4);
+  A4 = fma(-0.0214285714286007 * ab, d, A4);
+  A4 = fma(Le, fma(-0.133333333333333, a, 0.0333333333333333 * b), A4);
+  A4 = fma(0.128571428571433 * a, d2, A4);
+  A4 = fma(-0.00357142857143344 * b2, b, A4);
+  A4 = fma(0.1 * Le, d, A4);
+  A4 = fma(-0.128571428571377 * d2, d, A4);
+  const double f4 = fma(al, A4, de * fma(4.0, a, fma(2.0, b, -6.0 * d)));
+  // moment f6 (node 2)
+  double A6 = -0.00357142857143344 * a2 * a;
+  A6 = fma(0.00714285714286356 * a2, b, A6);
+  A6 = fma(-0.0107142857143003 * a2, d, A6);
+  A6 = fma(-0.0107142857142932 * a, b2, A6);
+  A6 = fma(-0.021428571428558 * ab, d, A6);
+  A6 = fma(Le, fma(0.0333333333333333, a, -0.133333333333333 * b), A6);
+  A6 = fma(0.0285714285714271 * b2, b, A6);
+  A6 = fma(0.0107142857142932 * b2, d, A6);
+  A6 = fma(0.128571428571428 * b, d2, A6);
+  A6 = fma(0.1 * Le, d, A6);
+  A6 = fma(-0.128571428571433 * d2, d, A6);
+  const double f6 = fma(al, A6, de * fma(2.0, a, fma(4.0, b, -6.0 * d)));
+  bA[0] -= f1;
+  bA[1] -= f3;
+  bA[2] -= f4;
+  bB[0] -= f2;
+  bB[1] += f3;
+  bB[2] -= f6;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-lane constant context of one member (loaded once per launch / per member batch).
+// ------------------------------------------------------------------------------------------
+template <int M>
+struct LaneCtx {
+  int G, g, levels;
+  int member;            // clamped member index
+  bool active;           // member < B
+  int n;                 // free position DOFs
+  int nseg;              // number of CSV rows (= elements)
+  int ri[M][3];          // reduced index of own DOFs (-1: constrained / phantom)
+  int et[M];             // type of the element left of own slot j
+  double4 kc[M];         // stiffness coefficients of that element
+  double drag[M];        // drag factor of own slot (0 = none)
+  double gl[M], gt[M];   // gravity half masses: two-ended pseudo-segment left of slot, tail
+  MassConsts<M> mc;
+  double* scratch;       // shared-memory scratch of this member (2n doubles) or nullptr
+};
+
+struct RhsFlags {
+  bool drag, grav_slot, grav_generic, mask, uconst, impulse, gain, fext;
+};
+
+__device__ __forceinline__ RhsFlags make_flags(const crb_system_t& s, const KPlan& p) {
+  RhsFlags f;
+  f.drag = s.drag != nullptr;
+  f.grav_slot = s.grav_mode == 1;
+  f.grav_generic = s.grav_mode == 2;
+  f.mask = p.has_mask != 0;
+  f.uconst = s.u_const != nullptr;
+  f.impulse = s.imp_amp != nullptr;
+  f.gain = s.gain != nullptr;
+  f.fext = s.f_ext != nullptr;
+  return f;
+}
+
+template <int M>
+__device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, const crb_system_t& S,
+                                              int member, int g, const double* mfac_smem,
+                                              double* scratch) {
+  L.G = P.g;
+  L.g = g;
+  L.levels = P.levels;
+  L.n = P.n_free;
+  L.nseg = P.N;
+  L.active = member < S.n_members;
+  L.member = L.active ? member : S.n_members - 1;
+  L.scratch = scratch;
+  const int s0 = g * M;
+  const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)L.member * P.p * 4);
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const int s = s0 + j;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) L.ri[j][d] = S.red_index[3 * s + d];
+    L.et[j] = S.elem_type[s];
+    const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * s);
+    const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * s + 2);
+    L.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
+    const long long fo = S.force_shared ? 0ll : (long long)L.member * P.p;
+    L.drag[j] = S.drag ? S.drag[fo + s] : 0.0;
+    L.gl[j] = (S.grav && S.grav_mode == 1) ? S.grav[2 * (fo + s)] : 0.0;
+    L.gt[j] = (S.grav && S.grav_mode == 1) ? S.grav[2 * (fo + s) + 1] : 0.0;
+  }
+  const double* mf = S.mass_shared ? mfac_smem : S.mfac + (long long)L.member * P.mfac_doubles;
+  L.mc.slot = mf;
+  L.mc.scan = mf + 2 * CRB_SLOT_PAIRS * P.p;
+  L.mc.G = P.g;
+  L.mc.g = g;
+}
+
+// Gravity contribution of one pseudo-segment (gravity_forces.py:117-125).
+__device__ __forceinline__ void grav_pair(double phi, double hm, double gx, double gy, double& fa,
+                                          double& ft) {
+  double sn, cs;
+  sincos(phi, &sn, &cs);
+  fa = fma(cs, gx, sn * gy) * hm;
+  ft = fma(-sn, gx, cs * gy) * hm;
+}
+
+// a = M^-1 ( -k(q) + f(x) + u(t) ) for the lane's slots.  q, v: stage state; out: acceleration.
+template <int M>
+__device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system_t& S, const RhsFlags F,
+                                           const double (&q)[M][3], const double (&v)[M][3],
+                                           double t, double (&acc)[M][3]) {
+  const int G = L.G;
+  // halo: q of the slot left of this lane's first slot (zero at the root / outside the beam)
+  double qh[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    qh[d] = shfl_up_d(q[M - 1][d], 1, G);
+    if (L.g == 0) qh[d] = 0.0;
+  }
+  double send[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) acc[j][d] = 0.0;
+
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    if (j == 0) {
+      if (L.et[0] == CRB_ELEM_LINEAR) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
+      else if (L.et[0] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
+    } else {
+      if (L.et[j] == CRB_ELEM_LINEAR) elem_linear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      else if (L.et[j] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+    }
+    if (F.grav_slot) {
+      // pseudo-segment between slot s-1 and s in REDUCED numbering
+      if (L.gl[j] != 0.0) {
+        const double pl = (j == 0) ? qh[2] : q[j == 0 ? 0 : j - 1][2];
+        double fa, ft;
+        grav_pair(0.5 * (pl + q[j][2]), L.gl[j], S.gx, S.gy, fa, ft);
+        acc[j][0] += fa;
+        acc[j][1] += ft;
+        if (j == 0) { send[0] += fa; send[1] += ft; }
+        else { acc[j == 0 ? 0 : j - 1][0] += fa; acc[j == 0 ? 0 : j - 1][1] += ft; }
+      }
+      if (L.gt[j] != 0.0) {  // last pseudo-segment: end node index falls off the reduced vector
+        double fa, ft;
+        grav_pair(q[j][2], L.gt[j], S.gx, S.gy, fa, ft);
+        acc[j][0] += fa;
+        acc[j][1] += ft;
+      }
+    }
+    if (F.drag) {
+      const double w = v[j][1];
+      acc[j][1] += (-L.drag[j] * w) * fabs(w);
+    }
+  }
+  // forces on the last slot of the left neighbour travel one lane down
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double r = shfl_down_d(send[d], 1, G);
+    if (L.g == G - 1) r = 0.0;
+    acc[M - 1][d] += r;
+  }
+
+  // ---- reduced-vector scratch paths: feedback gain and generic-BC gravity ----
+  if (F.gain || F.grav_generic) {
+    double* e = L.scratch;  // [2n]: e = x (positions then velocities) in reduced order
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.ri[j][d] >= 0) {
+          e[L.ri[j][d]] = q[j][d];
+          e[L.n + L.ri[j][d]] = v[j][d];
+        }
+    __syncwarp();
+    const int n = L.n;
+    if (F.gain) {
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int r = L.ri[j][d];
+          if (r >= 0) {
+            const double* row = S.gain + (long long)r * 2 * n;
+            double sacc = 0.0;
+            for (int c = 0; c < 2 * n; ++c) {
+              const double ref = S.ref ? __ldg(S.ref + c) : 0.0;
+              sacc = fma(__ldg(row + c), ref - e[c], sacc);
+            }
+            acc[j][d] += sacc;
+          }
+        }
+    }
+    if (F.grav_generic) {
+      // gravity_forces.py:97-146 evaluated in REDUCED indices: DOF r = 3k + c gets
+      // the axial (c=0) / transverse (c=1) share of pseudo-segment k (as its start node) and
+      // of pseudo-segment k-1 (as its end node); rotations are read at reduced 3i+2, 3i+5.
+      const double* hm = S.seg_half_mass + (S.force_shared ? 0ll : (long long)L.member * L.nseg);
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int r = L.ri[j][d];
+          if (r < 0) continue;
+          const int c = r % 3, k = r / 3;
+          if (c == 2) continue;
+          double tot = 0.0;
+          for (int side = 1; side >= 0; --side) {
+            const int i = k - side;
+            if (i < 0 || i >= L.nseg) continue;
+            const int ia = 3 * i + 2, ib = 3 * i + 5;
+            double phi = 0.0;
+            if (ia < n && ib < n) phi = 0.5 * (e[ia] + e[ib]);
+            else if (ia < n) phi = e[ia];
+            else if (ib < n) phi = e[ib];
+            double fa, ft;
+            grav_pair(phi, hm[i], S.gx, S.gy, fa, ft);
+            tot += (c == 0) ? fa : ft;
+          }
+          acc[j][d] += tot;
+        }
+    }
+  }
+
+  // ---- inputs u(t): constant part, impulse, external force (dynamic_beam_model.py:357-362) ----
+  if (F.uconst || F.fext || F.impulse) {
+    const long long mo = (long long)L.member * L.n;
+    const bool imp_on = F.impulse && (t < S.imp_duration);
+    const double amp = imp_on ? S.imp_amp[L.member] : 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int r = L.ri[j][d];
+        if (r >= 0) {
+          double u = 0.0;
+          if (F.uconst) u += S.u_const[mo + r];
+          if (F.fext) u += S.f_ext[mo + r];
+          if (imp_on && r == S.imp_dof) u += amp;
+          acc[j][d] += u;
+        }
+      }
+  }
+  if (F.mask) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.ri[j][d] < 0) acc[j][d] = 0.0;
+  }
+  mass_solve<M>(acc, L.mc, L.levels);
+}
+
+// ------------------------------------------------------------------------------------------
+// launch geometry, shared-memory staging and state I/O shared by all kernels
+// ------------------------------------------------------------------------------------------
+#define CRB_WARPS_PER_BLOCK 4
+#define CRB_THREADS (32 * CRB_WARPS_PER_BLOCK)
+
+// Shared memory: [mfac set (if mass_shared)] [per-member scratch of 2n doubles (if needed)]
+struct SmemLayout {
+  int mfac_doubles;     // 0 if not staged
+  int scratch_doubles;  // per member, 0 if unused
+};
+
+__device__ __forceinline__ const double* stage_mfac(const crb_system_t& S, const KPlan& P, double* smem) {
+  if (!S.mass_shared) return nullptr;
+  for (int k = threadIdx.x; k < (int)P.mfac_doubles; k += blockDim.x) smem[k] = S.mfac[k];
+  __syncthreads();
+  return smem;
+}
+
+template <int M>
+__device__ __forceinline__ void load_state(const LaneCtx<M>& L, const double* __restrict__ X,
+                                           double (&q)[M][3], double (&v)[M][3]) {
+  const double* x = X + (long long)L.member * 2 * L.n;
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int r = L.ri[j][d];
+      q[j][d] = r >= 0 ? x[r] : 0.0;
+      v[j][d] = r >= 0 ? x[L.n + r] : 0.0;
+    }
+}
+template <int M>
+__device__ __forceinline__ void store_state(const LaneCtx<M>& L, double* __restrict__ X,
+                                            const double (&q)[M][3], const double (&v)[M][3]) {
+  if (!L.active) return;
+  double* x = X + (long long)L.member * 2 * L.n;
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int r = L.ri[j][d];
+      if (r >= 0) {
+        x[r] = q[j][d];
+        x[L.n + r] = v[j][d];
+      }
+    }
+}
+

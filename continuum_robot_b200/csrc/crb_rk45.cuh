@@ -1,0 +1,330 @@
+// crb_rk45.cuh -- adaptive Dormand-Prince 5(4) with one independent (t, h) per member.
+//
+// Restates, per lane group, the step controller of SciPy's RK45 as the reference uses it through
+// scipy.integrate.solve_ivp (call sites: examples/pyodide_example/pyodide_example.py:69-75 and
+// the reference's tests; SciPy source scipy/integrate/_ivp/rk.py:14-72 rk_step, :111-176
+// _step_impl, :538-565 tableau, common.py:63-135 norm / select_initial_step, ivp.py t_eval
+// handling through the quartic dense output rk.py:178-180).
+//
+// Stage derivatives: K_s = (kq_s, kv_s) with kq_s = v-stage, so only the accelerations kv_s are
+// stored (shared memory, [stage][slot][dof][thread] = conflict-free); position stages use the
+// squared tableau  q_s = q + h c_s v + h^2 sum_l (A A)_{sl} kv_l, identical to SciPy's
+// y + h sum_j a_sj K_j up to rounding.
+#pragma once
+#include "crb_device.cuh"
+
+struct Rk45Args {
+  double* X;
+  double* t;
+  double* h_abs;
+  double t_bound, rtol, atol;
+  const double* t_eval;
+  int n_eval;
+  double* Y_eval;
+  int* status;
+  long long* counters;
+  int max_attempts;
+};
+
+// Extended tableau rows s = 1..6 (row 6 = the 5th-order weights B, used for y_new).
+struct DpTab {
+  double a[7][6];    // a[s][l], l < s
+  double a2[7][6];   // (A_ext A)[s][l]
+  double c[7];       // row sums (stage times)
+  double e[7];       // error weights for velocities
+  double e2[6];      // error weights for positions (h^2 factor)
+  double p[7][4];    // dense-output polynomial for velocities
+  double p2[6][4];   // dense-output polynomial for positions (h factor), plus colsum * v
+  double pcs[4];     // column sums of P
+};
+
+__host__ __device__ inline DpTab make_dp_tab() {
+  DpTab T = {};
+  const double A[6][5] = {{0, 0, 0, 0, 0},
+                          {1.0 / 5, 0, 0, 0, 0},
+                          {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                          {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                          {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                          {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+  const double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+  const double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+  const double Pm[7][4] = {
+      {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
+      {0, 0, 0, 0},
+      {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
+      {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
+      {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
+      {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
+      {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+  for (int s = 0; s < 6; ++s)
+    for (int l = 0; l < 5; ++l) T.a[s][l] = A[s][l];
+  for (int l = 0; l < 6; ++l) T.a[6][l] = B[l];
+  for (int s = 0; s < 7; ++s) {
+    double cs = 0;
+    for (int l = 0; l < 6; ++l) cs += T.a[s][l];
+    T.c[s] = cs;
+    for (int l = 0; l < 6; ++l) {
+      double v = 0;
+      for (int j = 0; j < 6; ++j) v += T.a[s][j] * T.a[j][l];
+      T.a2[s][l] = v;
+    }
+    T.e[s] = E[s];
+  }
+  for (int l = 0; l < 6; ++l) {
+    double v = 0;
+    for (int j = 0; j < 7; ++j) v += E[j] * T.a[j][l];
+    T.e2[l] = v;
+  }
+  for (int k = 0; k < 4; ++k) {
+    double cs = 0;
+    for (int j = 0; j < 7; ++j) {
+      T.p[j][k] = Pm[j][k];
+      cs += Pm[j][k];
+    }
+    T.pcs[k] = cs;
+    for (int l = 0; l < 6; ++l) {
+      double v = 0;
+      for (int j = 0; j < 7; ++j) v += Pm[j][k] * T.a[j][l];
+      T.p2[l][k] = v;
+    }
+  }
+  return T;
+}
+
+// nextafter(t, +inf) for finite t (rk.py:120)
+__device__ __forceinline__ double next_up(double t) {
+  if (t == 0.0) return __longlong_as_double(1ll);
+  const long long b = __double_as_longlong(t);
+  return __longlong_as_double(t > 0.0 ? b + 1 : b - 1);
+}
+
+// sum over the G lanes of a member (butterfly; every lane gets the total)
+__device__ __forceinline__ double group_sum(double v, int G) {
+  for (int d = G >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(CRB_FULL_MASK, v, d, G);
+  return v;
+}
+
+template <int M>
+__global__ void __launch_bounds__(CRB_THREADS)
+crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
+  extern __shared__ __align__(16) double smem[];
+  const double* mf = stage_mfac(S, P, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = P.g, mpw = 32 / G;
+  const int mloc = warp * mpw + lane / G;
+  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  LaneCtx<M> L;
+  const int mpb = CRB_WARPS_PER_BLOCK * mpw;
+  load_lane_ctx<M>(L, P, S, member, lane % G, mf,
+                   SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  const RhsFlags F = make_flags(S, P);
+  // kv stage storage: [stage 0..6][j][d][thread]
+  double* kvs = smem + SL.mfac_doubles + SL.scratch_doubles * mpb + threadIdx.x;
+  auto KV = [&](int s, int j, int d) -> double& { return kvs[((s * M + j) * 3 + d) * CRB_THREADS]; };
+  const double inv_size = 1.0 / (2.0 * L.n);
+
+  double q[M][3], v[M][3], qs[M][3], vs[M][3], a[M][3];
+  load_state<M>(L, A.X, q, v);
+  double t = A.t[L.member];
+  double h_abs = A.h_abs[L.member];
+  const double tb = A.t_bound, rtol = A.rtol, atol = A.atol;
+  long long nfev = 0, nacc = 0, nrej = 0;
+  int status = 0;
+  bool running = L.active && (t < tb);
+  int ie = 0;
+  while (ie < A.n_eval && A.t_eval[ie] < t) ++ie;  // outputs before the current time are not ours
+  if (ie < A.n_eval && A.t_eval[ie] == t && running) {
+    // SciPy emits t_eval == t0 from the first step's interpolant at x = 0, i.e. y_old itself
+    store_state<M>(L, A.Y_eval + (long long)ie * S.n_members * 2 * L.n, q, v);
+    ++ie;
+  }
+
+  // f0 = f(t, y)
+  beam_accel<M>(L, S, F, q, v, t, a);
+  nfev += 1;
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) KV(0, j, d) = a[j][d];
+
+  // ---- select_initial_step (common.py:68-135), order = 4 ----
+  {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.ri[j][d] >= 0) {
+          const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
+          const double yq = q[j][d] / scq, yv = v[j][d] / scv;
+          const double fq = v[j][d] / scq, fv = a[j][d] / scv;
+          s0 += yq * yq + yv * yv;
+          s1 += fq * fq + fv * fv;
+        }
+    const double d0 = sqrt(group_sum(s0, G) * inv_size), d1 = sqrt(group_sum(s1, G) * inv_size);
+    const double interval = fabs(tb - t);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, interval);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        qs[j][d] = fma(h0, v[j][d], q[j][d]);
+        vs[j][d] = fma(h0, a[j][d], v[j][d]);
+      }
+    double a1[M][3];
+    beam_accel<M>(L, S, F, qs, vs, t + h0, a1);
+    double s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.ri[j][d] >= 0) {
+          const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
+          const double dq = (vs[j][d] - v[j][d]) / scq, dv = (a1[j][d] - a[j][d]) / scv;
+          s2 += dq * dq + dv * dv;
+        }
+    const double d2 = sqrt(group_sum(s2, G) * inv_size) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 0.2);
+    const double hsel = fmin(fmin(100.0 * h0, h1), interval);
+    if (!(h_abs > 0.0)) {  // caller asked for automatic selection
+      h_abs = hsel;
+      nfev += 1;
+    }
+  }
+
+  bool step_rejected = false, new_step = true;
+  int attempts = 0;
+  while (__any_sync(CRB_FULL_MASK, running)) {
+    if (attempts >= A.max_attempts) {
+      if (running) status = 1;
+      break;
+    }
+    ++attempts;
+    const double min_step = 10.0 * fabs(next_up(t) - t);
+    if (running && new_step && h_abs < min_step) h_abs = min_step;
+    new_step = false;
+    if (running && h_abs < min_step) {  // TOO_SMALL_STEP
+      status = -1;
+      running = false;
+    }
+    double h = h_abs;
+    double t_new = t + h;
+    if (t_new - tb > 0.0) t_new = tb;
+    h = t_new - t;
+    if (running) h_abs = fabs(h);
+    const double h2 = h * h;
+
+    // ---- stages 1..6 (6 = y_new with the 5th-order weights) ----
+    for (int s = 1; s <= 6; ++s) {
+      const double hc = h * T.c[s];
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double sv = 0.0, sq = 0.0;
+          for (int l = 0; l < s; ++l) {
+            const double k = KV(l, j, d);
+            sv = fma(T.a[s][l], k, sv);
+            sq = fma(T.a2[s][l], k, sq);
+          }
+          vs[j][d] = fma(h, sv, v[j][d]);
+          qs[j][d] = fma(h2, sq, fma(hc, v[j][d], q[j][d]));
+        }
+      beam_accel<M>(L, S, F, qs, vs, t + T.c[s] * h, a);
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) KV(s, j, d) = a[j][d];
+    }
+    if (running) nfev += 6;
+
+    // ---- error norm (rk.py:100-105, common.py:63-65) ----
+    double se = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.ri[j][d] >= 0) {
+          double ev = 0.0, eq = 0.0;
+          for (int l = 0; l < 7; ++l) {
+            const double k = KV(l, j, d);
+            ev = fma(T.e[l], k, ev);
+            if (l < 6) eq = fma(T.e2[l], k, eq);
+          }
+          const double scq = fma(fmax(fabs(q[j][d]), fabs(qs[j][d])), rtol, atol);
+          const double scv = fma(fmax(fabs(v[j][d]), fabs(vs[j][d])), rtol, atol);
+          const double rq = eq * h2 / scq, rv = ev * h / scv;
+          se += rq * rq + rv * rv;
+        }
+    const double err = sqrt(group_sum(se, G) * inv_size);
+
+    if (running) {
+      if (err < 1.0) {
+        double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+        if (step_rejected) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        nacc += 1;
+        // dense output at every t_eval in (t, t_new]  (ivp.py: searchsorted side='right')
+        while (ie < A.n_eval && A.t_eval[ie] <= t_new) {
+          const double x = (A.t_eval[ie] - t) / h;
+          const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+          double* out = A.Y_eval + ((long long)ie * S.n_members + L.member) * 2 * L.n;
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const int r = L.ri[j][d];
+              if (r < 0) continue;
+              double pv = 0.0, pq = 0.0;
+              for (int l = 0; l < 7; ++l) {
+                const double k = KV(l, j, d);
+                const double w = fma(T.p[l][0], x, fma(T.p[l][1], x2, fma(T.p[l][2], x3, T.p[l][3] * x4)));
+                pv = fma(w, k, pv);
+                if (l < 6) {
+                  const double w2 = fma(T.p2[l][0], x, fma(T.p2[l][1], x2, fma(T.p2[l][2], x3, T.p2[l][3] * x4)));
+                  pq = fma(w2, k, pq);
+                }
+              }
+              const double wcs = fma(T.pcs[0], x, fma(T.pcs[1], x2, fma(T.pcs[2], x3, T.pcs[3] * x4)));
+              out[r] = fma(h, fma(h, pq, wcs * v[j][d]), q[j][d]);
+              out[L.n + r] = fma(h, pv, v[j][d]);
+            }
+          ++ie;
+        }
+        // commit
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            q[j][d] = qs[j][d];
+            v[j][d] = vs[j][d];
+            KV(0, j, d) = KV(6, j, d);  // FSAL
+          }
+        t = t_new;
+        step_rejected = false;
+        new_step = true;
+        if (t >= tb) running = false;
+      } else {
+        h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+        step_rejected = true;
+        nrej += 1;
+      }
+    }
+    __syncwarp();
+  }
+
+  if (L.active) {
+    store_state<M>(L, A.X, q, v);
+    if (L.g == 0) {
+      A.t[L.member] = t;
+      A.h_abs[L.member] = h_abs;
+      A.status[L.member] = status;
+      A.counters[3ll * L.member + 0] += nfev;
+      A.counters[3ll * L.member + 1] += nacc;
+      A.counters[3ll * L.member + 2] += nrej;
+    }
+  }
+}

@@ -1,0 +1,162 @@
+/* crb.h -- C ABI of libcrb.so, the B200 (sm_100a) batched beam integrator.
+ *
+ * Drop-in boundary for the ONE hot path of cram9030/continuum-robot: evaluating the
+ * Euler-Bernoulli finite-element state-space right-hand side and stepping it (RK4 / RK45)
+ * over an ensemble of beams.  The reference has no FFI (it is pure Python); each entry point
+ * below names the reference interface it replaces (paths relative to
+ * /root/reference/src/continuum_robot/).  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *  - every pointer marked "device" is CUDA device memory owned by the caller (PyTorch in the
+ *    shipped host layer); the library never allocates, frees or synchronises device memory;
+ *  - all work is enqueued on the caller's cudaStream_t (passed as void*);
+ *  - return value: 0 = success, negative = error, text in crb_last_error() (thread-local);
+ *  - per-member numerical outcomes (RK45 status, nfev ...) are data, not errors;
+ *  - the library keeps no mutable global state besides the thread-local error string.
+ *
+ * Memory layout ("member" = one beam of the ensemble, B members, N elements, n free position
+ * DOFs after boundary conditions, state x = [q(n) ; v(n)] in the reference's order
+ * (models/dynamic_beam_model.py:120-149, DOF order [u,w,phi] per free node)):
+ *     X        [B, 2n]  double, row-major, member-major (same vector the reference integrates)
+ *     params   [Bp, N, 7] double: length, elastic_modulus, moment_inertia, density, cross_area,
+ *              wetted_area, drag_coef  (the CSV columns of dynamic_beam_model.py:78-93);
+ *              Bp = 1 (one design shared by all members) or B
+ */
+#ifndef CRB_H_
+#define CRB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB_VERSION 100
+#define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
+#define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
+
+/* element types: models/abstractions.py:9-13 (ElementType) */
+#define CRB_ELEM_LINEAR 0
+#define CRB_ELEM_NONLINEAR 1
+#define CRB_ELEM_ABSENT 255
+/* boundary conditions: models/abstractions.py:16-20, euler_bernoulli_beam.py:240-254 */
+#define CRB_BC_NONE 0
+#define CRB_BC_FIXED 1
+#define CRB_BC_PINNED 2
+
+/* column order of params[..., 7] */
+enum { CRB_P_LENGTH = 0, CRB_P_E = 1, CRB_P_I = 2, CRB_P_RHO = 3, CRB_P_AREA = 4,
+       CRB_P_WETTED = 5, CRB_P_CD = 6, CRB_NPARAM = 7 };
+
+/* Topology of one ensemble: how the N+1 nodes map to "slots" of a lane group.
+ * A member is owned by G lanes of a warp, each lane owning m consecutive node slots
+ * (P = m*G >= active nodes).  A fully FIXED node 0 is trimmed (slot s = node s + n0).
+ * Filled by crb_plan() (host only). */
+typedef struct crb_plan_t {
+  int32_t n_elements;   /* N */
+  int32_t n_free;       /* n: free position DOFs (reduced vector length) */
+  int32_t n0;           /* 1 if node 0 is FIXED and trimmed, else 0 */
+  int32_t p_act;        /* active slots = N + 1 - n0 */
+  int32_t m;            /* slots per lane */
+  int32_t g;            /* lanes per member (power of two <= 32) */
+  int32_t p;            /* m * g */
+  int32_t levels;       /* log2(g) */
+  int32_t contiguous;   /* 1 if reduced index of (slot s, dof d) == 3 s + d for all s < p_act */
+  int32_t has_mask;     /* 1 if some DOF of an active slot is constrained */
+  int64_t mfac_doubles; /* doubles per mass-factor set */
+  int64_t kcoef_doubles;/* doubles per stiffness-coefficient set (4 per slot) */
+  int32_t red_index[3 * CRB_MAX_SLOTS]; /* (slot,dof) -> reduced index, or -1 */
+} crb_plan_t;
+
+/* Everything a RHS evaluation needs; all pointers are device pointers (NULL = feature off).
+ * Replaces the closure state of DynamicEulerBernoulliBeam (dynamic_beam_model.py:16-364):
+ * M_inv (:60) -> mfac, the stiffness closure (euler_bernoulli_beam.py:163-298) -> kcoef /
+ * elem_type / red_index, the auto-registered forces (:220-241) -> drag / grav. */
+typedef struct crb_system_t {
+  int32_t n_members;        /* B */
+  int32_t mass_shared;      /* 1: one mfac set for all members, 0: one per member */
+  int32_t stiff_shared;     /* same for kcoef */
+  int32_t force_shared;     /* same for drag / grav */
+  const double* mfac;       /* [Bm, plan.mfac_doubles]   (crb_assemble) */
+  const double* kcoef;      /* [Bk, P, 4]                (crb_assemble) */
+  const uint8_t* elem_type; /* [P] type of the element LEFT of slot s (CRB_ELEM_*) */
+  const int32_t* red_index; /* [3P] device copy of plan.red_index */
+  /* FluidDragForce (models/fluid_forces.py:24-142): F[w_k] = -drag[k] * wdot*|wdot| */
+  const double* drag;       /* [Bf, P] 0.5*rho_f*C_d*A_w per slot, or NULL */
+  /* GravityForce (models/gravity_forces.py:6-173), reduced-index semantics */
+  const double* grav;       /* [Bf, P, 2] half masses (left two-ended, tail), or NULL */
+  const double* seg_half_mass; /* [Bf, N] 0.5*rho*A*L per CSV row: generic-BC gravity path */
+  double gx, gy;            /* gravity_vector[0], [1] (gz ignored, gravity_forces.py:20) */
+  int32_t grav_mode;        /* 0 off, 1 slot-space (contiguous plans), 2 generic reduced-index */
+  /* inputs u (dynamic_beam_model.py:294-362): u = U + impulse(t) + gain (ref - x) */
+  const double* u_const;    /* [B, n] generalized force held constant over the call, or NULL */
+  const double* imp_amp;    /* [B] amplitude of a force on reduced DOF imp_dof for t < imp_duration */
+  int32_t imp_dof;          /* reduced position index (examples use n-2: tip w) */
+  double imp_duration;
+  /* FullStateLinear (control/full_state_linear.py:58): u_c = gain @ (ref - x) */
+  const double* gain;       /* [n, 2n] shared gain, or NULL */
+  const double* ref;        /* [2n] shared reference, NULL = 0 */
+  /* additive external generalized force (user torch callables evaluated between launches) */
+  const double* f_ext;      /* [B, n] or NULL */
+} crb_system_t;
+
+/* library version (CRB_VERSION of the build) */
+int crb_version(void);
+/* thread-local text of the last error returned on this thread ("" if none) */
+const char* crb_last_error(void);
+
+/* Host only.  Derive the slot layout for an N-element beam with boundary conditions bc[N+1]
+ * (CRB_BC_*; replaces EulerBernoulliBeam.apply_boundary_conditions bookkeeping,
+ * models/euler_bernoulli_beam.py:221-298).  max_slots_per_lane: 0 = library default. */
+int crb_plan(int32_t n_elements, const uint8_t* bc, int32_t max_slots_per_lane, crb_plan_t* out);
+
+/* One thread per member: element mass/stiffness assembly (segments.py:32-78,
+ * euler_bernoulli_beam.py:139-161), BC reduction (:221-298), and the factorisation that
+ * replaces scipy.sparse.linalg.inv(M) (dynamic_beam_model.py:60).
+ *   params device [Bp,N,7]; elem_type_host [N] (CRB_ELEM_LINEAR/NONLINEAR per CSV row)
+ *   n_mass / n_stiff / n_force: number of sets to emit (1 or Bp)
+ *   outputs (device): mfac [n_mass, mfac_doubles], kcoef [n_stiff, P, 4],
+ *     elem_type_slots [P], drag [n_force, P] (NULL to skip), grav [n_force, P, 2] (NULL to skip),
+ *     seg_half_mass [n_force, N] (NULL to skip) */
+int crb_assemble(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
+                 const uint8_t* elem_type_host, const uint8_t* bc_host,
+                 int32_t n_mass, int32_t n_stiff, int32_t n_force, double fluid_density,
+                 double* mfac, double* kcoef, uint8_t* elem_type_slots,
+                 double* drag, double* grav, double* seg_half_mass, void* stream);
+
+/* dX[B,2n] = f(t, X)  -- get_dynamic_system()(t, x, u) of dynamic_beam_model.py:343-362 for
+ * every member: [v ; M^-1(-k(q) + f(x) + u(t))]. */
+int crb_rhs(const crb_plan_t* plan, const crb_system_t* sys, const double* X, double t,
+            double* dX, void* stream);
+
+/* Classical fixed-step RK4 (north_star R1), nsteps steps fused in one launch, in place on X.
+ * t_k = t0 + k h; inputs evaluated at stage times.  If Y_out != NULL the state after every
+ * save_every-th step is stored at Y_out[(k/save_every - 1), B, 2n]. */
+int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
+            int32_t nsteps, double* Y_out, int32_t save_every, void* stream);
+
+/* Adaptive Dormand-Prince 5(4) with SciPy's controller (scipy/integrate/_ivp/rk.py:86-180),
+ * one independent (t, h) per member.  Replaces solve_ivp(method="RK45") as called at
+ * examples/pyodide_example/pyodide_example.py:69-75 and throughout the reference's tests.
+ *   t [B] in/out current time, h_abs [B] in/out next step size (<= 0: select_initial_step),
+ *   t_eval [n_eval] ascending output times (dense output), Y_eval [n_eval, B, 2n],
+ *   status [B]: 0 running/finished at t_bound, -1 step size too small, 1 attempt budget hit
+ *   counters [B,3]: nfev, accepted, rejected.  max_attempts bounds the work of one launch. */
+int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t,
+             double* h_abs, double t_bound, double rtol, double atol, const double* t_eval,
+             int32_t n_eval, double* Y_eval, int32_t* status, int64_t* counters,
+             int32_t max_attempts, void* stream);
+
+/* Dense BC-reduced matrices for one parameter set (host convenience for LQR synthesis;
+ * replaces get_mass_matrix / get_stiffness_matrix, euler_bernoulli_beam.py:357-361,422-511).
+ * params_host [N,7]; M_out, K_out host [n,n] row-major (K_out may be NULL). */
+int crb_dense_matrices(const crb_plan_t* plan, const double* params_host,
+                       const uint8_t* elem_type_host, const uint8_t* bc_host,
+                       double* M_out, double* K_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRB_H_ */

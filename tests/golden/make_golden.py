@@ -1,0 +1,343 @@
+"""Generate golden vectors by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py [--only rhs,cfg1,...]
+
+Imports ``continuum_robot`` from /root/reference/src, builds beams through the reference's own
+CSV path (examples/example_utilities.py:37-73 style), evaluates ``get_dynamic_system()`` and
+integrates with (a) the classical RK4 tableau around that RHS and (b) SciPy's
+``solve_ivp(method="RK45")``.  Outputs small ``.npz`` fixtures next to this file; parameters are
+stored as PARSED by the reference (``beam.params``; pandas' CSV float parsing is not round-trip
+exact) so every consumer sees the numbers the reference actually used.
+The GPU box has no /root/reference: nothing under tests/ reads it at run time.
+"""
+
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import os
+import sys
+import tempfile
+from multiprocessing import Pool
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/src")
+
+from continuum_robot_b200 import ensembles as ens  # noqa: E402
+
+COLS = "length,elastic_modulus,moment_inertia,density,cross_area,type,boundary_condition,wetted_area,drag_coef"
+
+
+def write_csv(length, E, I, rho, A, types, bcs, wet, cd):
+    f = tempfile.NamedTemporaryFile(mode="w", delete=False, suffix=".csv")
+    f.write(COLS + "\n")
+    for row in zip(length, E, I, rho, A, types, bcs, wet, cd):
+        f.write(",".join(str(x) for x in row) + "\n")
+    f.close()
+    return f.name
+
+
+def cantilever_csv(N, E_per_elem, type_name, bc_list=None, scale=None):
+    m = ens.material()
+    bcs = bc_list or (["FIXED"] + ["NONE"] * (N - 1))
+    types = type_name if isinstance(type_name, (list, tuple)) else [type_name] * N
+    sc = np.ones((N, 5)) if scale is None else scale
+    return write_csv(
+        m["length"] * sc[:, 0], np.asarray(E_per_elem, dtype=float), m["I"] * sc[:, 1],
+        m["rho"] * sc[:, 2], m["A"] * sc[:, 3], types, bcs,
+        m["wetted_area"] * sc[:, 4], [m["drag_coef"]] * N,
+    )
+
+
+def make_beam(csv, fluid_density=0.0, gravity=False, gravity_vector=None):
+    from continuum_robot.models.dynamic_beam_model import DynamicEulerBernoulliBeam
+    from continuum_robot.models.force_params import ForceParams
+
+    kw = {}
+    if gravity_vector is not None:
+        kw["gravity_vector"] = gravity_vector
+    fp = ForceParams(
+        fluid_density=fluid_density, enable_fluid_effects=fluid_density > 0,
+        enable_gravity_effects=gravity, **kw,
+    )
+    beam = DynamicEulerBernoulliBeam(csv, force_params=fp)
+    beam.create_system_func()
+    beam.create_input_func()
+    return beam
+
+
+def parsed(beam):
+    p = beam.params
+    out = {
+        k: p[k].to_numpy(dtype=float)
+        for k in ("length", "elastic_modulus", "moment_inertia", "density", "cross_area",
+                  "wetted_area", "drag_coef")
+    }
+    out["elem_type"] = np.array([0 if t.lower() == "linear" else 1 for t in p["type"]])
+    out["bc"] = np.array([{"NONE": 0, "FIXED": 1, "PINNED": 2}[b] for b in p["boundary_condition"]])
+    return out
+
+
+def rk4(fun, x0, t0, h, nsteps, save_every):
+    x = x0.copy()
+    out = []
+    for k in range(nsteps):
+        t = t0 + k * h
+        k1 = fun(t, x)
+        k2 = fun(t + 0.5 * h, x + (0.5 * h) * k1)
+        k3 = fun(t + 0.5 * h, x + (0.5 * h) * k2)
+        k4 = fun(t + h, x + h * k3)
+        x = x + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+        if (k + 1) % save_every == 0:
+            out.append(x.copy())
+    return np.array(out)
+
+
+def tip_impulse(n, amp, duration):
+    def u(t):
+        v = np.zeros(n)
+        if t < duration:
+            v[-2] = amp
+        return v
+
+    return u
+
+
+# ------------------------------------------------------------------------------------------
+def gen_rhs():
+    """RHS known-answer vectors on the reference's own test fixtures + BC edge cases."""
+    rng = np.random.default_rng(7)
+    cases = {}
+    m = ens.material()
+
+    def add(name, csv, **fk):
+        beam = make_beam(csv, **fk)
+        n = beam.beam_model.M.shape[0]
+        X = np.concatenate([1e-3 * rng.standard_normal((6, n)), 1e-1 * rng.standard_normal((6, n))], axis=1)
+        X[0] = 0.0
+        U = rng.standard_normal((6, n))
+        U[1] = 0.0
+        f = beam.get_dynamic_system()
+        Y = np.array([f(0.3, X[i], U[i]) for i in range(6)])
+        k = np.array([beam.beam_model.get_stiffness_function()(X[i, :n]) for i in range(6)])
+        d = {f"{name}/{a}": b for a, b in parsed(beam).items()}
+        d[f"{name}/X"] = X
+        d[f"{name}/U"] = U
+        d[f"{name}/Y"] = Y
+        d[f"{name}/k"] = k
+        d[f"{name}/M"] = beam.beam_model.get_mass_matrix()
+        d[f"{name}/fluid_density"] = np.array(fk.get("fluid_density", 0.0))
+        d[f"{name}/gravity"] = np.array(bool(fk.get("gravity", False)))
+        d[f"{name}/gravity_vector"] = np.array(fk.get("gravity_vector", [0.0, -9.81, 0.0]))
+        try:
+            d[f"{name}/K"] = beam.beam_model.get_stiffness_matrix()
+        except ValueError:
+            pass
+        cases.update(d)
+        os.unlink(csv)
+
+    E4 = [m["E"]] * 4
+    add("lin4", cantilever_csv(4, E4, "linear"))
+    add("lin4_grav_drag", cantilever_csv(4, E4, "linear"), fluid_density=1000.0, gravity=True)
+    add("nl4", cantilever_csv(4, E4, "nonlinear"))
+    add("nl4_grav_drag", cantilever_csv(4, E4, "nonlinear"), fluid_density=1000.0, gravity=True)
+    # mixed 5-element beam of tests/test_advanced_composition.py:13-20 (types only; Nitinol numbers)
+    add("mixed5", cantilever_csv(5, [m["E"]] * 5, ["linear", "linear", "nonlinear", "nonlinear", "linear"]),
+        fluid_density=800.0, gravity=True, gravity_vector=[1.5, -9.81, 0.0])
+    # non-uniform properties along the beam (distinct segment masses -> exposes quirk Q2)
+    sc = np.exp(0.3 * rng.standard_normal((7, 5)))
+    add("nonuni7", cantilever_csv(7, m["E"] * np.exp(0.2 * rng.standard_normal(7)),
+                                   ["nonlinear", "linear", "nonlinear", "linear", "linear", "nonlinear", "nonlinear"],
+                                   scale=sc), fluid_density=1000.0, gravity=True)
+    # boundary-condition edge cases: pinned root, interior pin, fixed interior node, free-free
+    add("pinned_root6", cantilever_csv(6, [m["E"]] * 6, "linear", ["PINNED"] + ["NONE"] * 5),
+        fluid_density=1000.0, gravity=True)
+    add("fixed_pinned6", cantilever_csv(6, [m["E"]] * 6, "nonlinear",
+                                        ["FIXED", "NONE", "NONE", "PINNED", "NONE", "NONE"]),
+        fluid_density=1000.0, gravity=True)
+    add("interior_fixed6", cantilever_csv(6, [m["E"]] * 6, "linear",
+                                          ["NONE", "NONE", "FIXED", "NONE", "NONE", "NONE"]), gravity=True)
+    add("free6", cantilever_csv(6, [m["E"]] * 6, "linear", ["NONE"] * 6), fluid_density=1000.0, gravity=True)
+    np.savez_compressed(os.path.join(HERE, "rhs_cases.npz"), **cases)
+    print("rhs_cases:", len(cases), "arrays")
+
+
+def _run_single(args):
+    (name, N, E, tname, fd, grav, amp, dur, h, nsteps, save_every, x0, rk45) = args
+    csv = cantilever_csv(N, E, tname)
+    beam = make_beam(csv, fluid_density=fd, gravity=grav)
+    os.unlink(csv)
+    n = beam.beam_model.M.shape[0]
+    u = tip_impulse(n, amp, dur) if amp else np.zeros(n)
+    f = beam.get_dynamic_system()
+    fun = lambda t, x: f(t, x, u)  # noqa: E731
+    out = {"params": parsed(beam)}
+    if nsteps:
+        out["Y"] = rk4(fun, x0, 0.0, h, nsteps, save_every)
+    if rk45:
+        from scipy.integrate import solve_ivp
+
+        sol = solve_ivp(fun, rk45["t_span"], x0, method="RK45", t_eval=rk45["t_eval"],
+                        rtol=rk45["rtol"], atol=rk45["atol"])
+        out["rk45_y"] = sol.y
+        out["rk45_t"] = sol.t
+        out["rk45_nfev"] = sol.nfev
+        out["rk45_status"] = sol.status
+        # full step sequence (no t_eval) for accepted-step bookkeeping
+        sol2 = solve_ivp(fun, rk45["t_span"], x0, method="RK45", rtol=rk45["rtol"], atol=rk45["atol"])
+        out["rk45_steps_t"] = sol2.t
+        out["rk45_final"] = sol2.y[:, -1]
+    return name, out
+
+
+def gen_cfg12():
+    e1, e2 = ens.config1(), ens.config2()
+    rk45 = {"t_span": (0.0, 0.02), "t_eval": np.linspace(0, 0.02, 21), "rtol": 1e-6, "atol": 1e-9}
+    tasks = [
+        ("cfg1", e1.n_elements, e1.E[0], "linear", 0.0, True, 0.1, 0.01, e1.h, 4000, 40, np.zeros(60), None),
+        ("cfg2", e2.n_elements, e2.E[0], "nonlinear", 1000.0, False, 0.1, 0.01, e2.h, 4000, 40, np.zeros(120), None),
+        ("cfg2_rk45", e2.n_elements, e2.E[0], "nonlinear", 1000.0, False, 0.1, 0.01, 0.0, 0, 0, np.zeros(120), rk45),
+        ("cfg1_rk45", e1.n_elements, e1.E[0], "linear", 0.0, True, 0.1, 0.01, 0.0, 0, 0, np.zeros(60),
+         {"t_span": (0.0, 0.02), "t_eval": np.linspace(0, 0.02, 11), "rtol": 1e-3, "atol": 1e-6}),
+    ]
+    with Pool(4) as p:
+        res = dict(p.map(_run_single, tasks))
+    d = {}
+    for name, out in res.items():
+        for k, v in out.items():
+            if k == "params":
+                for a, b in v.items():
+                    d[f"{name}/{a}"] = b
+            else:
+                d[f"{name}/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "cfg12.npz"), **d)
+    print("cfg12 done", {k: v.shape for k, v in d.items() if k.endswith("Y")})
+
+
+def gen_cfg3():
+    e = ens.config3()
+    idx = ens.sample_members(e.n_members, 64, 99)
+    tasks = [
+        (int(i), e.n_elements, e.E[i], "linear", 0.0, False, 0.0, 0.0, e.h, 1000, 250,
+         np.concatenate([e.q0[i], e.v0[i]]), None)
+        for i in idx
+    ]
+    with Pool(os.cpu_count()) as p:
+        res = dict(p.map(_run_single, tasks))
+    d = {
+        "idx": idx,
+        "E_parsed": np.array([res[int(i)]["params"]["elastic_modulus"] for i in idx]),
+        "E": e.E[idx], "q0": e.q0[idx], "v0": e.v0[idx],
+        "Y": np.array([res[int(i)]["Y"] for i in idx]),  # [64, 4, 192] at steps 250..1000
+        "h": np.array(e.h), "save_every": np.array(250),
+    }
+    p0 = res[int(idx[0])]["params"]
+    for k in ("length", "moment_inertia", "density", "cross_area"):
+        d[k] = p0[k]
+    np.savez_compressed(os.path.join(HERE, "cfg3_samples.npz"), **d)
+    print("cfg3 done", d["Y"].shape)
+
+
+def gen_cfg4():
+    e = ens.config4()
+    idx = ens.sample_members(e.n_members, 16, 99)
+    rk45 = {"t_span": (0.0, 0.02), "t_eval": np.linspace(0, 0.02, 21), "rtol": 1e-6, "atol": 1e-9}
+    tasks = [
+        (int(i), e.n_elements, e.E[i], "nonlinear", 1000.0, True, float(e.impulse_amp[i]), 0.01, 0.0, 0, 0,
+         np.zeros(2 * e.n_free), rk45)
+        for i in idx
+    ]
+    with Pool(os.cpu_count()) as p:
+        res = dict(p.map(_run_single, tasks))
+    d = {
+        "idx": idx, "amp": e.impulse_amp[idx], "E": e.E[idx],
+        "E_parsed": np.array([res[int(i)]["params"]["elastic_modulus"] for i in idx]),
+        "y": np.array([res[int(i)]["rk45_y"] for i in idx]),  # [16, 384, 21]
+        "t_eval": rk45["t_eval"],
+        "nfev": np.array([res[int(i)]["rk45_nfev"] for i in idx]),
+        "nsteps": np.array([len(res[int(i)]["rk45_steps_t"]) - 1 for i in idx]),
+        "final": np.array([res[int(i)]["rk45_final"] for i in idx]),
+        "rtol": np.array(1e-6), "atol": np.array(1e-9),
+    }
+    p0 = res[int(idx[0])]["params"]
+    for k in ("length", "moment_inertia", "density", "cross_area", "wetted_area", "drag_coef"):
+        d[k] = p0[k]
+    np.savez_compressed(os.path.join(HERE, "cfg4_samples.npz"), **d)
+    print("cfg4 done", d["y"].shape, d["nfev"])
+
+
+def _run_lqr(args):
+    i, amp, gain, nsteps, h, save_every = args
+    spec = importlib.util.spec_from_file_location(
+        "full_state_linear", "/root/reference/src/continuum_robot/control/full_state_linear.py"
+    )
+    # FullStateLinear imports ..models.abstractions relatively; load through the package path
+    sys.modules.setdefault("continuum_robot.control", type(sys)("continuum_robot.control"))
+    spec = importlib.util.spec_from_file_location(
+        "continuum_robot.control.full_state_linear",
+        "/root/reference/src/continuum_robot/control/full_state_linear.py",
+    )
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ctrl = mod.FullStateLinear(gain)
+    e = ens.config5(8)
+    csv = cantilever_csv(6, e.E[0], "linear")
+    beam = make_beam(csv, gravity=True)
+    os.unlink(csv)
+    n = beam.beam_model.M.shape[0]
+    imp = tip_impulse(n, amp, 0.01)
+    f = beam.get_dynamic_system()
+
+    def fun(t, x):
+        uc = ctrl.compute_input(x, np.zeros_like(x), t)  # examples/lqr_control.py:95-111
+        return f(t, x, imp(t) + uc)
+
+    return i, rk4(fun, np.zeros(2 * n), 0.0, h, nsteps, save_every)
+
+
+def gen_cfg5():
+    from scipy.linalg import solve_continuous_are
+
+    e = ens.config5()
+    idx = ens.sample_members(e.n_members, 32, 99)
+    csv = cantilever_csv(6, e.E[0], "linear")
+    beam = make_beam(csv, gravity=True)
+    os.unlink(csv)
+    Kb = beam.beam_model.get_stiffness_matrix()
+    Mb = beam.beam_model.get_mass_matrix()
+    n = Kb.shape[0]
+    # A, B as control/linear_quadratic_regulator.py:84-146; Q, R as examples/lqr_control.py:61-66
+    Minv = np.linalg.inv(Mb)
+    A = np.zeros((2 * n, 2 * n))
+    A[:n, n:] = np.eye(n)
+    A[n:, :n] = -Minv @ Kb
+    Bm = np.zeros((2 * n, n))
+    Bm[n:, :] = Minv
+    Q = np.eye(2 * n)
+    Q[:n, :n] *= 100
+    Q[n:, n:] *= 10
+    R = np.eye(n)
+    S = solve_continuous_are(A, Bm, Q, R)
+    gain = np.linalg.solve(R, Bm.T @ S)
+    tasks = [(int(i), float(e.impulse_amp[i]), gain, 2000, e.h, 500) for i in idx]
+    with Pool(os.cpu_count()) as p:
+        res = dict(p.map(_run_lqr, tasks))
+    d = {"idx": idx, "amp": e.impulse_amp[idx], "gain": gain, "K_beam": Kb, "M_beam": Mb,
+         "Y": np.array([res[int(i)] for i in idx]), "h": np.array(e.h), "save_every": np.array(500)}
+    for a, b in parsed(beam).items():
+        d[a] = b
+    np.savez_compressed(os.path.join(HERE, "cfg5_samples.npz"), **d)
+    print("cfg5 done", d["Y"].shape, "max Re(eig A_cl) =", np.max(np.linalg.eigvals(A - Bm @ gain).real))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="rhs,cfg12,cfg3,cfg4,cfg5")
+    a = ap.parse_args()
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    for name in a.only.split(","):
+        {"rhs": gen_rhs, "cfg12": gen_cfg12, "cfg3": gen_cfg3, "cfg4": gen_cfg4, "cfg5": gen_cfg5}[name]()

@@ -1,0 +1,99 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the reference's golden vectors / the oracle."""
+
+import numpy as np
+import pytest
+
+from helpers import block_err, case_names, load, make_gpu_beam, oracle_spec, params_array
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+RHS = load("rhs_cases.npz")
+
+
+@pytest.mark.parametrize("name", case_names(RHS))
+@pytest.mark.parametrize("slots", [0, 2, 1])
+def test_rhs_matches_reference(name, slots):
+    """get_dynamic_system()(t, x, u) on the reference's fixtures and BC edge cases (bit-level
+    quirks Q1-Q4 included); tolerance 1e-11 relative to the block inf-norm (FP64 noise ~1e-14)."""
+    p = name + "/"
+    par = params_array(RHS, p)
+    beam = make_gpu_beam(par, RHS[p + "elem_type"], RHS[p + "bc"], RHS[p + "fluid_density"], RHS[p + "gravity"],
+                         RHS[p + "gravity_vector"], max_slots_per_lane=slots)
+    X = torch.from_numpy(RHS[p + "X"]).cuda()
+    U = torch.from_numpy(RHS[p + "U"]).cuda()
+    Y = beam.get_dynamic_system()(0.3, X, U).cpu().numpy()
+    ref = RHS[p + "Y"]
+    n = beam.n_free
+    assert Y.shape == ref.shape
+    for i in range(len(ref)):
+        assert block_err(Y[i], ref[i], n) < 1e-11, (name, i)
+    # single-member (1-D) call mirrors the reference signature
+    y0 = beam.get_dynamic_system()(0.3, X[2], U[2]).cpu().numpy()
+    assert block_err(y0, ref[2], n) < 1e-11
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_rk4_configs_1_2(cfg):
+    """BASELINE configs 1 / 2: 4000 classical RK4 steps, every 40th state vs the reference (<= 1e-9)."""
+    from continuum_robot_b200 import TipImpulse, solve_ensemble
+
+    g = load("cfg12.npz")
+    p = cfg + "/"
+    par = params_array(g, p)
+    beam = make_gpu_beam(par, g[p + "elem_type"], g[p + "bc"], 1000.0 if cfg == "cfg2" else 0.0, cfg == "cfg1")
+    n = beam.n_free
+    X0 = torch.zeros(1, 2 * n, dtype=torch.float64, device="cuda")
+    res = solve_ensemble(beam, (0.0, 0.1), X0, method="RK4", h=2.5e-5, save_every=40,
+                         u=TipImpulse(torch.tensor([0.1], dtype=torch.float64, device="cuda")))
+    got = res.y[0].T.cpu().numpy()[1:]  # drop t0
+    ref = g[p + "Y"]
+    assert got.shape == ref.shape
+    worst = max(block_err(got[k], ref[k], n) for k in range(len(ref)))
+    assert worst < 1e-9, worst
+
+
+def test_rk4_config3_samples():
+    """BASELINE config 3: 64 sampled members, 1000 RK4 steps, checkpoints every 250 (<= 1e-9)."""
+    from continuum_robot_b200 import solve_ensemble
+
+    g = load("cfg3_samples.npz")
+    B, N = g["E_parsed"].shape
+    par = np.zeros((B, N, 7))
+    for k, c in enumerate(("length", "moment_inertia", "density", "cross_area")):
+        par[:, :, (0, 2, 3, 4)[k]] = g[c][None, :]
+    par[:, :, 1] = g["E_parsed"]
+    par[:, :, 5:] = 1.0
+    beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+    n = beam.n_free
+    X0 = torch.from_numpy(np.concatenate([g["q0"], g["v0"]], axis=1)).cuda()
+    res = solve_ensemble(beam, (0.0, 1000 * float(g["h"])), X0, method="RK4", h=float(g["h"]), save_every=250)
+    got = res.y.permute(0, 2, 1).cpu().numpy()[:, 1:]  # [B, 4, 2n]
+    ref = g["Y"]
+    worst = max(block_err(got[i, k], ref[i, k], n) for i in range(B) for k in range(4))
+    assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("cfg,rtol,atol", [("cfg2_rk45", 1e-6, 1e-9), ("cfg1_rk45", 1e-3, 1e-6)])
+def test_rk45_single(cfg, rtol, atol):
+    """Adaptive RK45 vs scipy.solve_ivp on the reference RHS: |dy| <= 10 (atol + rtol |y|) at t_eval,
+    and the same number of RHS evaluations within 1 %."""
+    from continuum_robot_b200 import TipImpulse, solve_ensemble
+
+    g = load("cfg12.npz")
+    p = cfg + "/"
+    par = params_array(g, p)
+    nl = cfg.startswith("cfg2")
+    beam = make_gpu_beam(par, g[p + "elem_type"], g[p + "bc"], 1000.0 if nl else 0.0, not nl)
+    n = beam.n_free
+    X0 = torch.zeros(1, 2 * n, dtype=torch.float64, device="cuda")
+    te = g[p + "rk45_t"]
+    res = solve_ensemble(beam, (0.0, 0.02), X0, method="RK45", t_eval=te, rtol=rtol, atol=atol,
+                         u=TipImpulse(torch.tensor([0.1], dtype=torch.float64, device="cuda")))
+    assert res.success
+    got = res.y[0].cpu().numpy()
+    ref = g[p + "rk45_y"]
+    assert got.shape == ref.shape
+    assert np.all(np.abs(got - ref) <= 10 * (atol + rtol * np.abs(ref)))
+    nfev_ref = int(g[p + "rk45_nfev"])
+    assert abs(int(res.nfev[0]) - nfev_ref) <= max(12, 0.01 * nfev_ref), (int(res.nfev[0]), nfev_ref)
