@@ -58,6 +58,10 @@ class CrbSystem(C.Structure):
         ("gain", C.c_void_p),
         ("ref", C.c_void_p),
         ("f_ext", C.c_void_p),
+        ("all_linear", C.c_int32),
+        ("uniform_mass", C.c_int32),
+        ("force_general", C.c_int32),
+        ("um", C.c_double * 4),
     ]
 
 

@@ -1,47 +1,22 @@
 // crb_api.cu -- kernels + C ABI of libcrb.so (see include/crb.h).  sm_100a only.
-#include <cuda_runtime.h>
-
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
+#include <algorithm>
 #include <vector>
 
-#include "crb.h"
+#include "crb_internal.h"
 #include "crb_assemble.cuh"
-#include "crb_device.cuh"
-#include "crb_rk45.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error handling (thread-local string; no other global mutable state)
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, ...) {
+int crb_fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
-#define CRB_E_ARG (-1)
-#define CRB_E_CUDA (-2)
-#define CRB_E_LIMIT (-3)
-
-static KPlan kplan_of(const crb_plan_t* p) {
-  KPlan k;
-  k.N = p->n_elements;
-  k.n_free = p->n_free;
-  k.n0 = p->n0;
-  k.p_act = p->p_act;
-  k.m = p->m;
-  k.g = p->g;
-  k.p = p->p;
-  k.levels = p->levels;
-  k.contiguous = p->contiguous;
-  k.has_mask = p->has_mask;
-  k.mfac_doubles = p->mfac_doubles;
-  return k;
-}
+#define fail crb_fail
 
 extern "C" int crb_version(void) { return CRB_VERSION; }
 extern "C" const char* crb_last_error(void) { return g_err; }
@@ -163,77 +138,6 @@ crb_rhs_kernel(KPlan P, crb_system_t S, SmemLayout SL, const double* __restrict_
   store_state<M>(L, dX, v, a);
 }
 
-// Classical RK4, nsteps fused: state, stage state and the running combination stay in registers.
-template <int M>
-__global__ void __launch_bounds__(CRB_THREADS)
-crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
-               int nsteps, double* __restrict__ Y, int save_every) {
-  extern __shared__ __align__(16) double smem[];
-  const double* mf = stage_mfac(S, P, smem);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mpw = 32 / P.g;
-  const int mloc = warp * mpw + lane / P.g;
-  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
-  LaneCtx<M> L;
-  load_lane_ctx<M>(L, P, S, member, lane % P.g, mf,
-                   SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
-  const RhsFlags F = make_flags(S, P);
-  double q[M][3], v[M][3];
-  load_state<M>(L, X, q, v);
-  const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
-  for (int k = 0; k < nsteps; ++k) {
-    const double t = t0 + k * h;
-    double qs[M][3], vs[M][3], aq[M][3], av[M][3], a[M][3];
-    // stage 1
-    beam_accel<M>(L, S, F, q, v, t, a);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        aq[j][d] = fma(h6, v[j][d], q[j][d]);
-        av[j][d] = fma(h6, a[j][d], v[j][d]);
-        qs[j][d] = fma(hh, v[j][d], q[j][d]);
-        vs[j][d] = fma(hh, a[j][d], v[j][d]);
-      }
-    // stage 2
-    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
-        av[j][d] = fma(h3, a[j][d], av[j][d]);
-        qs[j][d] = fma(hh, vs[j][d], q[j][d]);
-        vs[j][d] = fma(hh, a[j][d], v[j][d]);
-      }
-    // stage 3
-    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
-        av[j][d] = fma(h3, a[j][d], av[j][d]);
-        qs[j][d] = fma(h, vs[j][d], q[j][d]);
-        vs[j][d] = fma(h, a[j][d], v[j][d]);
-      }
-    // stage 4
-    beam_accel<M>(L, S, F, qs, vs, t + h, a);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        q[j][d] = fma(h6, vs[j][d], aq[j][d]);
-        v[j][d] = fma(h6, a[j][d], av[j][d]);
-      }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) {
-      const long long frame = (k + 1) / save_every - 1;
-      store_state<M>(L, Y + frame * (long long)S.n_members * 2 * L.n, q, v);
-    }
-  }
-  store_state<M>(L, X, q, v);
-}
-
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
@@ -251,34 +155,6 @@ static int check_system(const char* who, const crb_plan_t* plan, const crb_syste
     return fail(CRB_E_ARG, "%s: imp_dof %d outside [0,%d)", who, sys->imp_dof, plan->n_free);
   return 0;
 }
-
-static SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
-  SmemLayout SL;
-  SL.mfac_doubles = sys->mass_shared ? (int)plan->mfac_doubles : 0;
-  SL.scratch_doubles = (sys->gain || sys->grav_mode == 2) ? 2 * plan->n_free : 0;
-  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
-  *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
-  return SL;
-}
-
-template <typename K>
-static int set_smem(K kernel, size_t bytes, const char* who) {
-  if (bytes > 48 * 1024) {
-    if (bytes > 227 * 1024) return fail(CRB_E_LIMIT, "%s: needs %zu bytes of shared memory (> 227 KB)", who, bytes);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return fail(CRB_E_CUDA, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
-  }
-  return 0;
-}
-
-#define CRB_DISPATCH_M(mval, ...)                                  \
-  switch (mval) {                                                    \
-    case 1: { constexpr int M = 1; __VA_ARGS__; } break;                    \
-    case 2: { constexpr int M = 2; __VA_ARGS__; } break;                    \
-    case 3: { constexpr int M = 3; __VA_ARGS__; } break;                    \
-    case 4: { constexpr int M = 4; __VA_ARGS__; } break;                    \
-    default: return fail(CRB_E_LIMIT, "unsupported slots per lane %d", mval); \
-  }
 
 extern "C" int crb_rhs(const crb_plan_t* plan, const crb_system_t* sys, const double* X, double t, double* dX,
                        void* stream) {
@@ -306,16 +182,14 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
   if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_rk4: step h must be positive and finite");
   if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_rk4: save_every must be >= 1 when Y_out is given");
   if (nsteps == 0) return 0;
-  size_t bytes;
-  const SmemLayout SL = smem_layout(plan, sys, &bytes);
-  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
-  const int grid = (sys->n_members + mpb - 1) / mpb;
-  const KPlan P = kplan_of(plan);
-  CRB_DISPATCH_M(plan->m, {
-    if (int rc = set_smem(crb_rk4_kernel<M>, bytes, "crb_rk4")) return rc;
-    crb_rk4_kernel<M><<<grid, CRB_THREADS, bytes, (cudaStream_t)stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out,
-                                                                         save_every);
-  });
+  // fast path: all-linear, uniform element mass, contiguous plan without phantom slots, no
+  // forces and no input other than a tip impulse (BASELINE config 3 shape)
+  const bool fast = sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p &&
+                    !sys->drag && sys->grav_mode == 0 && !sys->u_const && !sys->gain && !sys->f_ext &&
+                    !sys->force_general;
+  int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream)
+                : crb_launch_rk4_general(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream);
+  if (rc) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -332,21 +206,9 @@ extern "C" int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double*
   if (n_eval < 0 || (n_eval > 0 && (!t_eval || !Y_eval))) return fail(CRB_E_ARG, "crb_rk45: bad t_eval / Y_eval");
   if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(CRB_E_ARG, "crb_rk45: rtol must be > 0 and atol >= 0");
   if (max_attempts < 1) return fail(CRB_E_ARG, "crb_rk45: max_attempts must be >= 1");
-  size_t bytes;
-  const SmemLayout SL = smem_layout(plan, sys, &bytes);
-  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
-  const int grid = (sys->n_members + mpb - 1) / mpb;
-  const KPlan P = kplan_of(plan);
-  Rk45Args A;
-  A.X = X; A.t = t; A.h_abs = h_abs; A.t_bound = t_bound; A.rtol = rtol; A.atol = atol;
-  A.t_eval = t_eval; A.n_eval = n_eval; A.Y_eval = Y_eval; A.status = status; A.counters = reinterpret_cast<long long*>(counters);
-  A.max_attempts = max_attempts;
-  const DpTab T = make_dp_tab();
-  CRB_DISPATCH_M(plan->m, {
-    const size_t total = bytes + sizeof(double) * 21 * M * CRB_THREADS;  // kv stage storage
-    if (int rc = set_smem(crb_rk45_kernel<M>, total, "crb_rk45")) return rc;
-    crb_rk45_kernel<M><<<grid, CRB_THREADS, total, (cudaStream_t)stream>>>(P, *sys, SL, A, T);
-  });
+  if (int rc = crb_launch_rk45(plan, sys, X, t, h_abs, t_bound, rtol, atol, t_eval, n_eval, Y_eval, status,
+                               reinterpret_cast<long long*>(counters), max_attempts, (cudaStream_t)stream))
+    return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk45: launch failed: %s", cudaGetErrorString(e));
   return 0;

@@ -1,0 +1,70 @@
+// crb_internal.h -- host-side helpers shared by the translation units of libcrb.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "crb.h"
+#include "crb_device.cuh"
+
+#define CRB_E_ARG (-1)
+#define CRB_E_CUDA (-2)
+#define CRB_E_LIMIT (-3)
+
+int crb_fail(int code, const char* fmt, ...);  // sets the thread-local error text, returns code
+
+inline KPlan kplan_of(const crb_plan_t* p) {
+  KPlan k;
+  k.N = p->n_elements;
+  k.n_free = p->n_free;
+  k.n0 = p->n0;
+  k.p_act = p->p_act;
+  k.m = p->m;
+  k.g = p->g;
+  k.p = p->p;
+  k.levels = p->levels;
+  k.contiguous = p->contiguous;
+  k.has_mask = p->has_mask;
+  k.mfac_doubles = p->mfac_doubles;
+  return k;
+}
+
+inline SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
+  SmemLayout SL;
+  SL.mfac_doubles = sys->mass_shared ? (int)plan->mfac_doubles : 0;
+  SL.scratch_doubles = (sys->gain || sys->grav_mode == 2) ? 2 * plan->n_free : 0;
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
+  return SL;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* who) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 227 * 1024) return crb_fail(CRB_E_LIMIT, "%s: needs %zu bytes of shared memory (> 227 KB)", who, bytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+#define CRB_DISPATCH_M(mval, ...)                                    \
+  switch (mval) {                                                    \
+    case 1: { constexpr int M = 1; __VA_ARGS__; } break;             \
+    case 2: { constexpr int M = 2; __VA_ARGS__; } break;             \
+    case 3: { constexpr int M = 3; __VA_ARGS__; } break;             \
+    case 4: { constexpr int M = 4; __VA_ARGS__; } break;             \
+    default: return crb_fail(CRB_E_LIMIT, "unsupported slots per lane %d", mval); \
+  }
+
+// launchers implemented in their own translation units (parallel nvcc builds)
+int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
+                           int nsteps, double* Y_out, int save_every, cudaStream_t stream);
+int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
+                        int nsteps, double* Y_out, int save_every, cudaStream_t stream);
+int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t, double* h_abs,
+                    double t_bound, double rtol, double atol, const double* t_eval, int n_eval, double* Y_eval,
+                    int* status, long long* counters, int max_attempts, cudaStream_t stream);

@@ -1,0 +1,88 @@
+// crb_rk4.cu -- general fused RK4 kernel (any element mix, forces, inputs, boundary conditions).
+#include "crb_internal.h"
+
+// Classical RK4, nsteps fused: state, stage state and the running combination stay in registers.
+template <int M>
+__global__ void __launch_bounds__(CRB_THREADS)
+crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
+               int nsteps, double* __restrict__ Y, int save_every) {
+  extern __shared__ __align__(16) double smem[];
+  const double* mf = stage_mfac(S, P, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mpw = 32 / P.g;
+  const int mloc = warp * mpw + lane / P.g;
+  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  LaneCtx<M> L;
+  load_lane_ctx<M>(L, P, S, member, lane % P.g, mf,
+                   SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  const RhsFlags F = make_flags(S, P);
+  double q[M][3], v[M][3];
+  load_state<M>(L, X, q, v);
+  const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
+  for (int k = 0; k < nsteps; ++k) {
+    const double t = t0 + k * h;
+    double qs[M][3], vs[M][3], aq[M][3], av[M][3], a[M][3];
+    // stage 1
+    beam_accel<M>(L, S, F, q, v, t, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        aq[j][d] = fma(h6, v[j][d], q[j][d]);
+        av[j][d] = fma(h6, a[j][d], v[j][d]);
+        qs[j][d] = fma(hh, v[j][d], q[j][d]);
+        vs[j][d] = fma(hh, a[j][d], v[j][d]);
+      }
+    // stage 2
+    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
+        av[j][d] = fma(h3, a[j][d], av[j][d]);
+        qs[j][d] = fma(hh, vs[j][d], q[j][d]);
+        vs[j][d] = fma(hh, a[j][d], v[j][d]);
+      }
+    // stage 3
+    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
+        av[j][d] = fma(h3, a[j][d], av[j][d]);
+        qs[j][d] = fma(h, vs[j][d], q[j][d]);
+        vs[j][d] = fma(h, a[j][d], v[j][d]);
+      }
+    // stage 4
+    beam_accel<M>(L, S, F, qs, vs, t + h, a);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        q[j][d] = fma(h6, vs[j][d], aq[j][d]);
+        v[j][d] = fma(h6, a[j][d], av[j][d]);
+      }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) {
+      const long long frame = (k + 1) / save_every - 1;
+      store_state<M>(L, Y + frame * (long long)S.n_members * 2 * L.n, q, v);
+    }
+  }
+  store_state<M>(L, X, q, v);
+}
+
+
+int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
+                           int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
+  size_t bytes;
+  const SmemLayout SL = smem_layout(plan, sys, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  CRB_DISPATCH_M(plan->m, {
+    if (int rc = set_smem(crb_rk4_kernel<M>, bytes, "crb_rk4")) return rc;
+    crb_rk4_kernel<M><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every);
+  });
+  return 0;
+}

@@ -1,0 +1,24 @@
+// crb_rk45.cu -- launcher of the adaptive Dormand-Prince kernel.
+#include "crb_internal.h"
+#include "crb_rk45.cuh"
+
+int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t, double* h_abs,
+                    double t_bound, double rtol, double atol, const double* t_eval, int n_eval, double* Y_eval,
+                    int* status, long long* counters, int max_attempts, cudaStream_t stream) {
+  size_t bytes;
+  const SmemLayout SL = smem_layout(plan, sys, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  Rk45Args A;
+  A.X = X; A.t = t; A.h_abs = h_abs; A.t_bound = t_bound; A.rtol = rtol; A.atol = atol;
+  A.t_eval = t_eval; A.n_eval = n_eval; A.Y_eval = Y_eval; A.status = status; A.counters = counters;
+  A.max_attempts = max_attempts;
+  const DpTab T = make_dp_tab();
+  CRB_DISPATCH_M(plan->m, {
+    const size_t total = bytes + sizeof(double) * 21 * M * CRB_THREADS;  // kv stage storage
+    if (int rc = set_smem(crb_rk45_kernel<M>, total, "crb_rk45")) return rc;
+    crb_rk45_kernel<M><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);
+  });
+  return 0;
+}

@@ -344,6 +344,13 @@ class BatchedDynamicEulerBernoulliBeam:
         def shared(cols):
             return Bp == 1 or bool(np.all(par[:, :, cols] == par[0:1, :, cols]))
 
+        # dispatch hints for the fast kernels: all-linear beam, one (rho A L, L) for every element
+        self._all_linear = bool(np.all(self._etype == 0))
+        L0, rho0, A0 = par[0, 0, 0], par[0, 0, 3], par[0, 0, 4]
+        self._uniform_mass = bool(np.all(par[:, :, 0] == L0) and np.all(par[:, :, 3] == rho0) and np.all(par[:, :, 4] == A0))
+        mu = rho0 * A0 * L0 / 420
+        self._um = (54 * mu, 13 * L0 * mu, 3 * L0 * L0 * mu, 70 * mu)
+        self.force_general_kernels = False
         self._mass_shared = shared([0, 3, 4])
         self._stiff_shared = shared([0, 1, 2, 4])
         self._force_shared = shared([0, 3, 4, 5, 6])
@@ -415,6 +422,11 @@ class BatchedDynamicEulerBernoulliBeam:
         s.kcoef = self._d_kcoef.data_ptr()
         s.elem_type = self._d_etype.data_ptr()
         s.red_index = self._d_red.data_ptr()
+        s.all_linear = int(self._all_linear)
+        s.uniform_mass = int(self._uniform_mass)
+        s.force_general = int(self.force_general_kernels)
+        for k in range(4):
+            s.um[k] = float(self._um[k])
         if drag is not None:
             if drag.fluid_density != self.force_params.fluid_density:
                 raise ValueError("FluidDragForce.fluid_density differs from the assembled ForceParams.fluid_density")

@@ -100,6 +100,11 @@ typedef struct crb_system_t {
   const double* ref;        /* [2n] shared reference, NULL = 0 */
   /* additive external generalized force (user torch callables evaluated between launches) */
   const double* f_ext;      /* [B, n] or NULL */
+  /* dispatch hints filled by the host layer from the parameter table */
+  int32_t all_linear;       /* 1: every element is CRB_ELEM_LINEAR */
+  int32_t uniform_mass;     /* 1: rho*A*L and L identical for every element of every member */
+  int32_t force_general;    /* 1: always use the general kernels (testing / comparison) */
+  double um[4];             /* uniform-mass coupling block: 54 mu, 13 L mu, 3 L^2 mu, 70 mu, mu = rho A L / 420 */
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */

@@ -97,3 +97,47 @@ def test_rk45_single(cfg, rtol, atol):
     assert np.all(np.abs(got - ref) <= 10 * (atol + rtol * np.abs(ref)))
     nfev_ref = int(g[p + "rk45_nfev"])
     assert abs(int(res.nfev[0]) - nfev_ref) <= max(12, 0.01 * nfev_ref), (int(res.nfev[0]), nfev_ref)
+
+
+@pytest.mark.parametrize("N,B", [(32, 37), (6, 5), (64, 9), (16, 33)])
+def test_rk4_fast_kernel_matches_general_and_oracle(N, B):
+    """The linear / uniform-mass fast kernel (Nystrom form, recomputed spikes) against the general
+    kernel (<= 1e-11, both are the same RK4 up to rounding) and against the NumPy oracle (<= 1e-9);
+    ragged member counts exercise the inactive-lane paths."""
+    from continuum_robot_b200 import TipImpulse
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    e = ens.config3(B, N, seed=7)
+    m = ens.material()
+    par = np.zeros((B, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E
+    par[:, :, 5:] = 1.0
+    beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+    n = beam.n_free
+    x0 = np.concatenate([e.q0, e.v0], axis=1)
+    amp = torch.linspace(0.05, 0.5, B, dtype=torch.float64, device="cuda")
+    imp = TipImpulse(amp, duration=30 * e.h)
+    steps = 60
+    Xf = torch.from_numpy(x0).cuda()
+    rk4_steps(beam, Xf, 0.0, e.h, steps, u=imp)
+    beam.force_general_kernels = True
+    Xg = torch.from_numpy(x0).cuda()
+    rk4_steps(beam, Xg, 0.0, e.h, steps, u=imp)
+    f, g = Xf.cpu().numpy(), Xg.cpu().numpy()
+    assert max(block_err(f[i], g[i], n) for i in range(B)) < 1e-11
+    for i in (0, B - 1):
+        spec = bo.BeamSpec.uniform(N)
+        spec.elastic_modulus = e.E[i].copy()
+        b = bo.BeamOracle(spec)
+
+        def u(t, a=float(amp[i])):
+            v = np.zeros(n)
+            if t < 30 * e.h:
+                v[-2] = a
+            return v
+
+        ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, u), x0[i], 0.0, e.h, steps)
+        assert block_err(f[i], ref, n) < 1e-9
