@@ -187,8 +187,9 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
   const bool fast = sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p &&
                     !sys->drag && sys->grav_mode == 0 && !sys->u_const && !sys->gain && !sys->f_ext &&
                     !sys->force_general;
-  int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream)
-                : crb_launch_rk4_general(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream);
+  int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream) : 1;
+  if (rc == 1)  // not eligible, or shape not instantiated in the fast family
+    rc = crb_launch_rk4_general(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream);
   if (rc) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));

@@ -2,18 +2,31 @@
 #include "crb_internal.h"
 #include "crb_rk4_fast.cuh"
 
-int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
-                        int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
+template <int M, int LV>
+static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
+                  double* Y_out, int save_every, cudaStream_t stream) {
   size_t bytes;
-  const SmemLayout SL = smem_layout(plan, sys, &bytes);
-  (void)SL;
-  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  smem_layout(plan, sys, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 >> LV);
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
-  UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
-  CRB_DISPATCH_M(plan->m, {
-    if (int rc = set_smem(crb_rk4_fast_kernel<M>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
-  });
+  const UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
+  if (sys->imp_amp) {
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
+    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
+  } else {
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
+    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
+  }
   return 0;
+}
+
+int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
+                        int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
+#define CRB_CASE(MM, LL) \
+  if (plan->m == MM && plan->levels == LL) return launch<MM, LL>(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
+  CRB_CASE(4, 3) CRB_CASE(4, 4) CRB_CASE(4, 5) CRB_CASE(4, 2)
+  CRB_CASE(3, 1) CRB_CASE(3, 2) CRB_CASE(3, 3) CRB_CASE(2, 0) CRB_CASE(2, 1) CRB_CASE(4, 0) CRB_CASE(3, 0) CRB_CASE(1, 0) CRB_CASE(4, 1)
+#undef CRB_CASE
+  return 1;  // shape not instantiated: the caller falls back to the general kernel
 }

@@ -27,7 +27,7 @@ struct UniformMass {
 
 template <int M>
 struct FastCtx {
-  int G, g, levels;
+  int g;
   int member;
   bool active;
   int n;
@@ -39,9 +39,9 @@ struct FastCtx {
   int imp_local;
 };
 
-template <int M>
+template <int M, int LV>
 __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& C) {
-  const int G = C.G;
+  constexpr int G = 1 << LV;
   const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
   // Sinv of the lane's slots stays in registers for the four sweeps
   double s00[M], s01[M], s11[M], su[M];
@@ -66,7 +66,8 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
   }
   double xi0 = 0.0, xi1 = 0.0, xi2 = 0.0;  // xhat of the left neighbour's last slot
   if (G > 1) {
-    for (int l = 0; l < C.levels; ++l) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
       const int d = 1 << l;
       const double t0 = shfl_up_d(y0, d, G), t1 = shfl_up_d(y1, d, G), t2 = shfl_up_d(y2, d, G);
       const double2 c0 = C.mc.lds(l, 0), c1 = C.mc.lds(l, 1), cu = C.mc.lds(l, 2);
@@ -107,7 +108,8 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
   }
   double n0 = 0.0, n1 = 0.0, n2 = 0.0;  // x of the right neighbour's first slot
   if (G > 1) {
-    for (int l = 0; l < C.levels; ++l) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
       const int d = 1 << l;
       const double t0 = shfl_down_d(r0, d, G), t1 = shfl_down_d(r1, d, G), t2 = shfl_down_d(r2, d, G);
       const double2 c0 = C.mc.lds(l, 3), c1 = C.mc.lds(l, 4), cu = C.mc.lds(l, 5);
@@ -135,9 +137,9 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
 }
 
 // a <- M^-1 (-K w + impulse(t));  `w` holds the stage positions on entry, accelerations on exit.
-template <int M>
+template <int M, int LV, bool IMP>
 __device__ __forceinline__ void fast_accel(const FastCtx<M>& C, double (&w)[M][3], double t) {
-  const int G = C.G;
+  constexpr int G = 1 << LV;
   double qh[3], send[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -158,40 +160,38 @@ __device__ __forceinline__ void fast_accel(const FastCtx<M>& C, double (&w)[M][3
     if (C.g == G - 1) r = 0.0;
     b[M - 1][d] += r;
   }
-  if (C.imp_local >= 0 && t < C.imp_dur) {
+  if (IMP && C.imp_local >= 0 && t < C.imp_dur) {
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d)
         if (C.imp_local == 3 * j + d) b[j][d] += C.imp_amp;
   }
-  fast_solve<M>(b, C);
+  fast_solve<M, LV>(b, C);
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int d = 0; d < 3; ++d) w[j][d] = b[j][d];
 }
 
-template <int M>
+template <int M, int LV, bool IMP>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double t0, double h,
                     int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
   const double* mf = stage_mfac(S, P, smem);
+  constexpr int G = 1 << LV, mpw = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = P.g, mpw = 32 / G;
   const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + warp * mpw + lane / G;
   FastCtx<M> C;
-  C.G = G;
   C.g = lane % G;
-  C.levels = P.levels;
   C.n = P.n_free;
   C.active = member < S.n_members;
   C.member = C.active ? member : S.n_members - 1;
   C.um = um;
   const int s0 = C.g * M;
   {
-    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * P.p * 4);
+    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
@@ -200,13 +200,13 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
     }
   }
   C.mc.slot = mf;
-  C.mc.scan = mf + 2 * CRB_SLOT_PAIRS * P.p;
+  C.mc.scan = mf + 2 * CRB_SLOT_PAIRS * (M * G);
   C.mc.G = G;
   C.mc.g = C.g;
-  C.imp_amp = S.imp_amp ? S.imp_amp[C.member] : 0.0;
+  C.imp_amp = (IMP && S.imp_amp) ? S.imp_amp[C.member] : 0.0;
   C.imp_dur = S.imp_duration;
   C.imp_local = -1;
-  if (S.imp_amp) {
+  if (IMP && S.imp_amp) {
     const int rel = S.imp_dof - 3 * s0;  // contiguous plan: reduced index = 3 slot + dof
     if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
   }
@@ -225,55 +225,46 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
   const double hh = 0.5 * h, h6 = h / 6.0, hq = 0.25 * h * h, hs = 0.5 * h * h, hx = h * h / 6.0;
   for (int k = 0; k < nsteps; ++k) {
     const double t = t0 + k * h;
-    // stage 1 at q
+    // Nystrom form of the classical tableau; the stage loop is kept rolled so the step body
+    // (one copy of the RHS) stays inside the instruction cache.
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        w[j][d] = Q0[j][d];
-        Q0[j][d] = fma(hh, v[j][d], Q0[j][d]);
+        w[j][d] = Q0[j][d];                     // stage 1 input: q
+        Q0[j][d] = fma(hh, v[j][d], Q0[j][d]);  // Q0 = q + h/2 v
+        Sa[j][d] = 0.0;
+        Aa[j][d] = 0.0;
       }
-    fast_accel<M>(C, w, t);
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+      const double ts = t + (st == 0 ? 0.0 : (st == 3 ? h : hh));
+      fast_accel<M, LV, IMP>(C, w, ts);
+      // weights: S = a1+a2+a3, A = a1+2a2+2a3+a4; next input:
+      //   st0 -> Q0 ; st1 -> Q0 + h^2/4 a1 ; st2 -> Q0 + h/2 v + h^2/2 a2
+      const double wa = (st == 1 || st == 2) ? 2.0 : 1.0;
+      const double ws = st == 3 ? 0.0 : 1.0;
+      const double ca = st == 1 ? hq : (st == 2 ? hs : 0.0);  // coefficient of the recovered stage accel
+      const double cv = st == 2 ? hh : 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double a = w[j][d];
+          // acceleration entering the next stage input: a1 (= S before this update) after
+          // stage 2, a2 (= A - S before this update) after stage 3
+          const double prev = st == 1 ? Sa[j][d] : (Aa[j][d] - Sa[j][d]);
+          Sa[j][d] = fma(ws, a, Sa[j][d]);
+          Aa[j][d] = fma(wa, a, Aa[j][d]);
+          w[j][d] = fma(ca, prev, fma(cv, v[j][d], Q0[j][d]));
+        }
+    }
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        Sa[j][d] = w[j][d];
-        Aa[j][d] = w[j][d];
-        w[j][d] = Q0[j][d];
-      }
-    // stage 2 at q + h/2 v
-    fast_accel<M>(C, w, t + hh);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double a2 = w[j][d], a1 = Sa[j][d];
-        Sa[j][d] = a1 + a2;
-        Aa[j][d] = fma(2.0, a2, Aa[j][d]);
-        w[j][d] = fma(hq, a1, Q0[j][d]);
-      }
-    // stage 3 at q + h/2 v + h^2/4 a1
-    fast_accel<M>(C, w, t + hh);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double a3 = w[j][d];
-        const double a2 = Aa[j][d] - Sa[j][d];
-        Sa[j][d] += a3;
-        Aa[j][d] = fma(2.0, a3, Aa[j][d]);
-        w[j][d] = fma(hs, a2, fma(hh, v[j][d], Q0[j][d]));
-      }
-    // stage 4 at q + h v + h^2/2 a2
-    fast_accel<M>(C, w, t + h);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double A4 = Aa[j][d] + w[j][d];
         Q0[j][d] = fma(hx, Sa[j][d], fma(hh, v[j][d], Q0[j][d]));  // q+
-        v[j][d] = fma(h6, A4, v[j][d]);                            // v+
+        v[j][d] = fma(h6, Aa[j][d], v[j][d]);                      // v+
       }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
       double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
