@@ -14,7 +14,7 @@ CRB_MAX_SLOTS = 256
 CRB_VERSION = 100
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrb.so")
+LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
 
 
 class CrbPlan(C.Structure):

@@ -65,7 +65,8 @@ extern "C" int crb_plan(int32_t n_elements, const uint8_t* bc, int32_t max_slots
   out->n_free = r;
   out->contiguous = contiguous;
   out->has_mask = !contiguous;
-  out->mfac_doubles = 2ll * CRB_SLOT_PAIRS * out->p + 2ll * CRB_SCAN_PAIRS * (levels > 0 ? levels : 1) * g;
+  out->mfac_doubles = 2ll * CRB_SLOT_PAIRS * out->p + 2ll * CRB_SCAN_PAIRS * (levels > 0 ? levels : 1) * g +
+                      4ll * out->p + 10ll * (levels > 0 ? levels : 1) * g;  // + compact copy for the fast kernels
   out->kcoef_doubles = 4ll * out->p;
   return 0;
 }

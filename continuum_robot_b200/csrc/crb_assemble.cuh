@@ -301,4 +301,30 @@ crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n
       sc[sc_addr(l, 10, g, G)] = cbu;
     }
   }
+  // ---- compact copy for the uniform-mass fast kernels (crb_rk4_fast.cuh):
+  //   slot part  [pair 0..1][j][g]:  (s00, s01), (s11, sinv_u)
+  //   scan part  [level][pair 0..4][g]: C fwd (2 pairs), C bwd (2 pairs), (cu_fwd, cu_bwd)
+  {
+    const int lv = P.levels > 0 ? P.levels : 1;
+    double* fs = sc + 2 * CRB_SCAN_PAIRS * lv * G;
+    double* fc = fs + 4 * Pn;
+    for (int s = 0; s < Pn; ++s) {
+      const int g = s / m, j = s - g * m;
+      const M2 Sinv = ld_m2(mf, 4, s, m, G);
+      fs[(((0 * m + j) * G + g) << 1) + 0] = Sinv.a;
+      fs[(((0 * m + j) * G + g) << 1) + 1] = Sinv.b;
+      fs[(((1 * m + j) * G + g) << 1) + 0] = Sinv.d;
+      fs[(((1 * m + j) * G + g) << 1) + 1] = mf[mf_addr(21, s, m, G)];
+    }
+    for (int l = 0; l < P.levels; ++l)
+      for (int g = 0; g < G; ++g) {
+        double* o = fc + ((long long)(l * 5) * G << 1);
+        for (int k = 0; k < 4; ++k) {
+          o[(((k >> 1) * G + g) << 1) + (k & 1)] = sc[sc_addr(l, k, g, G)];
+          o[(((2 + (k >> 1)) * G + g) << 1) + (k & 1)] = sc[sc_addr(l, 6 + k, g, G)];
+        }
+        o[((4 * G + g) << 1) + 0] = sc[sc_addr(l, 4, g, G)];
+        o[((4 * G + g) << 1) + 1] = sc[sc_addr(l, 10, g, G)];
+      }
+  }
 }

@@ -5,18 +5,18 @@
 template <int M, int LV>
 static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
                   double* Y_out, int save_every, cudaStream_t stream) {
-  size_t bytes;
-  smem_layout(plan, sys, &bytes);
-  const int mpb = CRB_WARPS_PER_BLOCK * (32 >> LV);
+  const size_t bytes = sizeof(double) * (4 * plan->p + 10 * (plan->levels > 0 ? plan->levels : 1) * plan->g);
+  if (!sys->mass_shared) return 1;  // the fast family stages ONE shared compact factor set
+  const int mpb = CRB_FAST_WARPS * (32 >> LV);
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
   if (sys->imp_amp) {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
+    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
   } else {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
+    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
   }
   return 0;
 }

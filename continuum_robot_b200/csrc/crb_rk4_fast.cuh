@@ -21,6 +21,14 @@
 #pragma once
 #include "crb_device.cuh"
 
+#ifndef CRB_FAST_WARPS
+#define CRB_FAST_WARPS 4      // warps per block of the fast kernel
+#endif
+#ifndef CRB_FAST_MINBLOCKS
+#define CRB_FAST_MINBLOCKS 2  // resident blocks per SM the register allocation is sized for
+#endif
+#define CRB_FAST_THREADS (32 * CRB_FAST_WARPS)
+
 struct UniformMass {
   double o11, o12, o22, ou;  // 54 mu, 13 L mu, 3 L^2 mu, 70 mu   (mu = rho A L / 420)
 };
@@ -32,12 +40,22 @@ struct FastCtx {
   bool active;
   int n;
   double4 kc[M];
-  MassConsts<M> mc;
+  const double* fslot;  // compact Sinv copy   [pair 0..1][j][g] double2 (shared memory)
+  const double* fscan;  // compact scan copy   [level][pair 0..4][g] double2
   UniformMass um;
   // impulse: amplitude (0 if none) and the (slot, dof) it acts on, as a flat local index or -1
   double imp_amp, imp_dur;
   int imp_local;
 };
+
+template <int M, int G>
+__device__ __forceinline__ double2 ld_fslot(const FastCtx<M>& C, int pair, int j) {
+  return *reinterpret_cast<const double2*>(C.fslot + (((pair * M + j) * G + C.g) << 1));
+}
+template <int M, int G>
+__device__ __forceinline__ double2 ld_fscan(const FastCtx<M>& C, int level, int pair) {
+  return *reinterpret_cast<const double2*>(C.fscan + (((level * 5 + pair) * G + C.g) << 1));
+}
 
 template <int M, int LV>
 __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& C) {
@@ -47,11 +65,11 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
   double s00[M], s01[M], s11[M], su[M];
 #pragma unroll
   for (int j = 0; j < M; ++j) {
-    const double2 a = C.mc.ld(2, j), c = C.mc.ld(3, j);
+    const double2 a = ld_fslot<M, G>(C, 0, j), c = ld_fslot<M, G>(C, 1, j);
     s00[j] = a.x;
     s01[j] = a.y;
-    s11[j] = c.y;
-    su[j] = C.mc.ld(10, j).y;
+    s11[j] = c.x;
+    su[j] = c.y;
   }
   // ---- forward A: y~ at the chunk's last slot, zero incoming ----
   double y0 = b[0][0], y1 = b[0][1], y2 = b[0][2];
@@ -65,12 +83,14 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
     y2 = fma(-o12, xw, fma(o22, xp, b[j][2]));
   }
   double xi0 = 0.0, xi1 = 0.0, xi2 = 0.0;  // xhat of the left neighbour's last slot
+  double cub[LV > 0 ? LV : 1];             // u-scan coefficients of the backward scan (loaded with the forward ones)
   if (G > 1) {
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
       const int d = 1 << l;
       const double t0 = shfl_up_d(y0, d, G), t1 = shfl_up_d(y1, d, G), t2 = shfl_up_d(y2, d, G);
-      const double2 c0 = C.mc.lds(l, 0), c1 = C.mc.lds(l, 1), cu = C.mc.lds(l, 2);
+      const double2 c0 = ld_fscan<M, G>(C, l, 0), c1 = ld_fscan<M, G>(C, l, 1), cu = ld_fscan<M, G>(C, l, 4);
+      cub[l] = cu.y;
       y0 = fma(cu.x, t0, y0);
       mv2(c0, c1, t1, t2, y1, y2);
     }
@@ -112,8 +132,8 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
     for (int l = 0; l < LV; ++l) {
       const int d = 1 << l;
       const double t0 = shfl_down_d(r0, d, G), t1 = shfl_down_d(r1, d, G), t2 = shfl_down_d(r2, d, G);
-      const double2 c0 = C.mc.lds(l, 3), c1 = C.mc.lds(l, 4), cu = C.mc.lds(l, 5);
-      r0 = fma(cu.x, t0, r0);
+      const double2 c0 = ld_fscan<M, G>(C, l, 2), c1 = ld_fscan<M, G>(C, l, 3);
+      r0 = fma(cub[l], t0, r0);
       mv2(c0, c1, t1, t2, r1, r2);
     }
     n0 = shfl_down_d(r0, 1, G);
@@ -136,29 +156,46 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
   }
 }
 
+// Linear element force as VALUES: f on node 1 = (fu, V, m1), on node 2 = (-fu, -V, m2)
+// (models/segments.py:32-62); c = (EA/L, 12EI/L^3, 6EI/L^2, 2EI/L).
+__device__ __forceinline__ void elem_linear_vals(const double4 c, const double (&qa)[3], const double (&qb)[3],
+                                                 double& fu, double& V, double& m1, double& m2) {
+  const double d = qa[1] - qb[1];
+  const double s = qa[2] + qb[2];
+  fu = c.x * (qa[0] - qb[0]);
+  V = fma(c.y, d, -c.z * s);
+  const double R = fma(c.w, s, -c.z * d);
+  m1 = fma(c.w, qa[2], R);
+  m2 = fma(c.w, qb[2], R);
+}
+
 // a <- M^-1 (-K w + impulse(t));  `w` holds the stage positions on entry, accelerations on exit.
 template <int M, int LV, bool IMP>
 __device__ __forceinline__ void fast_accel(const FastCtx<M>& C, double (&w)[M][3], double t) {
   constexpr int G = 1 << LV;
-  double qh[3], send[3] = {0.0, 0.0, 0.0};
+  double qh[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     qh[d] = shfl_up_d(w[M - 1][d], 1, G);
     if (C.g == 0) qh[d] = 0.0;
   }
+  // element j sits left of slot j; element M (left of the right neighbour's first slot) is
+  // evaluated by that neighbour and its node-1 force comes back by shuffle
+  double fu[M + 1], V[M + 1], m1[M + 1], m2[M];
+  elem_linear_vals(C.kc[0], qh, w[0], fu[0], V[0], m1[0], m2[0]);
+#pragma unroll
+  for (int j = 1; j < M; ++j) elem_linear_vals(C.kc[j], w[j - 1], w[j], fu[j], V[j], m1[j], m2[j]);
+  fu[M] = shfl_down_d(fu[0], 1, G);
+  V[M] = shfl_down_d(V[0], 1, G);
+  m1[M] = shfl_down_d(m1[0], 1, G);
+  if (C.g == G - 1) { fu[M] = 0.0; V[M] = 0.0; m1[M] = 0.0; }
   double b[M][3];
 #pragma unroll
-  for (int j = 0; j < M; ++j)
-#pragma unroll
-    for (int d = 0; d < 3; ++d) b[j][d] = 0.0;
-  elem_linear(C.kc[0], qh, w[0], send, b[0]);
-#pragma unroll
-  for (int j = 1; j < M; ++j) elem_linear(C.kc[j], w[j - 1], w[j], b[j - 1], b[j]);
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    double r = shfl_down_d(send[d], 1, G);
-    if (C.g == G - 1) r = 0.0;
-    b[M - 1][d] += r;
+  for (int j = 0; j < M; ++j) {
+    // b = -(f_node2(element j) + f_node1(element j+1))
+    b[j][0] = fu[j] - fu[j + 1];
+    b[j][1] = V[j] - V[j + 1];
+    b[j][2] = -(m2[j] + m1[j + 1]);
   }
   if (IMP && C.imp_local >= 0 && t < C.imp_dur) {
 #pragma unroll
@@ -175,20 +212,28 @@ __device__ __forceinline__ void fast_accel(const FastCtx<M>& C, double (&w)[M][3
 }
 
 template <int M, int LV, bool IMP>
-__global__ void __launch_bounds__(CRB_THREADS)
+__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double t0, double h,
                     int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  const double* mf = stage_mfac(S, P, smem);
-  constexpr int G = 1 << LV, mpw = 32 / G;
+  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
+  // stage the compact (Sinv + scan) copy of the shared mass factors: 4 P + 10 LV G doubles
+  constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
+  {
+    const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+    for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + warp * mpw + lane / G;
+  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + warp * mpw + lane / G;
   FastCtx<M> C;
   C.g = lane % G;
   C.n = P.n_free;
   C.active = member < S.n_members;
   C.member = C.active ? member : S.n_members - 1;
   C.um = um;
+  C.fslot = smem;
+  C.fscan = smem + 4 * M * G;
   const int s0 = C.g * M;
   {
     const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
@@ -199,10 +244,6 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
       C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
     }
   }
-  C.mc.slot = mf;
-  C.mc.scan = mf + 2 * CRB_SLOT_PAIRS * (M * G);
-  C.mc.G = G;
-  C.mc.g = C.g;
   C.imp_amp = (IMP && S.imp_amp) ? S.imp_amp[C.member] : 0.0;
   C.imp_dur = S.imp_duration;
   C.imp_local = -1;
@@ -219,60 +260,71 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      Q0[j][d] = xq[3 * j + d];  // holds q until the first stage is set up
+      w[j][d] = xq[3 * j + d];
       v[j][d] = xq[n + 3 * j + d];
+      Q0[j][d] = fma(0.5 * h, v[j][d], w[j][d]);
     }
   const double hh = 0.5 * h, h6 = h / 6.0, hq = 0.25 * h * h, hs = 0.5 * h * h, hx = h * h / 6.0;
   for (int k = 0; k < nsteps; ++k) {
     const double t = t0 + k * h;
-    // Nystrom form of the classical tableau; the stage loop is kept rolled so the step body
-    // (one copy of the RHS) stays inside the instruction cache.
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        w[j][d] = Q0[j][d];                     // stage 1 input: q
-        Q0[j][d] = fma(hh, v[j][d], Q0[j][d]);  // Q0 = q + h/2 v
-        Sa[j][d] = 0.0;
-        Aa[j][d] = 0.0;
-      }
+    // Nystrom form of the classical tableau.  Invariant at loop entry: w = q, Q0 = q + h/2 v.
+    // The stage loop stays rolled so that one copy of the RHS serves all four stages (I-cache).
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
       const double ts = t + (st == 0 ? 0.0 : (st == 3 ? h : hh));
       fast_accel<M, LV, IMP>(C, w, ts);
-      // weights: S = a1+a2+a3, A = a1+2a2+2a3+a4; next input:
-      //   st0 -> Q0 ; st1 -> Q0 + h^2/4 a1 ; st2 -> Q0 + h/2 v + h^2/2 a2
-      const double wa = (st == 1 || st == 2) ? 2.0 : 1.0;
-      const double ws = st == 3 ? 0.0 : 1.0;
-      const double ca = st == 1 ? hq : (st == 2 ? hs : 0.0);  // coefficient of the recovered stage accel
-      const double cv = st == 2 ? hh : 0.0;
+      if (st == 0) {  // a1: next input q + h/2 v
 #pragma unroll
-      for (int j = 0; j < M; ++j)
+        for (int j = 0; j < M; ++j)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const double a = w[j][d];
-          // acceleration entering the next stage input: a1 (= S before this update) after
-          // stage 2, a2 (= A - S before this update) after stage 3
-          const double prev = st == 1 ? Sa[j][d] : (Aa[j][d] - Sa[j][d]);
-          Sa[j][d] = fma(ws, a, Sa[j][d]);
-          Aa[j][d] = fma(wa, a, Aa[j][d]);
-          w[j][d] = fma(ca, prev, fma(cv, v[j][d], Q0[j][d]));
-        }
-    }
+          for (int d = 0; d < 3; ++d) {
+            Sa[j][d] = w[j][d];
+            Aa[j][d] = w[j][d];
+            w[j][d] = Q0[j][d];
+          }
+      } else if (st == 1) {  // a2: next input q + h/2 v + h^2/4 a1
 #pragma unroll
-    for (int j = 0; j < M; ++j)
+        for (int j = 0; j < M; ++j)
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        Q0[j][d] = fma(hx, Sa[j][d], fma(hh, v[j][d], Q0[j][d]));  // q+
-        v[j][d] = fma(h6, Aa[j][d], v[j][d]);                      // v+
+          for (int d = 0; d < 3; ++d) {
+            const double a2 = w[j][d], a1 = Sa[j][d];
+            Sa[j][d] = a1 + a2;
+            Aa[j][d] = fma(2.0, a2, a1);
+            w[j][d] = fma(hq, a1, Q0[j][d]);
+          }
+      } else if (st == 2) {  // a3: next input q + h v + h^2/2 a2  (a2 = A - S)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double a3 = w[j][d];
+            const double a2 = Aa[j][d] - Sa[j][d];
+            Sa[j][d] += a3;
+            Aa[j][d] = fma(2.0, a3, Aa[j][d]);
+            Q0[j][d] = fma(hh, v[j][d], Q0[j][d]);  // now q + h v
+            w[j][d] = fma(hs, a2, Q0[j][d]);
+          }
+      } else {  // a4: close the step, set up the next one
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double A4 = Aa[j][d] + w[j][d];
+            const double qn = fma(hx, Sa[j][d], Q0[j][d]);  // q+ = q + h v + h^2/6 (a1+a2+a3)
+            const double vn = fma(h6, A4, v[j][d]);         // v+ = v + h/6 (a1+2a2+2a3+a4)
+            w[j][d] = qn;
+            v[j][d] = vn;
+            Q0[j][d] = fma(hh, vn, qn);
+          }
       }
+    }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
       double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          yq[3 * j + d] = Q0[j][d];
+          yq[3 * j + d] = w[j][d];
           yq[n + 3 * j + d] = v[j][d];
         }
     }
@@ -282,7 +334,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        xq[3 * j + d] = Q0[j][d];
+        xq[3 * j + d] = w[j][d];
         xq[n + 3 * j + d] = v[j][d];
       }
   }
