@@ -22,10 +22,10 @@
 #include "crb_device.cuh"
 
 #ifndef CRB_FAST_WARPS
-#define CRB_FAST_WARPS 4      // warps per block of the fast kernel
+#define CRB_FAST_WARPS 2      // warps per block of the fast kernel
 #endif
 #ifndef CRB_FAST_MINBLOCKS
-#define CRB_FAST_MINBLOCKS 2  // resident blocks per SM the register allocation is sized for
+#define CRB_FAST_MINBLOCKS 4  // resident blocks per SM the register allocation is sized for
 #endif
 #define CRB_FAST_THREADS (32 * CRB_FAST_WARPS)
 

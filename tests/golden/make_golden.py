@@ -243,9 +243,12 @@ def gen_cfg3():
 
 
 def gen_cfg4():
+    # BASELINE config 4 asks for t in [0, 0.02]; the reference's own 64-element nonlinear beam is
+    # unstable (one-sided axial coupling, SURVEY Q1/P11: |v| reaches 3e4 at t = 6 ms and overflows
+    # soon after), so the golden horizon is the first 3 ms, where the reference is still finite.
     e = ens.config4()
     idx = ens.sample_members(e.n_members, 16, 99)
-    rk45 = {"t_span": (0.0, 0.02), "t_eval": np.linspace(0, 0.02, 21), "rtol": 1e-6, "atol": 1e-9}
+    rk45 = {"t_span": (0.0, 0.003), "t_eval": np.linspace(0, 0.003, 7), "rtol": 1e-6, "atol": 1e-9}
     tasks = [
         (int(i), e.n_elements, e.E[i], "nonlinear", 1000.0, True, float(e.impulse_amp[i]), 0.01, 0.0, 0, 0,
          np.zeros(2 * e.n_free), rk45)

@@ -141,3 +141,63 @@ def test_rk4_fast_kernel_matches_general_and_oracle(N, B):
 
         ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, u), x0[i], 0.0, e.h, steps)
         assert block_err(f[i], ref, n) < 1e-9
+
+
+def test_rk45_config4_samples():
+    """BASELINE config 4 (nonlinear, 64 elements, drag + gravity, per-member E and impulse), 16
+    sampled members, adaptive per-member dt: outputs within 10 (atol + rtol |y|) of SciPy RK45 on
+    the reference RHS, nfev within 2 %.  Horizon 3 ms: the reference's own 64-element nonlinear
+    beam diverges after ~5 ms."""
+    from continuum_robot_b200 import TipImpulse, solve_ensemble
+
+    g = load("cfg4_samples.npz")
+    B, N = g["E_parsed"].shape
+    par = np.zeros((B, N, 7))
+    for col, key in ((0, "length"), (2, "moment_inertia"), (3, "density"), (4, "cross_area"), (5, "wetted_area"), (6, "drag_coef")):
+        par[:, :, col] = g[key][None, :]
+    par[:, :, 1] = g["E_parsed"]
+    beam = make_gpu_beam(par, np.ones(N, dtype=int), np.array([1] + [0] * N), 1000.0, True)
+    n = beam.n_free
+    X0 = torch.zeros(B, 2 * n, dtype=torch.float64, device="cuda")
+    rtol, atol = float(g["rtol"]), float(g["atol"])
+    res = solve_ensemble(beam, (0.0, 0.003), X0, method="RK45", t_eval=g["t_eval"], rtol=rtol, atol=atol,
+                         u=TipImpulse(torch.from_numpy(g["amp"]).cuda()))
+    assert res.success
+    got, ref = res.y.cpu().numpy(), g["y"]
+    assert got.shape == ref.shape
+    assert np.all(np.abs(got - ref) <= 10 * (atol + rtol * np.abs(ref)))
+    nfev = res.nfev.cpu().numpy()
+    assert np.all(np.abs(nfev - g["nfev"]) <= np.maximum(12, 0.02 * g["nfev"])), (nfev, g["nfev"])
+    # per-member step counts differ across the ensemble: the controller really is per member
+    assert len(set(nfev.tolist())) > 4
+
+
+def test_lqr_rollout_config5_samples():
+    """BASELINE config 5: closed-loop LQR rollout (shared gain from the golden file, u = K(0 - x)
+    plus a per-member tip disturbance, gravity on), 2000 RK4 steps, <= 1e-9 at 4 checkpoints."""
+    from continuum_robot_b200 import FullStateLinear, TipImpulse, solve_ensemble
+
+    g = load("cfg5_samples.npz")
+    par = params_array(g)[None]
+    beam = make_gpu_beam(par, g["elem_type"], g["bc"], 0.0, True)
+    n = beam.n_free
+    B = len(g["amp"])
+    ctrl = FullStateLinear(torch.from_numpy(g["gain"]).cuda())
+    X0 = torch.zeros(B, 2 * n, dtype=torch.float64, device="cuda")
+    res = solve_ensemble(beam, (0.0, 2000 * float(g["h"])), X0, method="RK4", h=float(g["h"]), save_every=500,
+                         u=TipImpulse(torch.from_numpy(g["amp"]).cuda()), controller=ctrl)
+    got = res.y.permute(0, 2, 1).cpu().numpy()[:, 1:]
+    ref = g["Y"]
+    assert got.shape == ref.shape
+    worst = max(block_err(got[i, k], ref[i, k], n) for i in range(B) for k in range(ref.shape[1]))
+    assert worst < 1e-9, worst
+    # host-side synthesis gives the same gain as the one stored with the golden trajectories
+    from continuum_robot_b200 import LinearQuadraticRegulator
+
+    Kb, Mb = beam.beam_model.get_stiffness_matrix(), beam.beam_model.get_mass_matrix()
+    assert np.abs(Kb - g["K_beam"]).max() <= 1e-14 * np.abs(Kb).max()
+    Q = np.eye(2 * n)
+    Q[:n, :n] *= 100
+    Q[n:, n:] *= 10
+    K = LinearQuadraticRegulator(Kb, Mb, Q, np.eye(n)).compute_gain_matrix()
+    assert np.abs(K - g["gain"]).max() <= 1e-8 * np.abs(g["gain"]).max()

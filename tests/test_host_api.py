@@ -1,0 +1,239 @@
+"""CPU suite, part 2: host-side logic, the C ABI's host-only entry points, exported symbols."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import case_names, load, oracle_spec, params_array
+from oracle import beam_oracle as bo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from continuum_robot_b200 import _lib
+
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/crb.h is exported by libcrb.so (no compute calls)."""
+    hdr = open(os.path.join(ROOT, "include", "crb.h")).read()
+    names = set(re.findall(r"^(?:int|const char\*)\s+(crb_\w+)\s*\(", hdr, flags=re.M))
+    assert names >= {"crb_version", "crb_last_error", "crb_plan", "crb_assemble", "crb_rhs", "crb_rk4", "crb_rk45",
+                     "crb_dense_matrices"}
+    L = _lib()
+    lib = L.load()
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(L.EXPORTED_SYMBOLS) == names
+    assert lib.crb_version() == L.CRB_VERSION
+    assert C.sizeof(L.CrbPlan) == 4 * 10 + 8 * 2 + 4 * 3 * 256
+
+
+def _plan(N, bc, mmax=0):
+    L = _lib()
+    p = L.CrbPlan()
+    rc = L.load().crb_plan(N, bytes(bc), mmax, C.byref(p))
+    return rc, p
+
+
+@pytest.mark.parametrize("N,m,g", [(32, 4, 8), (64, 4, 16), (6, 3, 2), (10, 3, 4), (20, 3, 8), (1, 1, 1), (128, 4, 32)])
+def test_plan_cantilever_shapes(N, m, g):
+    rc, p = _plan(N, [1] + [0] * N)
+    assert rc == 0
+    assert (p.m, p.g, p.n0, p.p_act, p.n_free, p.contiguous, p.has_mask) == (m, g, 1, N, 3 * N, 1, 0)
+    assert p.p == m * g >= N and p.levels == int(np.log2(g))
+    red = np.ctypeslib.as_array(p.red_index)[: 3 * p.p]
+    assert np.array_equal(red[: 3 * N], np.arange(3 * N)) and np.all(red[3 * N:] == -1)
+
+
+@pytest.mark.parametrize("name", case_names(load("rhs_cases.npz")))
+def test_plan_reduced_index_matches_reference_bc_reduction(name):
+    """(slot, dof) -> reduced index equals the reference's sorted unconstrained-DOF list
+    (euler_bernoulli_beam.py:256-258) for every BC pattern in the golden set."""
+    g = load("rhs_cases.npz")
+    spec = oracle_spec(g, name + "/")
+    N = spec.n_elements
+    bc = list(spec.bc) + [0]
+    rc, p = _plan(N, bc)
+    assert rc == 0
+    unc = bo.unconstrained_dofs(spec)
+    assert p.n_free == len(unc)
+    red = np.ctypeslib.as_array(p.red_index)[: 3 * p.p]
+    for r, full in enumerate(unc):
+        node, d = divmod(int(full), 3)
+        assert red[3 * (node - p.n0) + d] == r
+    assert (red >= 0).sum() == len(unc)
+
+
+def test_plan_errors_are_reported_not_raised():
+    L = _lib()
+    rc, _ = _plan(0, [0])
+    assert rc < 0 and b"n_elements" in L.load().crb_last_error()
+    rc, _ = _plan(3, [1, 1, 1, 1])
+    assert rc < 0 and b"constrain all" in L.load().crb_last_error()
+    rc, _ = _plan(2, [1, 7, 0])
+    assert rc < 0 and b"boundary condition" in L.load().crb_last_error()
+    rc, _ = _plan(200, [1] + [0] * 200)
+    assert rc < 0 and b"limit" in L.load().crb_last_error()
+    with pytest.raises(ValueError):
+        L.check(rc)
+
+
+@pytest.mark.parametrize("name", ["lin4", "pinned_root6", "interior_fixed6", "free6"])
+def test_dense_matrices_match_reference(name):
+    """crb_dense_matrices (host) vs the reference's get_mass_matrix / get_stiffness_matrix."""
+    L = _lib()
+    g = load("rhs_cases.npz")
+    p = name + "/"
+    par = np.ascontiguousarray(params_array(g, p))
+    N = par.shape[0]
+    bc = np.array(list(g[p + "bc"]) + [0], dtype=np.uint8)
+    et = np.asarray(g[p + "elem_type"], dtype=np.uint8)
+    rc, plan = _plan(N, bc)
+    n = plan.n_free
+    M = np.zeros((n, n))
+    K = np.zeros((n, n))
+    rc = L.load().crb_dense_matrices(C.byref(plan), par.ctypes.data_as(C.c_void_p), et.tobytes(), bc.tobytes(),
+                                     M.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert np.abs(M - g[p + "M"]).max() <= 1e-14 * np.abs(M).max()
+    assert np.abs(K - g[p + "K"]).max() <= 1e-14 * np.abs(K).max()
+
+
+def test_dense_stiffness_rejects_nonlinear():
+    L = _lib()
+    g = load("rhs_cases.npz")
+    par = np.ascontiguousarray(params_array(g, "nl4/"))
+    bc = np.array([1, 0, 0, 0, 0], dtype=np.uint8)
+    rc, plan = _plan(4, bc)
+    M = np.zeros((12, 12))
+    K = np.zeros((12, 12))
+    rc = L.load().crb_dense_matrices(C.byref(plan), par.ctypes.data_as(C.c_void_p), bytes([1] * 4), bc.tobytes(),
+                                     M.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p))
+    assert rc < 0 and b"nonlinear" in L.load().crb_last_error()
+
+
+# ---- functional-composition API semantics (reference tests/test_functional_composition.py) ----
+class _MockForce:
+    fused_kind = None
+
+    def __init__(self, value, enabled=True):
+        self.value, self.enabled, self.calls = value, enabled, 0
+
+    def compute_forces(self, x, t):
+        import torch
+
+        self.calls += 1
+        return torch.full((x.shape[0], x.shape[1] // 2), self.value, dtype=x.dtype)
+
+    def is_enabled(self):
+        return self.enabled
+
+
+def test_force_registry_semantics():
+    import torch
+
+    from continuum_robot_b200 import ForceRegistry
+
+    reg = ForceRegistry()
+    a, b, off = _MockForce(1.0), _MockForce(2.5), _MockForce(9.0, enabled=False)
+    reg.register(a)
+    reg.register(b)
+    reg.register(off)  # disabled instances are ignored at registration
+    assert len(reg) == 2 and a in reg and off not in reg
+    lst = reg.get_registered_forces()
+    lst.clear()
+    assert len(reg) == 2  # a copy was returned
+    f = reg.create_aggregated_function()
+    x = torch.zeros(3, 8, dtype=torch.float64)
+    assert torch.equal(f(x, 0.0), torch.full((3, 4), 3.5, dtype=torch.float64))
+    b.enabled = False  # toggling after creation takes effect on the next call
+    assert torch.equal(f(x, 0.0), torch.full((3, 4), 1.0, dtype=torch.float64))
+    assert reg.unregister(a) is True and reg.unregister(a) is False
+    b.enabled = True
+    reg.clear()
+    assert len(reg) == 0 and torch.equal(f(x), torch.zeros(3, 4, dtype=torch.float64))
+
+
+def test_input_registry_adds_deltas():
+    import torch
+
+    from continuum_robot_b200 import InputRegistry
+
+    class H:
+        def __init__(self, d, en=True):
+            self.d, self.en = d, en
+
+        def compute_input(self, x, r, t):
+            return torch.full_like(r, self.d)
+
+        def is_enabled(self):
+            return self.en
+
+    reg = InputRegistry()
+    h1, h2 = H(1.0), H(0.25)
+    reg.register(h1)
+    reg.register(h2)
+    u = torch.ones(2, 3, dtype=torch.float64)
+    out = reg.create_aggregated_function()(torch.zeros(2, 6, dtype=torch.float64), u, 0.0)
+    assert torch.equal(out, u + 1.25) and torch.equal(u, torch.ones(2, 3, dtype=torch.float64))
+    assert len(reg.get_registered_handlers()) == 2 and h1 in reg
+
+
+def test_force_params_and_properties_validation():
+    from continuum_robot_b200 import ForceParams, Properties
+
+    assert not ForceParams() and ForceParams(enable_gravity_effects=True)
+    assert ForceParams(gravity_vector=[0, 0, 0], enable_gravity_effects=True).enable_gravity_effects is False
+    with pytest.raises(ValueError, match="fluid_density must be positive"):
+        ForceParams(enable_fluid_effects=True)
+    with pytest.raises(ValueError, match="exactly 3 components"):
+        ForceParams(gravity_vector=[0, 1])
+    ok = dict(length=1.0, elastic_modulus=1.0, moment_inertia=1.0, density=1.0, cross_area=1.0, segment_id=0, element_type="Linear")
+    assert Properties(**ok).get_element_type().value == "linear"
+    for k, label in (("length", "Length"), ("density", "Density"), ("cross_area", "Cross area")):
+        with pytest.raises(ValueError, match=f"{label} must be positive"):
+            Properties(**{**ok, k: 0.0})
+    with pytest.raises(ValueError, match="Invalid element type"):
+        Properties(**{**ok, "element_type": "cubic"})
+
+
+def test_lqr_host_synthesis_contract():
+    """LinearQuadraticRegulator: shapes, block structure of A/B, stable closed loop, cached gain
+    (the checks of the reference's tests/test_control.py)."""
+    from continuum_robot_b200 import LinearQuadraticRegulator
+
+    b = bo.BeamOracle(bo.BeamSpec.uniform(4))
+    K, M = b.stiffness_matrix(), b.M
+    n = K.shape[0]
+    lqr = LinearQuadraticRegulator(K, M, np.eye(2 * n), np.eye(n))
+    A, B = lqr.get_A(), lqr.get_B()
+    assert np.array_equal(A[:n, n:], np.eye(n)) and not A[:n, :n].any() and not A[n:, n:].any() and not B[:n].any()
+    G = lqr.compute_gain_matrix()
+    assert G.shape == (n, 2 * n) and lqr.get_K() is G
+    assert np.all(np.linalg.eigvals(A - B @ G).real < 0)
+    with pytest.raises(ValueError, match="Q matrix dimension"):
+        LinearQuadraticRegulator(K, M, np.eye(3), np.eye(n)).compute_gain_matrix()
+    with pytest.raises(ValueError, match="same dimensions"):
+        LinearQuadraticRegulator(K, np.eye(n + 1), np.eye(2 * n), np.eye(n))
+
+
+def test_no_cpu_fallback():
+    """The product refuses to run without a CUDA device instead of falling back to the oracle."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from continuum_robot_b200.dynamic_beam import BatchedDynamicEulerBernoulliBeam
+
+    g = load("rhs_cases.npz")
+    with pytest.raises((RuntimeError, AssertionError)):
+        BatchedDynamicEulerBernoulliBeam({"params": params_array(g, "lin4/"), "type": ["linear"] * 4}, device="cpu")
+    src = "".join(open(os.path.join(ROOT, "continuum_robot_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "continuum_robot_b200")) if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src
