@@ -249,6 +249,7 @@ def run_gpu(args):
         tip = X[:, beam.n_free - 2].contiguous()
         out = torch.empty(world * B, dtype=tip.dtype, device=dev) if rank == 0 else None
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.gather(tip, list(out.chunk(world)) if rank == 0 else None, dst=0)  # connection set-up, untimed
         barrier()
         g0.record()
         dist.gather(tip, list(out.chunk(world)) if rank == 0 else None, dst=0)

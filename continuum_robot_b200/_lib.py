@@ -61,6 +61,7 @@ class CrbSystem(C.Structure):
         ("all_linear", C.c_int32),
         ("uniform_mass", C.c_int32),
         ("force_general", C.c_int32),
+        ("force_staged", C.c_int32),
         ("um", C.c_double * 4),
     ]
 

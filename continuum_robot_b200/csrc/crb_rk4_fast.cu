@@ -11,7 +11,10 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
-  if (sys->imp_amp) {
+  if (!sys->imp_amp && !sys->force_staged) {  // autonomous force-free case: paired operator applications
+    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV>, bytes, "crb_rk4")) return rc;
+    crb_rk4_lin2_kernel<M, LV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, h, nsteps, Y_out, save_every);
+  } else if (sys->imp_amp) {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
     crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
   } else {

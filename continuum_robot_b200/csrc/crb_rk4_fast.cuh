@@ -339,3 +339,275 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
       }
   }
 }
+
+// ==========================================================================================
+// Paired variant for the autonomous force-free linear case (config 3: u = 0).
+//
+// For x' = J x with J = [[0, I], [-A, 0]], A = M^-1 K, the classical RK4 update is the degree-4
+// Taylor polynomial of hJ; with F(w) = -A w,
+//     a1 = F(q), p = F(v), r = F(a1), s = F(p)
+//     a2 = a1 + h/2 p,  a3 = a1 + h/2 p + h^2/4 r,  a4 = a1 + h p + h^2/2 r + h^3/4 s
+//     q+ = q + h/6 (k1q + 2 k2q + 2 k3q + k4q) = q + h v + h^2/2 a1 + h^3/6 p + h^4/24 r
+//     v+ = v + h/6 (a1 + 2 a2 + 2 a3 + a4)     = v + h a1 + h^2/2 p + h^3/6 r + h^4/24 s
+// i.e. the same four stage derivatives k1..k4 of north_star row R1, evaluated as TWO rounds of TWO
+// independent operator applications.  The pair shares every mass constant read from shared
+// memory (half the LDS traffic per step) and gives the FP64 pipe two independent dependency
+// chains per lane.
+// ==========================================================================================
+template <int M, int LV>
+__device__ __forceinline__ void fast_solve2(double (&b)[2][M][3], const FastCtx<M>& C) {
+  constexpr int G = 1 << LV;
+  const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
+  double s00[M], s01[M], s11[M], su[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const double2 a = ld_fslot<M, G>(C, 0, j), c = ld_fslot<M, G>(C, 1, j);
+    s00[j] = a.x;
+    s01[j] = a.y;
+    s11[j] = c.x;
+    su[j] = c.y;
+  }
+  double y0[2], y1[2], y2[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) { y0[r] = b[r][0][0]; y1[r] = b[r][0][1]; y2[r] = b[r][0][2]; }
+  // ---- forward A ----
+#pragma unroll
+  for (int j = 1; j < M; ++j)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double xu = su[j - 1] * y0[r];
+      const double xw = fma(s00[j - 1], y1[r], s01[j - 1] * y2[r]);
+      const double xp = fma(s01[j - 1], y1[r], s11[j - 1] * y2[r]);
+      y0[r] = fma(-ou, xu, b[r][j][0]);
+      y1[r] = fma(-o11, xw, fma(o12, xp, b[r][j][1]));
+      y2[r] = fma(-o12, xw, fma(o22, xp, b[r][j][2]));
+    }
+  double xi0[2] = {0.0, 0.0}, xi1[2] = {0.0, 0.0}, xi2[2] = {0.0, 0.0};
+  double cub[LV > 0 ? LV : 1];
+  if (G > 1) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+      const int d = 1 << l;
+      const double2 c0 = ld_fscan<M, G>(C, l, 0), c1 = ld_fscan<M, G>(C, l, 1), cu = ld_fscan<M, G>(C, l, 4);
+      cub[l] = cu.y;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double t0 = shfl_up_d(y0[r], d, G), t1 = shfl_up_d(y1[r], d, G), t2 = shfl_up_d(y2[r], d, G);
+        y0[r] = fma(cu.x, t0, y0[r]);
+        mv2(c0, c1, t1, t2, y1[r], y2[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double xu = su[M - 1] * y0[r];
+      const double xw = fma(s00[M - 1], y1[r], s01[M - 1] * y2[r]);
+      const double xp = fma(s01[M - 1], y1[r], s11[M - 1] * y2[r]);
+      xi0[r] = shfl_up_d(xu, 1, G);
+      xi1[r] = shfl_up_d(xw, 1, G);
+      xi2[r] = shfl_up_d(xp, 1, G);
+      if (C.g == 0) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
+    }
+  }
+  // ---- forward B ----
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double t0 = fma(-ou, xi0[r], b[r][j][0]);
+      const double t1 = fma(-o11, xi1[r], fma(o12, xi2[r], b[r][j][1]));
+      const double t2 = fma(-o12, xi1[r], fma(o22, xi2[r], b[r][j][2]));
+      xi0[r] = su[j] * t0;
+      xi1[r] = fma(s00[j], t1, s01[j] * t2);
+      xi2[r] = fma(s01[j], t1, s11[j] * t2);
+      b[r][j][0] = xi0[r];
+      b[r][j][1] = xi1[r];
+      b[r][j][2] = xi2[r];
+    }
+  // ---- backward A ----
+  double r0[2], r1[2], r2[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) { r0[r] = b[r][M - 1][0]; r1[r] = b[r][M - 1][1]; r2[r] = b[r][M - 1][2]; }
+#pragma unroll
+  for (int j = M - 2; j >= 0; --j)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double t0 = ou * r0[r];
+      const double t1 = fma(o11, r1[r], o12 * r2[r]);
+      const double t2 = -fma(o12, r1[r], o22 * r2[r]);
+      r0[r] = fma(-su[j], t0, b[r][j][0]);
+      r1[r] = b[r][j][1] - fma(s00[j], t1, s01[j] * t2);
+      r2[r] = b[r][j][2] - fma(s01[j], t1, s11[j] * t2);
+    }
+  double n0[2] = {0.0, 0.0}, n1[2] = {0.0, 0.0}, n2[2] = {0.0, 0.0};
+  if (G > 1) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+      const int d = 1 << l;
+      const double2 c0 = ld_fscan<M, G>(C, l, 2), c1 = ld_fscan<M, G>(C, l, 3);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double t0 = shfl_down_d(r0[r], d, G), t1 = shfl_down_d(r1[r], d, G), t2 = shfl_down_d(r2[r], d, G);
+        r0[r] = fma(cub[l], t0, r0[r]);
+        mv2(c0, c1, t1, t2, r1[r], r2[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      n0[r] = shfl_down_d(r0[r], 1, G);
+      n1[r] = shfl_down_d(r1[r], 1, G);
+      n2[r] = shfl_down_d(r2[r], 1, G);
+      if (C.g == G - 1) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
+    }
+  }
+  // ---- backward B ----
+#pragma unroll
+  for (int j = M - 1; j >= 0; --j)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double t0 = ou * n0[r];
+      const double t1 = fma(o11, n1[r], o12 * n2[r]);
+      const double t2 = -fma(o12, n1[r], o22 * n2[r]);
+      n0[r] = fma(-su[j], t0, b[r][j][0]);
+      n1[r] = b[r][j][1] - fma(s00[j], t1, s01[j] * t2);
+      n2[r] = b[r][j][2] - fma(s01[j], t1, s11[j] * t2);
+      b[r][j][0] = n0[r];
+      b[r][j][1] = n1[r];
+      b[r][j][2] = n2[r];
+    }
+}
+
+// w[r] <- -M^-1 K w[r] for r = 0, 1 (two independent operator applications).
+template <int M, int LV>
+__device__ __forceinline__ void fast_apply2(const FastCtx<M>& C, double (&w)[2][M][3]) {
+  constexpr int G = 1 << LV;
+  double b[2][M][3];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    double qh[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      qh[d] = shfl_up_d(w[r][M - 1][d], 1, G);
+      if (C.g == 0) qh[d] = 0.0;
+    }
+    double fu[M + 1], V[M + 1], m1[M + 1], m2[M];
+    elem_linear_vals(C.kc[0], qh, w[r][0], fu[0], V[0], m1[0], m2[0]);
+#pragma unroll
+    for (int j = 1; j < M; ++j) elem_linear_vals(C.kc[j], w[r][j - 1], w[r][j], fu[j], V[j], m1[j], m2[j]);
+    fu[M] = shfl_down_d(fu[0], 1, G);
+    V[M] = shfl_down_d(V[0], 1, G);
+    m1[M] = shfl_down_d(m1[0], 1, G);
+    if (C.g == G - 1) { fu[M] = 0.0; V[M] = 0.0; m1[M] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      b[r][j][0] = fu[j] - fu[j + 1];
+      b[r][j][1] = V[j] - V[j + 1];
+      b[r][j][2] = -(m2[j] + m1[j + 1]);
+    }
+  }
+  fast_solve2<M, LV>(b, C);
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) w[r][j][d] = b[r][j][d];
+}
+
+template <int M, int LV>
+__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
+crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double h, int nsteps,
+                    double* __restrict__ Y, int save_every) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
+  constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
+  {
+    const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+    for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + warp * mpw + lane / G;
+  FastCtx<M> C;
+  C.g = lane % G;
+  C.n = P.n_free;
+  C.active = member < S.n_members;
+  C.member = C.active ? member : S.n_members - 1;
+  C.um = um;
+  C.fslot = smem;
+  C.fscan = smem + 4 * M * G;
+  C.imp_amp = 0.0;
+  C.imp_dur = 0.0;
+  C.imp_local = -1;
+  const int s0 = C.g * M;
+  {
+    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
+      const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
+      C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
+    }
+  }
+  const int n = C.n;
+  double* xq = X + (long long)C.member * 2 * n + 3 * s0;
+  double q[M][3], v[M][3], w[2][M][3];
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      q[j][d] = xq[3 * j + d];
+      v[j][d] = xq[n + 3 * j + d];
+    }
+  const double h2 = 0.5 * h * h, h3 = h * h * h / 6.0, h4 = h * h * h * h / 24.0;
+  for (int k = 0; k < nsteps; ++k) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        w[0][j][d] = q[j][d];
+        w[1][j][d] = v[j][d];
+      }
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+      fast_apply2<M, LV>(C, w);
+      if (round == 0) {  // w = (a1, p)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double a1 = w[0][j][d], p = w[1][j][d];
+            q[j][d] = fma(h3, p, fma(h2, a1, fma(h, v[j][d], q[j][d])));
+            v[j][d] = fma(h2, p, fma(h, a1, v[j][d]));
+          }
+      } else {  // w = (r, s)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double r = w[0][j][d], s = w[1][j][d];
+            q[j][d] = fma(h4, r, q[j][d]);
+            v[j][d] = fma(h4, s, fma(h3, r, v[j][d]));
+          }
+      }
+    }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
+      double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          yq[3 * j + d] = q[j][d];
+          yq[n + 3 * j + d] = v[j][d];
+        }
+    }
+  }
+  if (C.active) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        xq[3 * j + d] = q[j][d];
+        xq[n + 3 * j + d] = v[j][d];
+      }
+  }
+}

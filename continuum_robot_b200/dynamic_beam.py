@@ -351,6 +351,7 @@ class BatchedDynamicEulerBernoulliBeam:
         mu = rho0 * A0 * L0 / 420
         self._um = (54 * mu, 13 * L0 * mu, 3 * L0 * L0 * mu, 70 * mu)
         self.force_general_kernels = False
+        self.force_staged_kernels = False
         self._mass_shared = shared([0, 3, 4])
         self._stiff_shared = shared([0, 1, 2, 4])
         self._force_shared = shared([0, 3, 4, 5, 6])
@@ -425,6 +426,7 @@ class BatchedDynamicEulerBernoulliBeam:
         s.all_linear = int(self._all_linear)
         s.uniform_mass = int(self._uniform_mass)
         s.force_general = int(self.force_general_kernels)
+        s.force_staged = int(self.force_staged_kernels)
         for k in range(4):
             s.um[k] = float(self._um[k])
         if drag is not None:

@@ -104,6 +104,7 @@ typedef struct crb_system_t {
   int32_t all_linear;       /* 1: every element is CRB_ELEM_LINEAR */
   int32_t uniform_mass;     /* 1: rho*A*L and L identical for every element of every member */
   int32_t force_general;    /* 1: always use the general kernels (testing / comparison) */
+  int32_t force_staged;     /* 1: fast path keeps the stage-by-stage kernel (no paired operator form) */
   double um[4];             /* uniform-mass coupling block: 54 mu, 13 L mu, 3 L^2 mu, 70 mu, mu = rho A L / 420 */
 } crb_system_t;
 

@@ -201,3 +201,42 @@ def test_lqr_rollout_config5_samples():
     Q[n:, n:] *= 10
     K = LinearQuadraticRegulator(Kb, Mb, Q, np.eye(n)).compute_gain_matrix()
     assert np.abs(K - g["gain"]).max() <= 1e-8 * np.abs(g["gain"]).max()
+
+
+@pytest.mark.parametrize("N,B", [(32, 37), (64, 9), (6, 5)])
+def test_rk4_paired_linear_kernel(N, B):
+    """Autonomous force-free linear case (config 3): the paired operator form (two rounds of two
+    independent applications of -M^-1 K = the degree-4 Taylor polynomial of the classical tableau)
+    against the stage-by-stage fast kernel and the general kernel (<= 1e-11) and the oracle."""
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    e = ens.config3(B, N, seed=3)
+    m = ens.material()
+    par = np.zeros((B, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E
+    par[:, :, 5:] = 1.0
+    beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+    n = beam.n_free
+    x0 = np.concatenate([e.q0, e.v0], axis=1)
+    steps = 80
+    out = {}
+    for mode in ("paired", "staged", "general"):
+        beam.force_staged_kernels = mode == "staged"
+        beam.force_general_kernels = mode == "general"
+        X = torch.from_numpy(x0).cuda()
+        Y = torch.empty(2, B, 2 * n, dtype=torch.float64, device="cuda")
+        rk4_steps(beam, X, 0.0, e.h, steps, Y_out=Y, save_every=40)
+        assert torch.equal(Y[1], X)
+        out[mode] = (X.cpu().numpy(), Y[0].cpu().numpy())
+    for mode in ("staged", "general"):
+        for k in range(2):
+            assert max(block_err(out["paired"][k][i], out[mode][k][i], n) for i in range(B)) < 1e-11, mode
+    i = B - 1
+    spec = bo.BeamSpec.uniform(N)
+    spec.elastic_modulus = e.E[i].copy()
+    b = bo.BeamOracle(spec)
+    ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, np.zeros(n)), x0[i], 0.0, e.h, steps)
+    assert block_err(out["paired"][0][i], ref, n) < 1e-9
