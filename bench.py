@@ -223,25 +223,28 @@ def run_gpu(args):
     full_steps = S if any(c == S for c in chunks(args.steps)) else chunks(args.steps)[0]
     finite = bool(torch.isfinite(X).all().item())
 
-    # ---- e2e: host buffers, H2D + fused steps + D2H every launch ----
-    Xe = torch.empty_like(X)
-    for _ in range(2):
-        Xe.copy_(x_host, non_blocking=True)
-        rk4_steps(beam, Xe, 0.0, h, min(S, args.steps), system=system)
-        x_host.copy_(Xe, non_blocking=True)
+    # ---- e2e: host buffers through the public host-pipeline API: every launch group copies the
+    # state from pinned host memory, runs its fused steps and copies the state back (chunked so the
+    # copies overlap the kernels on three streams) ----
+    from continuum_robot_b200.integrate import HostPipeline
+
+    pipe = HostPipeline(beam, B, n_chunks=args.e2e_chunks)
+    for _ in range(3):
+        pipe.run(x_host, 0.0, h, min(S, args.steps))
+    pipe.synchronize()
     x_host.copy_(torch.from_numpy(x0))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     te = 0
     for c in chunks(args.steps):
-        Xe.copy_(x_host, non_blocking=True)
-        rk4_steps(beam, Xe, te * h, h, c, system=system)
-        x_host.copy_(Xe, non_blocking=True)
+        pipe.run(x_host, te * h, h, c)
         te += c
     e1.record()
     barrier()
+    pipe.synchronize()
     e2e_ms = e0.elapsed_time(e1)
+    e2e_ok = bool(np.isfinite(x_host.numpy()).all())
 
     # ---- final gather (the only collective of the job; outside the step path) ----
     gather_ms = None
@@ -292,7 +295,8 @@ def run_gpu(args):
             },
             "e2e": {"value": e2e_val, "unit": "element-steps/s", "h2d_bytes_per_step": X.numel() * 8 / S,
                     "d2h_bytes_per_step": X.numel() * 8 / S,
-                    "call": f"per launch: H2D state {X.numel() * 8} B (pinned) + {S} fused RK4 steps + D2H state"},
+                    "call": f"HostPipeline.run per {S} fused RK4 steps: H2D state {X.numel() * 8} B (pinned) + kernels + D2H state, "
+                            f"{args.e2e_chunks} member chunks on 3 streams", "finite": e2e_ok},
             "gpu_launches": len(chunks(args.steps)),
             "clocks": clocks,
             "kernel_ms_per_launch": mean_launch,
@@ -318,6 +322,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=50)
     ap.add_argument("--cpu-steps", type=int, default=2000, help="RK4 steps per member in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=16)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -408,19 +408,28 @@ class BatchedDynamicEulerBernoulliBeam:
             raise ValueError(f"state batch has {B} members but the ensemble was built with {self.n_param_sets} parameter sets")
 
     def make_system(self, B: int, *, drag: Optional[FluidDragForce] = None, gravity: Optional[GravityForce] = None,
-                    u_const=None, impulse: Optional[TipImpulse] = None, gain=None, ref=None, f_ext=None):
-        """Fill a crb_system_t; returns (struct, keepalive list)."""
+                    u_const=None, impulse: Optional[TipImpulse] = None, gain=None, ref=None, f_ext=None,
+                    member_range=None):
+        """Fill a crb_system_t; returns (struct, keepalive list).
+
+        ``member_range=(lo, hi)`` describes the sub-ensemble lo..hi-1 of a B-member ensemble (every
+        per-member pointer is offset); used to pipeline host<->device copies chunk by chunk."""
         torch = _torch()
         self._check_members(B)
         n = self.n_free
         keep = []
         s = _lib.CrbSystem()
-        s.n_members = B
+        lo, hi = member_range if member_range is not None else (0, B)
+        if not 0 <= lo < hi <= B:
+            raise ValueError(f"bad member_range {member_range} for {B} members")
+        s.n_members = hi - lo
         s.mass_shared = int(self._mass_shared)
         s.stiff_shared = int(self._stiff_shared)
         s.force_shared = int(self._force_shared)
-        s.mfac = self._d_mfac.data_ptr()
-        s.kcoef = self._d_kcoef.data_ptr()
+        P = int(self._plan.p)
+        s.mfac = self._d_mfac.data_ptr() + (0 if self._mass_shared else 8 * lo * int(self._plan.mfac_doubles))
+        s.kcoef = self._d_kcoef.data_ptr() + (0 if self._stiff_shared else 8 * lo * P * 4)
+        fo = 0 if self._force_shared else lo
         s.elem_type = self._d_etype.data_ptr()
         s.red_index = self._d_red.data_ptr()
         s.all_linear = int(self._all_linear)
@@ -432,13 +441,13 @@ class BatchedDynamicEulerBernoulliBeam:
         if drag is not None:
             if drag.fluid_density != self.force_params.fluid_density:
                 raise ValueError("FluidDragForce.fluid_density differs from the assembled ForceParams.fluid_density")
-            s.drag = self._d_drag.data_ptr()
+            s.drag = self._d_drag.data_ptr() + 8 * fo * P
         if gravity is not None:
             gv = gravity.gravity_vector
             s.gx, s.gy = float(gv[0]), float(gv[1])
-            s.seg_half_mass = self._d_hmass.data_ptr()
+            s.seg_half_mass = self._d_hmass.data_ptr() + 8 * fo * self.n_elements
             if self._plan.contiguous:
-                s.grav = self._d_grav.data_ptr()
+                s.grav = self._d_grav.data_ptr() + 8 * fo * P * 2
                 s.grav_mode = 1
             else:
                 s.grav_mode = 2
@@ -452,14 +461,14 @@ class BatchedDynamicEulerBernoulliBeam:
             keep.append(tn)
             return tn
         if u_const is not None:
-            s.u_const = dev64(u_const, (B, n), "u").data_ptr()
+            s.u_const = dev64(u_const, (B, n), "u").data_ptr() + 8 * lo * n
         if f_ext is not None:
-            s.f_ext = dev64(f_ext, (B, n), "forces").data_ptr()
+            s.f_ext = dev64(f_ext, (B, n), "forces").data_ptr() + 8 * lo * n
         if impulse is not None:
             amp = impulse.amplitude
             if not isinstance(amp, torch.Tensor):
                 amp = torch.as_tensor(np.asarray(amp, dtype=np.float64))
-            s.imp_amp = dev64(amp.reshape(-1), (B,), "impulse amplitude").data_ptr()
+            s.imp_amp = dev64(amp.reshape(-1), (B,), "impulse amplitude").data_ptr() + 8 * lo
             dof = impulse.dof if impulse.dof >= 0 else n + impulse.dof
             if not 0 <= dof < n:
                 raise ValueError(f"impulse dof {impulse.dof} outside the {n} position DOFs")
