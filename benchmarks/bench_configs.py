@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench line): BASELINE configs 2, 4 and 5 as ensembles.
+
+    python benchmarks/bench_configs.py [--only cfg5] [--members N]
+
+Prints one JSON line per config: element-steps/s (RK4) or element-attempts/s (RK45), CUDA-event
+timed, state resident in HBM.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def params(e, B, fluid=True):
+    from continuum_robot_b200 import ensembles as ens
+
+    m = ens.material()
+    par = np.empty((B, e.n_elements, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E[:B]
+    par[:, :, 5], par[:, :, 6] = m["wetted_area"], m["drag_coef"]
+    return par
+
+
+def timed(fn, reps=3):
+    import torch
+
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def main():
+    import torch
+
+    from continuum_robot_b200 import (BatchedDynamicEulerBernoulliBeam, ForceParams, FullStateLinear,
+                                      LinearQuadraticRegulator, TipImpulse, solve_ensemble)
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="cfg2,cfg4,cfg5,cfg3g")
+    ap.add_argument("--slots", type=int, default=0)
+    a = ap.parse_args()
+    dev = "cuda"
+    for name in a.only.split(","):
+        if name == "cfg2":  # nonlinear 20-element + drag, replicated: RK4 h = 2.5e-5
+            B, steps = 32768, 200
+            e = ens.config2()
+            par = np.repeat(params(e, 1), 1, axis=0)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["nonlinear"] * 20},
+                                                    ForceParams(fluid_density=1000.0, enable_fluid_effects=True),
+                                                    max_slots_per_lane=a.slots)
+            beam.create_system_func(); beam.create_input_func()
+            X = torch.zeros(B, 120, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.full((B,), 0.1, dtype=torch.float64, device=dev))
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
+            print(json.dumps({"config": "cfg2 x%d (nonlinear 20 el + drag), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
+                              "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg3g":  # config 3 through the GENERAL kernel (comparison)
+            B, steps = 65536, 50
+            e = ens.config3(B, 32)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, B), "type": ["linear"] * 32})
+            beam.create_system_func(); beam.create_input_func()
+            beam.force_general_kernels = True
+            X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
+            print(json.dumps({"config": "cfg3 general kernel", "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg4":  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
+            B = 4096
+            e = ens.config4(B)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, B), "type": ["nonlinear"] * 64},
+                                                    ForceParams(fluid_density=1000.0, enable_fluid_effects=True, enable_gravity_effects=True),
+                                                    max_slots_per_lane=a.slots)
+            beam.create_system_func(); beam.create_input_func()
+            X0 = torch.zeros(B, 384, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.from_numpy(e.impulse_amp).to(dev))
+            out = {}
+
+            def run():
+                out["r"] = solve_ensemble(beam, (0.0, 0.003), X0, method="RK45", rtol=1e-6, atol=1e-9, u=imp,
+                                          t_eval=np.linspace(0, 0.003, 7))
+
+            ms = timed(run, reps=2)
+            r = out["r"]
+            att = (r.naccept + r.nreject).double()
+            print(json.dumps({"config": "cfg4 4096 x 64 nonlinear RK45 to 3 ms", "m": beam._plan.m, "g": beam._plan.g, "ms": ms,
+                              "attempts_mean": float(att.mean()), "attempts_max": float(att.max()),
+                              "element_attempts_per_s": float(att.sum()) * 64 / (ms * 1e-3), "success": r.success}))
+        if name == "cfg5":  # LQR rollout, shared N = 6 design, 131072 members per GPU
+            B, steps = 131072, 200
+            e = ens.config5(B)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, 1), "type": ["linear"] * 6},
+                                                    ForceParams(enable_gravity_effects=True), max_slots_per_lane=a.slots)
+            beam.create_system_func(); beam.create_input_func()
+            n = beam.n_free
+            Q = np.eye(2 * n); Q[:n, :n] *= 100; Q[n:, n:] *= 10
+            K = LinearQuadraticRegulator(beam.beam_model.get_stiffness_matrix(), beam.beam_model.get_mass_matrix(), Q, np.eye(n)).compute_gain_matrix()
+            ctrl = FullStateLinear(torch.from_numpy(K).to(dev))
+            X = torch.zeros(B, 2 * n, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.from_numpy(e.impulse_amp).to(dev))
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp, controller=ctrl))
+            print(json.dumps({"config": "cfg5 LQR rollout 131072 x 6 el, RK4", "m": beam._plan.m, "g": beam._plan.g,
+                              "element_steps_per_s": B * 6 * steps / (ms * 1e-3), "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}))
+
+
+if __name__ == "__main__":
+    main()

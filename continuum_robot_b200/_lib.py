@@ -57,6 +57,7 @@ class CrbSystem(C.Structure):
         ("imp_duration", C.c_double),
         ("gain", C.c_void_p),
         ("ref", C.c_void_p),
+        ("gain_frag", C.c_void_p),
         ("f_ext", C.c_void_p),
         ("all_linear", C.c_int32),
         ("uniform_mass", C.c_int32),
@@ -86,6 +87,7 @@ _SIGNATURES = {
          C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_int32, C.c_void_p],
     ),
+    "crb_gain_fragments": (C.c_int64, [C.POINTER(CrbPlan), C.c_void_p, C.c_void_p]),
     "crb_dense_matrices": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p,
                                      C.c_void_p, C.c_void_p]),
 }

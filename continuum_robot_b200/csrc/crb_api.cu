@@ -217,6 +217,33 @@ extern "C" int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double*
 }
 
 // ------------------------------------------------------------------------------------------
+// crb_gain_fragments (host)
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t crb_gain_fragments(const crb_plan_t* plan, const double* gain, double* out) {
+  if (!plan) return fail(CRB_E_ARG, "crb_gain_fragments: null plan");
+  if (plan->g != 4) return fail(CRB_E_ARG, "crb_gain_fragments: needs a plan with 4 lanes per member, got %d", plan->g);
+  const int m = plan->m, n = plan->n_free, KT = 6 * m, NT = (3 * m + 1) / 2;
+  const int64_t count = (int64_t)KT * NT * 32;
+  if (!out) return count;
+  if (!gain) return fail(CRB_E_ARG, "crb_gain_fragments: null gain");
+  for (int kt = 0; kt < KT; ++kt)
+    for (int nt = 0; nt < NT; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int src = lane % 4, col8 = lane / 4, dst = col8 / 2, el = col8 % 2;
+        const int oidx = 2 * nt + el;  // own position DOF of the destination lane
+        double val = 0.0;
+        if (oidx < 3 * m) {
+          const int r_out = plan->red_index[3 * (dst * m) + oidx];
+          const int kk = kt < 3 * m ? kt : kt - 3 * m;
+          const int r_in = plan->red_index[3 * (src * m) + kk];
+          if (r_out >= 0 && r_in >= 0) val = gain[(int64_t)r_out * 2 * n + (kt < 3 * m ? r_in : n + r_in)];
+        }
+        out[((int64_t)kt * NT + nt) * 32 + lane] = val;
+      }
+  return count;
+}
+
+// ------------------------------------------------------------------------------------------
 // crb_dense_matrices (host): BC-reduced M and K of one design, for LQR synthesis on the host.
 // models/segments.py:32-78, euler_bernoulli_beam.py:139-161, 265, 422-511.
 // ------------------------------------------------------------------------------------------

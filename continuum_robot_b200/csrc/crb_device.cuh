@@ -238,6 +238,7 @@ __device__ __forceinline__ void elem_nonlinear(const double4 c, const double (&q
 template <int M>
 struct LaneCtx {
   int G, g, levels;
+  int lane;              // lane id in the warp
   int member;            // clamped member index
   bool active;           // member < B
   int n;                 // free position DOFs
@@ -274,6 +275,7 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
                                               double* scratch) {
   L.G = P.g;
   L.g = g;
+  L.lane = threadIdx.x & 31;
   L.levels = P.levels;
   L.n = P.n_free;
   L.nseg = P.N;
@@ -371,8 +373,43 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
     acc[M - 1][d] += r;
   }
 
-  // ---- reduced-vector scratch paths: feedback gain and generic-BC gravity ----
-  if (F.gain || F.grav_generic) {
+  // ---- state feedback u_c = gain (ref - x) as an FP64 tensor-core contraction ----
+  // The gain is ONE operator shared by the whole ensemble, so the feedback of 8 members is a
+  // dense [8 x 2n] x [2n x n] product: mma.sync.m8n8k4.f64 with rows = members (4 lanes each,
+  // plan.g == 4), k-tiles = the lanes' own state values (no shuffle needed to build A) and n-tiles
+  // = the lanes' own position DOFs (the C fragment lands where the force is consumed).
+  const bool gain_mma = F.gain && S.gain_frag != nullptr && G == 4;
+  if (gain_mma) {
+    constexpr int KT = 6 * M, NT = (3 * M + 1) / 2;
+    double ev[KT];
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int r = L.ri[j][d];
+        const double rq = (S.ref && r >= 0) ? __ldg(S.ref + r) : 0.0;
+        const double rv = (S.ref && r >= 0) ? __ldg(S.ref + L.n + r) : 0.0;
+        ev[3 * j + d] = r >= 0 ? rq - q[j][d] : 0.0;
+        ev[3 * M + 3 * j + d] = r >= 0 ? rv - v[j][d] : 0.0;
+      }
+    const double* fr = S.gain_frag + L.lane;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const double bfrag = __ldg(fr + (kt * NT + nt) * 32);
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1)
+                     : "d"(ev[kt]), "d"(bfrag));
+      }
+      acc[(2 * nt) / 3][(2 * nt) % 3] += c0;
+      if (2 * nt + 1 < 3 * M) acc[(2 * nt + 1) / 3][(2 * nt + 1) % 3] += c1;
+    }
+  }
+
+  // ---- reduced-vector scratch paths: feedback gain (other lane layouts) and generic-BC gravity ----
+  if ((F.gain && !gain_mma) || F.grav_generic) {
     double* e = L.scratch;  // [2n]: e = x (positions then velocities) in reduced order
     __syncwarp();
 #pragma unroll
@@ -385,7 +422,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
         }
     __syncwarp();
     const int n = L.n;
-    if (F.gain) {
+    if (F.gain && !gain_mma) {
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll

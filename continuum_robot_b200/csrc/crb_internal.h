@@ -35,7 +35,7 @@ inline KPlan kplan_of(const crb_plan_t* p) {
 inline SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
   SmemLayout SL;
   SL.mfac_doubles = sys->mass_shared ? (int)plan->mfac_doubles : 0;
-  SL.scratch_doubles = (sys->gain || sys->grav_mode == 2) ? 2 * plan->n_free : 0;
+  SL.scratch_doubles = ((sys->gain && !(sys->gain_frag && plan->g == 4)) || sys->grav_mode == 2) ? 2 * plan->n_free : 0;
   const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
   *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
   return SL;

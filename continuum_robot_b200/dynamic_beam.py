@@ -249,6 +249,8 @@ class BatchedDynamicEulerBernoulliBeam:
     def __init__(self, params, force_params: Optional[ForceParams] = None, *, device=None,
                  max_slots_per_lane: int = 0):
         torch = _torch()
+        self._ctor = (params, max_slots_per_lane)
+        self._siblings = {}
         self.force_params = force_params or ForceParams()
         fluid = bool(self.force_params.enable_fluid_effects)
         if fluid and self.force_params.fluid_density <= 0:
@@ -385,6 +387,23 @@ class BatchedDynamicEulerBernoulliBeam:
         if self.force_params.enable_gravity_effects:
             self.force_registry.register(GravityForce(self, self.force_params.get_gravity_vector(), True))
 
+    def with_slots(self, max_slots_per_lane: int) -> "BatchedDynamicEulerBernoulliBeam":
+        """Same ensemble assembled for another lane decomposition (e.g. 2 slots per lane for the
+        register-hungry adaptive kernel).  Registries and function state are SHARED with ``self``."""
+        if max_slots_per_lane == self._ctor[1] or int(self._plan.m) <= max_slots_per_lane:
+            return self
+        if max_slots_per_lane not in self._siblings:
+            sib = BatchedDynamicEulerBernoulliBeam(
+                {"params": self._params_np, "type": [int(t) for t in self._etype],
+                 "boundary_condition": [int(b) for b in self._bc[: self.n_elements]]},
+                self.force_params, device=self.device, max_slots_per_lane=max_slots_per_lane)
+            self._siblings[max_slots_per_lane] = sib
+        sib = self._siblings[max_slots_per_lane]
+        sib.force_registry, sib.input_registry = self.force_registry, self.input_registry
+        sib._forces_func, sib.system_func, sib.input_func = self._forces_func, self.system_func, self.input_func
+        sib.force_general_kernels, sib.force_staged_kernels = self.force_general_kernels, self.force_staged_kernels
+        return sib
+
     # -- state maps -----------------------------------------------------------------------------
     def get_state_to_node_param(self, state_idx):
         if state_idx not in self.state_to_node_param:
@@ -479,7 +498,19 @@ class BatchedDynamicEulerBernoulliBeam:
                 gain = torch.as_tensor(np.asarray(gain, dtype=np.float64))
             if gain.ndim != 2 or tuple(gain.shape) != (n, 2 * n):
                 raise ValueError(f"Gain matrix must have shape ({n}, {2 * n}), got {tuple(gain.shape)}")
-            s.gain = dev64(gain, (n, 2 * n), "gain").data_ptr()
+            gdev = dev64(gain, (n, 2 * n), "gain")
+            s.gain = gdev.data_ptr()
+            if int(self._plan.g) == 4:  # shared operator -> FP64 tensor-core fragments (crb_gain_fragments)
+                lib = _lib.load()
+                cnt = int(lib.crb_gain_fragments(C.byref(self._plan), None, None))
+                gh = np.ascontiguousarray(gdev.detach().cpu().numpy())
+                fr = np.empty(cnt, dtype=np.float64)
+                got = lib.crb_gain_fragments(C.byref(self._plan), gh.ctypes.data_as(C.c_void_p), fr.ctypes.data_as(C.c_void_p))
+                if got != cnt:
+                    _lib.check(int(got))
+                frd = torch.from_numpy(fr).to(self.device)
+                keep.append(frd)
+                s.gain_frag = frd.data_ptr()
             if ref is not None:
                 if not isinstance(ref, torch.Tensor):
                     ref = torch.as_tensor(np.asarray(ref, dtype=np.float64))

@@ -50,6 +50,14 @@ def _feedback(controller):
     return controller.gain_matrix, getattr(controller, "reference", None)
 
 
+def _feedback_layout(beam, controller):
+    """State feedback runs on the FP64 tensor cores when a member spans 4 lanes (8 members = the 8
+    rows of mma.m8n8k4): short beams are re-assembled with 2 slots per lane to get that layout."""
+    if controller is not None and controller.is_enabled() and int(beam._plan.g) != 4 and beam._plan.p_act <= 8:
+        return beam.with_slots(2)
+    return beam
+
+
 def rk4_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, nsteps: int, *, u=None,
               controller=None, Y_out=None, save_every: int = 0, system=None):
     """Advance X[B,2n] in place by ``nsteps`` classical RK4 steps in ONE kernel launch.
@@ -68,6 +76,7 @@ def rk4_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, ns
         if callable(uc) and not isinstance(uc, torch.Tensor):
             raise TypeError("fused RK4 needs a constant tensor or TipImpulse input; use solve_ensemble for callables")
         gain, ref = _feedback(controller)
+        beam = _feedback_layout(beam, controller)
         system = beam.make_system(X.shape[0], drag=drag, gravity=grav, u_const=uc, impulse=impulse, gain=gain, ref=ref)
     sysm, _keep = system
     with torch.cuda.device(beam.device):
@@ -107,6 +116,7 @@ class HostPipeline:
         impulse = u if isinstance(u, TipImpulse) else None
         uc = None if impulse is not None else u
         gain, ref = _feedback(controller)
+        beam = self.beam = _feedback_layout(beam, controller)
         self.systems = [beam.make_system(self.B, drag=drag, gravity=grav, u_const=uc, impulse=impulse, gain=gain,
                                          ref=ref, member_range=r) for r in self.ranges]
         self.ev_out = [None] * len(self.ranges)
@@ -244,6 +254,8 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
     impulse = u if isinstance(u, TipImpulse) else None
     uc = None if impulse is not None else u
     gain, ref = _feedback(controller)
+    if beam.n_elements <= 64:
+        beam = beam.with_slots(2)  # the adaptive kernel keeps 7 stage vectors: 2 slots per lane avoid spills
     sysm, keep = beam.make_system(B, drag=drag, gravity=grav, u_const=uc, impulse=impulse, gain=gain, ref=ref)
     dev = beam.device
     t = torch.full((B,), t0, dtype=torch.float64, device=dev)

@@ -98,6 +98,8 @@ typedef struct crb_system_t {
   /* FullStateLinear (control/full_state_linear.py:58): u_c = gain @ (ref - x) */
   const double* gain;       /* [n, 2n] shared gain, or NULL */
   const double* ref;        /* [2n] shared reference, NULL = 0 */
+  const double* gain_frag;  /* [6m][(3m+1)/2][32] gain re-tiled as FP64 mma B-fragments (crb_gain_fragments),
+                               used when plan.g == 4 (8 members per warp = the 8 rows of mma.m8n8k4); else NULL */
   /* additive external generalized force (user torch callables evaluated between launches) */
   const double* f_ext;      /* [B, n] or NULL */
   /* dispatch hints filled by the host layer from the parameter table */
@@ -154,6 +156,13 @@ int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double*
              double* h_abs, double t_bound, double rtol, double atol, const double* t_eval,
              int32_t n_eval, double* Y_eval, int32_t* status, int64_t* counters,
              int32_t max_attempts, void* stream);
+
+/* Host only.  Re-tile a shared feedback gain[n,2n] (control/full_state_linear.py:58) into the
+ * B-fragment order of mma.sync.m8n8k4.f64 for the lane layout of `plan` (requires plan->g == 4):
+ * out[kt][nt][lane], kt < 6m (k-tile = the kt-th own state value of each of the 4 lanes of a member),
+ * nt < (3m+1)/2 (n-tile = own position DOFs 2nt, 2nt+1 of each lane).  Returns the number of doubles
+ * written (out may be NULL to query), or a negative error code. */
+int64_t crb_gain_fragments(const crb_plan_t* plan, const double* gain_host, double* out_host);
 
 /* Dense BC-reduced matrices for one parameter set (host convenience for LQR synthesis;
  * replaces get_mass_matrix / get_stiffness_matrix, euler_bernoulli_beam.py:357-361,422-511).

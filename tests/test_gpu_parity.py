@@ -240,3 +240,50 @@ def test_rk4_paired_linear_kernel(N, B):
     b = bo.BeamOracle(spec)
     ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, np.zeros(n)), x0[i], 0.0, e.h, steps)
     assert block_err(out["paired"][0][i], ref, n) < 1e-9
+
+
+@pytest.mark.parametrize("N", [6, 10, 13])
+def test_feedback_tensor_core_path_matches_scalar_path(N):
+    """u_c = K (r - x): FP64 mma path (4 lanes per member) vs the shared-memory scalar path (other
+    lane layouts) vs the oracle, with a non-zero reference, gravity, drag and an impulse."""
+    from continuum_robot_b200 import FullStateLinear, TipImpulse
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    rng = np.random.default_rng(N)
+    spec = bo.BeamSpec.uniform(N)
+    fs = bo.ForceSpec(1000.0, True, (0.3, -9.81, 0.0), True)
+    b = bo.BeamOracle(spec, fs)
+    n = b.n
+    K = rng.standard_normal((n, 2 * n)) * 0.5  # small enough for h = 5e-6 to stay inside RK4's stability region
+    ref = rng.standard_normal(2 * n) * 1e-3
+    par = np.stack([spec.length, spec.elastic_modulus, spec.moment_inertia, spec.density, spec.cross_area,
+                    spec.wetted_area, spec.drag_coef], axis=1)[None]
+    B = 21
+    x0 = np.concatenate([1e-3 * rng.standard_normal((B, n)), 1e-1 * rng.standard_normal((B, n))], axis=1)
+    amp = np.linspace(1.0, 5.0, B)
+    res = {}
+    for slots in (2, 4, 1):
+        beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N), 1000.0, True, (0.3, -9.81, 0.0),
+                             max_slots_per_lane=slots)
+        ctrl = FullStateLinear(torch.from_numpy(K).cuda(), reference=torch.from_numpy(ref).cuda())
+        X = torch.from_numpy(x0).cuda()
+        imp = TipImpulse(torch.from_numpy(amp).cuda(), duration=1e-4)
+        # explicit system: no automatic re-layout, so every lane decomposition is really exercised
+        drag, grav, _ = beam._active_forces()
+        system = beam.make_system(B, drag=drag, gravity=grav, impulse=imp, gain=ctrl.gain_matrix, ref=ctrl.reference)
+        rk4_steps(beam, X, 0.0, 5e-6, 40, system=system)
+        res[(int(beam._plan.m), int(beam._plan.g))] = X.cpu().numpy()
+    assert any(g == 4 for (_, g) in res) and any(g != 4 for (_, g) in res), list(res)
+    vals = list(res.values())
+    for v in vals[1:]:
+        assert max(block_err(v[i], vals[0][i], n) for i in range(B)) < 1e-11
+    i = 7
+
+    def f(t, x):
+        u = np.zeros(n)
+        if t < 1e-4:
+            u[-2] = amp[i]
+        return b.rhs(t, x, u + bo.full_state_feedback(K, x, ref))
+
+    assert block_err(vals[0][i], bo.rk4_solve(f, x0[i], 0.0, 5e-6, 40), n) < 1e-9

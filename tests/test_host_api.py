@@ -22,9 +22,9 @@ def _lib():
 def test_library_exports_every_declared_symbol():
     """Every function declared in include/crb.h is exported by libcrb.so (no compute calls)."""
     hdr = open(os.path.join(ROOT, "include", "crb.h")).read()
-    names = set(re.findall(r"^(?:int|const char\*)\s+(crb_\w+)\s*\(", hdr, flags=re.M))
+    names = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(crb_\w+)\s*\(", hdr, flags=re.M))
     assert names >= {"crb_version", "crb_last_error", "crb_plan", "crb_assemble", "crb_rhs", "crb_rk4", "crb_rk45",
-                     "crb_dense_matrices"}
+                     "crb_dense_matrices", "crb_gain_fragments"}
     L = _lib()
     lib = L.load()
     for n in names:
@@ -237,3 +237,28 @@ def test_no_cpu_fallback():
     src = "".join(open(os.path.join(ROOT, "continuum_robot_b200", f)).read()
                   for f in os.listdir(os.path.join(ROOT, "continuum_robot_b200")) if f.endswith(".py"))
     assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_gain_fragments_layout():
+    """crb_gain_fragments: every gain entry appears exactly once at the (k-tile, n-tile, lane) slot
+    the mma layout prescribes; plans without 4 lanes per member are rejected."""
+    L = _lib()
+    lib = L.load()
+    rc, p = _plan(6, [1] + [0] * 6, 2)
+    assert rc == 0 and (p.m, p.g) == (2, 4)
+    n = p.n_free
+    gain = np.arange(n * 2 * n, dtype=np.float64).reshape(n, 2 * n) + 1.0
+    cnt = lib.crb_gain_fragments(C.byref(p), None, None)
+    assert cnt == 12 * 3 * 32
+    out = np.zeros(cnt)
+    assert lib.crb_gain_fragments(C.byref(p), gain.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == cnt
+    fr = out.reshape(12, 3, 32)
+    assert sorted(fr[fr != 0].tolist()) == sorted(gain.ravel().tolist())
+    red = np.ctypeslib.as_array(p.red_index)
+    # k-tile 4 = own value #4 (slot 1, dof 1) of source lane 2; n-tile 1, element 0 = own dof #2 of dest lane 2
+    lane = 2 + 4 * (2 * 2 + 0)
+    assert fr[4, 1, lane] == gain[red[3 * (2 * 2) + 2], red[3 * (2 * 2) + 4]]
+    assert fr[6 + 4, 1, lane] == gain[red[3 * (2 * 2) + 2], n + red[3 * (2 * 2) + 4]]
+    assert not fr[:, :, 4 * 6:].any()  # destination lane 3 owns only phantom slots (6 active of 8)
+    rc, p2 = _plan(6, [1] + [0] * 6, 0)
+    assert lib.crb_gain_fragments(C.byref(p2), None, None) < 0 and b"4 lanes" in lib.crb_last_error()
