@@ -60,6 +60,7 @@ class CrbSystem(C.Structure):
         ("gain_frag", C.c_void_p),
         ("f_ext", C.c_void_p),
         ("all_linear", C.c_int32),
+        ("all_nonlinear", C.c_int32),
         ("uniform_mass", C.c_int32),
         ("force_general", C.c_int32),
         ("force_staged", C.c_int32),

@@ -256,6 +256,18 @@ struct RhsFlags {
   bool drag, grav_slot, grav_generic, mask, uconst, impulse, gain, fext;
 };
 
+// Compile-time feature sets: a kernel instantiated for a feature set contains only that code
+// (the full RHS is > 60 KB of SASS; the instruction cache is 32 KB).  The host picks the smallest
+// set that covers what the system enables.
+enum : unsigned {
+  CRB_F_LINEAR = 1, CRB_F_NONLIN = 2, CRB_F_DRAG = 4, CRB_F_GRAVS = 8, CRB_F_GRAVG = 16, CRB_F_MASK = 32,
+  CRB_F_INPUT = 64, CRB_F_GAINM = 128, CRB_F_GAINS = 256, CRB_F_ALL = 511,
+  // profile A: linear elements, slot gravity, inputs, tensor-core feedback (configs 1, 5)
+  CRB_F_PROFILE_A = CRB_F_LINEAR | CRB_F_GRAVS | CRB_F_INPUT | CRB_F_GAINM,
+  // profile B: nonlinear elements, drag, slot gravity, inputs (configs 2, 4)
+  CRB_F_PROFILE_B = CRB_F_NONLIN | CRB_F_DRAG | CRB_F_GRAVS | CRB_F_INPUT,
+};
+
 __device__ __forceinline__ RhsFlags make_flags(const crb_system_t& s, const KPlan& p) {
   RhsFlags f;
   f.drag = s.drag != nullptr;
@@ -306,8 +318,9 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
 }
 
 // Gravity contribution of one pseudo-segment (gravity_forces.py:117-125).
-__device__ __forceinline__ void grav_pair(double phi, double hm, double gx, double gy, double& fa,
-                                          double& ft) {
+// (not inlined: one copy of the double-precision sincos in the instruction stream)
+static __device__ __noinline__ void grav_pair(double phi, double hm, double gx, double gy, double& fa,
+                                       double& ft) {
   double sn, cs;
   sincos(phi, &sn, &cs);
   fa = fma(cs, gx, sn * gy) * hm;
@@ -315,11 +328,21 @@ __device__ __forceinline__ void grav_pair(double phi, double hm, double gx, doub
 }
 
 // a = M^-1 ( -k(q) + f(x) + u(t) ) for the lane's slots.  q, v: stage state; out: acceleration.
-template <int M>
-__device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system_t& S, const RhsFlags F,
+template <int M, unsigned FEAT = CRB_F_ALL>
+__device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system_t& S, const RhsFlags F0,
                                            const double (&q)[M][3], const double (&v)[M][3],
                                            double t, double (&acc)[M][3]) {
   const int G = L.G;
+  RhsFlags F;
+  F.drag = (FEAT & CRB_F_DRAG) && F0.drag;
+  F.grav_slot = (FEAT & CRB_F_GRAVS) && F0.grav_slot;
+  F.grav_generic = (FEAT & CRB_F_GRAVG) && F0.grav_generic;
+  F.mask = (FEAT & CRB_F_MASK) && F0.mask;
+  F.uconst = (FEAT & CRB_F_INPUT) && F0.uconst;
+  F.impulse = (FEAT & CRB_F_INPUT) && F0.impulse;
+  F.fext = (FEAT & CRB_F_INPUT) && F0.fext;
+  F.gain = (FEAT & (CRB_F_GAINM | CRB_F_GAINS)) && F0.gain;
+  constexpr bool kLin = (FEAT & CRB_F_LINEAR) != 0, kNl = (FEAT & CRB_F_NONLIN) != 0;
   // halo: q of the slot left of this lane's first slot (zero at the root / outside the beam)
   double qh[3];
 #pragma unroll
@@ -336,11 +359,11 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
 #pragma unroll
   for (int j = 0; j < M; ++j) {
     if (j == 0) {
-      if (L.et[0] == CRB_ELEM_LINEAR) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
-      else if (L.et[0] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
+      if (kLin && L.et[0] == CRB_ELEM_LINEAR) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
+      else if (kNl && L.et[0] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
     } else {
-      if (L.et[j] == CRB_ELEM_LINEAR) elem_linear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
-      else if (L.et[j] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      if (kLin && L.et[j] == CRB_ELEM_LINEAR) elem_linear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      else if (kNl && L.et[j] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
     }
     if (F.grav_slot) {
       // pseudo-segment between slot s-1 and s in REDUCED numbering
@@ -378,7 +401,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   // dense [8 x 2n] x [2n x n] product: mma.sync.m8n8k4.f64 with rows = members (4 lanes each,
   // plan.g == 4), k-tiles = the lanes' own state values (no shuffle needed to build A) and n-tiles
   // = the lanes' own position DOFs (the C fragment lands where the force is consumed).
-  const bool gain_mma = F.gain && S.gain_frag != nullptr && G == 4;
+  const bool gain_mma = (FEAT & CRB_F_GAINM) && F.gain && S.gain_frag != nullptr && G == 4;
   if (gain_mma) {
     constexpr int KT = 6 * M, NT = (3 * M + 1) / 2;
     double ev[KT];
@@ -409,7 +432,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   }
 
   // ---- reduced-vector scratch paths: feedback gain (other lane layouts) and generic-BC gravity ----
-  if ((F.gain && !gain_mma) || F.grav_generic) {
+  if (((FEAT & CRB_F_GAINS) && F.gain && !gain_mma) || F.grav_generic) {
     double* e = L.scratch;  // [2n]: e = x (positions then velocities) in reduced order
     __syncwarp();
 #pragma unroll
@@ -422,7 +445,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
         }
     __syncwarp();
     const int n = L.n;
-    if (F.gain && !gain_mma) {
+    if ((FEAT & CRB_F_GAINS) && F.gain && !gain_mma) {
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -440,10 +463,24 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
         }
     }
     if (F.grav_generic) {
-      // gravity_forces.py:97-146 evaluated in REDUCED indices: DOF r = 3k + c gets
-      // the axial (c=0) / transverse (c=1) share of pseudo-segment k (as its start node) and
-      // of pseudo-segment k-1 (as its end node); rotations are read at reduced 3i+2, 3i+5.
+      // gravity_forces.py:97-146 evaluated in REDUCED indices.  Pass 1: the lanes of the
+      // member share the pseudo-segments (one sincos each; rotations read at reduced 3i+2, 3i+5) and
+      // leave (axial, transverse) half-forces in shared memory.  Pass 2: DOF r = 3k + c (c = 0 axial,
+      // 1 transverse) collects segment k (as its start node) and segment k-1 (as its end node).
       const double* hm = S.seg_half_mass + (S.force_shared ? 0ll : (long long)L.member * L.nseg);
+      double* fseg = e + 2 * n;  // [nseg][2]
+      for (int i = L.g; i < L.nseg; i += G) {
+        const int ia = 3 * i + 2, ib = 3 * i + 5;
+        double phi = 0.0;
+        if (ia < n && ib < n) phi = 0.5 * (e[ia] + e[ib]);
+        else if (ia < n) phi = e[ia];
+        else if (ib < n) phi = e[ib];
+        double fa, ft;
+        grav_pair(phi, hm[i], S.gx, S.gy, fa, ft);
+        fseg[2 * i] = fa;
+        fseg[2 * i + 1] = ft;
+      }
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -453,18 +490,8 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
           const int c = r % 3, k = r / 3;
           if (c == 2) continue;
           double tot = 0.0;
-          for (int side = 1; side >= 0; --side) {
-            const int i = k - side;
-            if (i < 0 || i >= L.nseg) continue;
-            const int ia = 3 * i + 2, ib = 3 * i + 5;
-            double phi = 0.0;
-            if (ia < n && ib < n) phi = 0.5 * (e[ia] + e[ib]);
-            else if (ia < n) phi = e[ia];
-            else if (ib < n) phi = e[ib];
-            double fa, ft;
-            grav_pair(phi, hm[i], S.gx, S.gy, fa, ft);
-            tot += (c == 0) ? fa : ft;
-          }
+          if (k - 1 >= 0 && k - 1 < L.nseg) tot += fseg[2 * (k - 1) + c];
+          if (k < L.nseg) tot += fseg[2 * k + c];
           acc[j][d] += tot;
         }
     }

@@ -35,7 +35,8 @@ inline KPlan kplan_of(const crb_plan_t* p) {
 inline SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
   SmemLayout SL;
   SL.mfac_doubles = sys->mass_shared ? (int)plan->mfac_doubles : 0;
-  SL.scratch_doubles = ((sys->gain && !(sys->gain_frag && plan->g == 4)) || sys->grav_mode == 2) ? 2 * plan->n_free : 0;
+  SL.scratch_doubles = ((sys->gain && !(sys->gain_frag && plan->g == 4)) || sys->grav_mode == 2)
+                           ? 2 * plan->n_free + 2 * plan->n_elements : 0;  // reduced state + per-segment gravity
   const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
   *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
   return SL;
@@ -58,6 +59,31 @@ int set_smem(K kernel, size_t bytes, const char* who) {
     case 3: { constexpr int M = 3; __VA_ARGS__; } break;             \
     case 4: { constexpr int M = 4; __VA_ARGS__; } break;             \
     default: return crb_fail(CRB_E_LIMIT, "unsupported slots per lane %d", mval); \
+  }
+
+// feature bits a system needs (see CRB_F_* in crb_device.cuh) and the smallest compiled profile
+inline unsigned crb_needed_features(const crb_plan_t* plan, const crb_system_t* s) {
+  unsigned f = 0;
+  f |= s->all_linear ? CRB_F_LINEAR : (CRB_F_LINEAR | CRB_F_NONLIN);
+  if (s->all_nonlinear) f = (f & ~CRB_F_LINEAR) | CRB_F_NONLIN;
+  if (s->drag) f |= CRB_F_DRAG;
+  if (s->grav_mode == 1) f |= CRB_F_GRAVS;
+  if (s->grav_mode == 2) f |= CRB_F_GRAVG;
+  if (plan->has_mask) f |= CRB_F_MASK;
+  if (s->u_const || s->imp_amp || s->f_ext) f |= CRB_F_INPUT;
+  if (s->gain) f |= (s->gain_frag && plan->g == 4) ? CRB_F_GAINM : CRB_F_GAINS;
+  return f;
+}
+inline unsigned crb_pick_profile(unsigned need) {
+  if ((need & ~CRB_F_PROFILE_A) == 0) return CRB_F_PROFILE_A;
+  if ((need & ~CRB_F_PROFILE_B) == 0) return CRB_F_PROFILE_B;
+  return CRB_F_ALL;
+}
+#define CRB_DISPATCH_PROFILE(need, ...)                                          \
+  switch (crb_pick_profile(need)) {                                              \
+    case CRB_F_PROFILE_A: { constexpr unsigned FEAT = CRB_F_PROFILE_A; __VA_ARGS__; } break; \
+    case CRB_F_PROFILE_B: { constexpr unsigned FEAT = CRB_F_PROFILE_B; __VA_ARGS__; } break; \
+    default: { constexpr unsigned FEAT = CRB_F_ALL; __VA_ARGS__; } break;        \
   }
 
 // launchers implemented in their own translation units (parallel nvcc builds)

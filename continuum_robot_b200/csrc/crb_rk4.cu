@@ -2,7 +2,7 @@
 #include "crb_internal.h"
 
 // Classical RK4, nsteps fused: state, stage state and the running combination stay in registers.
-template <int M>
+template <int M, unsigned FEAT>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
                int nsteps, double* __restrict__ Y, int save_every) {
@@ -22,47 +22,38 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   for (int k = 0; k < nsteps; ++k) {
     const double t = t0 + k * h;
     double qs[M][3], vs[M][3], aq[M][3], av[M][3], a[M][3];
-    // stage 1
-    beam_accel<M>(L, S, F, q, v, t, a);
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        aq[j][d] = fma(h6, v[j][d], q[j][d]);
-        av[j][d] = fma(h6, a[j][d], v[j][d]);
-        qs[j][d] = fma(hh, v[j][d], q[j][d]);
-        vs[j][d] = fma(hh, a[j][d], v[j][d]);
+        qs[j][d] = q[j][d];
+        vs[j][d] = v[j][d];
+        aq[j][d] = q[j][d];
+        av[j][d] = v[j][d];
       }
-    // stage 2
-    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
+    // the stage loop stays rolled: ONE copy of the (large) RHS in the instruction stream
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+      const double ts = t + (st == 0 ? 0.0 : (st == 3 ? h : hh));
+      beam_accel<M, FEAT>(L, S, F, qs, vs, ts, a);
+      const double wgt = (st == 0 || st == 3) ? h6 : h3;  // b = (1/6, 1/3, 1/3, 1/6)
+      const double cn = st == 2 ? h : hh;                 // next stage: x + c k
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          aq[j][d] = fma(wgt, vs[j][d], aq[j][d]);
+          av[j][d] = fma(wgt, a[j][d], av[j][d]);
+          qs[j][d] = fma(cn, vs[j][d], q[j][d]);
+          vs[j][d] = fma(cn, a[j][d], v[j][d]);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
-        av[j][d] = fma(h3, a[j][d], av[j][d]);
-        qs[j][d] = fma(hh, vs[j][d], q[j][d]);
-        vs[j][d] = fma(hh, a[j][d], v[j][d]);
-      }
-    // stage 3
-    beam_accel<M>(L, S, F, qs, vs, t + hh, a);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        aq[j][d] = fma(h3, vs[j][d], aq[j][d]);
-        av[j][d] = fma(h3, a[j][d], av[j][d]);
-        qs[j][d] = fma(h, vs[j][d], q[j][d]);
-        vs[j][d] = fma(h, a[j][d], v[j][d]);
-      }
-    // stage 4
-    beam_accel<M>(L, S, F, qs, vs, t + h, a);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        q[j][d] = fma(h6, vs[j][d], aq[j][d]);
-        v[j][d] = fma(h6, a[j][d], av[j][d]);
+        q[j][d] = aq[j][d];
+        v[j][d] = av[j][d];
       }
     if (Y && save_every > 0 && (k + 1) % save_every == 0) {
       const long long frame = (k + 1) / save_every - 1;
@@ -80,9 +71,12 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
   const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
+  const unsigned need = crb_needed_features(plan, sys);
   CRB_DISPATCH_M(plan->m, {
-    if (int rc = set_smem(crb_rk4_kernel<M>, bytes, "crb_rk4")) return rc;
-    crb_rk4_kernel<M><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every);
+    CRB_DISPATCH_PROFILE(need, {
+      if (int rc = set_smem(crb_rk4_kernel<M, FEAT>, bytes, "crb_rk4")) return rc;
+      crb_rk4_kernel<M, FEAT><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every);
+    });
   });
   return 0;
 }

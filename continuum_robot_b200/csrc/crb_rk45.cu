@@ -15,10 +15,13 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   A.t_eval = t_eval; A.n_eval = n_eval; A.Y_eval = Y_eval; A.status = status; A.counters = counters;
   A.max_attempts = max_attempts;
   const DpTab T = make_dp_tab();
+  const unsigned need = crb_needed_features(plan, sys);
   CRB_DISPATCH_M(plan->m, {
     const size_t total = bytes + sizeof(double) * 21 * M * CRB_THREADS;  // kv stage storage
-    if (int rc = set_smem(crb_rk45_kernel<M>, total, "crb_rk45")) return rc;
-    crb_rk45_kernel<M><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);
+    CRB_DISPATCH_PROFILE(need, {
+      if (int rc = set_smem(crb_rk45_kernel<M, FEAT>, total, "crb_rk45")) return rc;
+      crb_rk45_kernel<M, FEAT><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);
+    });
   });
   return 0;
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ double group_sum(double v, int G) {
   return v;
 }
 
-template <int M>
+template <int M, unsigned FEAT>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   extern __shared__ __align__(16) double smem[];
@@ -139,68 +139,48 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
     ++ie;
   }
 
-  // f0 = f(t, y)
-  beam_accel<M>(L, S, F, q, v, t, a);
-  nfev += 1;
+  // One call site of the (large) RHS: a small state machine walks through
+  //   phase 0  f0 = f(t, y)                      (FSAL seed, nfev 1)
+  //   phase 1  f(t + h0, y + h0 f0)              (select_initial_step, common.py:68-135)
+  //   phase 2  stages s = 1..6 of an attempt     (rk.py:14-72; 6 = y_new with the 5th-order weights)
+  // Every lane of the warp is always in the same phase / stage; members differ only in
+  // `running`, t, h and the accept / reject outcome (predicated).
+  double hsel_h0 = 0.0, hsel_d1 = 0.0;
+  bool step_rejected = false, new_step = true;
+  int attempts = 0, phase = 0, st = 0;
+  double h = 0.0, h2 = 0.0, t_new = t, ts = t;
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) KV(0, j, d) = a[j][d];
+    for (int d = 0; d < 3; ++d) {
+      qs[j][d] = q[j][d];
+      vs[j][d] = v[j][d];
+    }
 
-  // ---- select_initial_step (common.py:68-135), order = 4 ----
-  {
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        if (L.ri[j][d] >= 0) {
-          const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
-          const double yq = q[j][d] / scq, yv = v[j][d] / scv;
-          const double fq = v[j][d] / scq, fv = a[j][d] / scv;
-          s0 += yq * yq + yv * yv;
-          s1 += fq * fq + fv * fv;
-        }
-    const double d0 = sqrt(group_sum(s0, G) * inv_size), d1 = sqrt(group_sum(s1, G) * inv_size);
-    const double interval = fabs(tb - t);
-    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-    h0 = fmin(h0, interval);
+  // stage inputs of stage s from the stored accelerations (position rows use the squared tableau)
+  auto prep_stage = [&](int s) {
+    const double hc = h * T.c[s];
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        qs[j][d] = fma(h0, v[j][d], q[j][d]);
-        vs[j][d] = fma(h0, a[j][d], v[j][d]);
-      }
-    double a1[M][3];
-    beam_accel<M>(L, S, F, qs, vs, t + h0, a1);
-    double s2 = 0.0;
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        if (L.ri[j][d] >= 0) {
-          const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
-          const double dq = (vs[j][d] - v[j][d]) / scq, dv = (a1[j][d] - a[j][d]) / scv;
-          s2 += dq * dq + dv * dv;
+        double sv = 0.0, sq = 0.0;
+        for (int l = 0; l < s; ++l) {
+          const double k = KV(l, j, d);
+          sv = fma(T.a[s][l], k, sv);
+          sq = fma(T.a2[s][l], k, sq);
         }
-    const double d2 = sqrt(group_sum(s2, G) * inv_size) / h0;
-    double h1;
-    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-    else h1 = pow(0.01 / fmax(d1, d2), 0.2);
-    const double hsel = fmin(fmin(100.0 * h0, h1), interval);
-    if (!(h_abs > 0.0)) {  // caller asked for automatic selection
-      h_abs = hsel;
-      nfev += 1;
-    }
-  }
-
-  bool step_rejected = false, new_step = true;
-  int attempts = 0;
-  while (__any_sync(CRB_FULL_MASK, running)) {
+        vs[j][d] = fma(h, sv, v[j][d]);
+        qs[j][d] = fma(h2, sq, fma(hc, v[j][d], q[j][d]));
+      }
+    ts = t + T.c[s] * h;
+  };
+  // start of an attempt (rk.py:111-140); returns false when the warp is done or out of budget
+  auto begin_attempt = [&]() -> bool {
+    if (!__any_sync(CRB_FULL_MASK, running)) return false;
     if (attempts >= A.max_attempts) {
       if (running) status = 1;
-      break;
+      return false;
     }
     ++attempts;
     const double min_step = 10.0 * fabs(next_up(t) - t);
@@ -210,38 +190,90 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
       status = -1;
       running = false;
     }
-    double h = h_abs;
-    double t_new = t + h;
+    h = h_abs;
+    t_new = t + h;
     if (t_new - tb > 0.0) t_new = tb;
     h = t_new - t;
     if (running) h_abs = fabs(h);
-    const double h2 = h * h;
+    h2 = h * h;
+    st = 1;
+    prep_stage(1);
+    return true;
+  };
 
-    // ---- stages 1..6 (6 = y_new with the 5th-order weights) ----
-    for (int s = 1; s <= 6; ++s) {
-      const double hc = h * T.c[s];
+  while (true) {
+    beam_accel<M, FEAT>(L, S, F, qs, vs, ts, a);
+    if (phase == 0) {
+      nfev += 1;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) KV(0, j, d) = a[j][d];
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          if (L.ri[j][d] >= 0) {
+            const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
+            const double yq = q[j][d] / scq, yv = v[j][d] / scv;
+            const double fq = v[j][d] / scq, fv = a[j][d] / scv;
+            s0 += yq * yq + yv * yv;
+            s1 += fq * fq + fv * fv;
+          }
+      const double d0 = sqrt(group_sum(s0, G) * inv_size), d1 = sqrt(group_sum(s1, G) * inv_size);
+      double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+      h0 = fmin(h0, fabs(tb - t));
+      hsel_h0 = h0;
+      hsel_d1 = d1;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          double sv = 0.0, sq = 0.0;
-          for (int l = 0; l < s; ++l) {
-            const double k = KV(l, j, d);
-            sv = fma(T.a[s][l], k, sv);
-            sq = fma(T.a2[s][l], k, sq);
-          }
-          vs[j][d] = fma(h, sv, v[j][d]);
-          qs[j][d] = fma(h2, sq, fma(hc, v[j][d], q[j][d]));
+          qs[j][d] = fma(h0, v[j][d], q[j][d]);
+          vs[j][d] = fma(h0, a[j][d], v[j][d]);
         }
-      beam_accel<M>(L, S, F, qs, vs, t + T.c[s] * h, a);
+      ts = t + h0;
+      phase = 1;
+      continue;
+    }
+    if (phase == 1) {
+      double s2 = 0.0;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) KV(s, j, d) = a[j][d];
+        for (int d = 0; d < 3; ++d)
+          if (L.ri[j][d] >= 0) {
+            const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
+            const double dq = (vs[j][d] - v[j][d]) / scq, dv = (a[j][d] - KV(0, j, d)) / scv;
+            s2 += dq * dq + dv * dv;
+          }
+      const double d2 = sqrt(group_sum(s2, G) * inv_size) / hsel_h0;
+      double h1;
+      if (hsel_d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, hsel_h0 * 1e-3);
+      else h1 = pow(0.01 / fmax(hsel_d1, d2), 0.2);
+      const double hsel = fmin(fmin(100.0 * hsel_h0, h1), fabs(tb - t));
+      if (!(h_abs > 0.0)) {  // caller asked for automatic selection
+        h_abs = hsel;
+        nfev += 1;
+      }
+      phase = 2;
+      if (!begin_attempt()) break;
+      continue;
+    }
+    // ---- phase 2: result of stage st ----
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) KV(st, j, d) = a[j][d];
+    if (st < 6) {
+      ++st;
+      prep_stage(st);
+      continue;
     }
     if (running) nfev += 6;
 
-    // ---- error norm (rk.py:100-105, common.py:63-65) ----
+    // ---- error norm (rk.py:100-105, common.py:63-65); qs, vs hold y_new ----
     double se = 0.0;
 #pragma unroll
     for (int j = 0; j < M; ++j)
@@ -314,6 +346,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
       }
     }
     __syncwarp();
+    if (!begin_attempt()) break;
   }
 
   if (L.active) {

@@ -452,6 +452,7 @@ class BatchedDynamicEulerBernoulliBeam:
         s.elem_type = self._d_etype.data_ptr()
         s.red_index = self._d_red.data_ptr()
         s.all_linear = int(self._all_linear)
+        s.all_nonlinear = int(bool(np.all(self._etype == 1)))
         s.uniform_mass = int(self._uniform_mass)
         s.force_general = int(self.force_general_kernels)
         s.force_staged = int(self.force_staged_kernels)

@@ -104,6 +104,7 @@ typedef struct crb_system_t {
   const double* f_ext;      /* [B, n] or NULL */
   /* dispatch hints filled by the host layer from the parameter table */
   int32_t all_linear;       /* 1: every element is CRB_ELEM_LINEAR */
+  int32_t all_nonlinear;    /* 1: every element is CRB_ELEM_NONLINEAR */
   int32_t uniform_mass;     /* 1: rho*A*L and L identical for every element of every member */
   int32_t force_general;    /* 1: always use the general kernels (testing / comparison) */
   int32_t force_staged;     /* 1: fast path keeps the stage-by-stage kernel (no paired operator form) */
