@@ -80,6 +80,7 @@ _SIGNATURES = {
     ),
     "crb_rhs": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_double,
                           C.c_void_p, C.c_void_p]),
+    "crb_forces": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crb_rk4": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_double,
                           C.c_double, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "crb_rk45": (

@@ -139,6 +139,33 @@ crb_rhs_kernel(KPlan P, crb_system_t S, SmemLayout SL, const double* __restrict_
   store_state<M>(L, dX, v, a);
 }
 
+// built-in force vector f(x)[B, n] (drag + gravity), no stiffness / inputs / solve
+template <int M>
+__global__ void __launch_bounds__(CRB_THREADS)
+crb_forces_kernel(KPlan P, crb_system_t S, SmemLayout SL, const double* __restrict__ X, double* __restrict__ Fout) {
+  extern __shared__ __align__(16) double smem[];
+  const double* mf = stage_mfac(S, P, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mpw = 32 / P.g;
+  const int mloc = warp * mpw + lane / P.g;
+  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  LaneCtx<M> L;
+  load_lane_ctx<M>(L, P, S, member, lane % P.g, mf,
+                   SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  RhsFlags F = make_flags(S, P);
+  F.gain = false;
+  double q[M][3], v[M][3], a[M][3];
+  load_state<M>(L, X, q, v);
+  beam_accel<M, CRB_F_ALL, true>(L, S, F, q, v, 0.0, a);
+  if (!L.active) return;
+  double* f = Fout + (long long)L.member * L.n;
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (L.ri[j][d] >= 0) f[L.ri[j][d]] = a[j][d];
+}
+
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
@@ -172,6 +199,26 @@ extern "C" int crb_rhs(const crb_plan_t* plan, const crb_system_t* sys, const do
   });
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rhs: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const double* X, double* F_out,
+                          void* stream) {
+  if (int rc = check_system("crb_forces", plan, sys)) return rc;
+  if (!X || !F_out) return fail(CRB_E_ARG, "crb_forces: null pointer");
+  size_t bytes;
+  crb_system_t s2 = *sys;
+  s2.gain = nullptr;
+  const SmemLayout SL = smem_layout(plan, &s2, &bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  CRB_DISPATCH_M(plan->m, {
+    if (int rc = set_smem(crb_forces_kernel<M>, bytes, "crb_forces")) return rc;
+    crb_forces_kernel<M><<<grid, CRB_THREADS, bytes, (cudaStream_t)stream>>>(P, s2, SL, X, F_out);
+  });
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_forces: launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -328,7 +328,8 @@ static __device__ __noinline__ void grav_pair(double phi, double hm, double gx, 
 }
 
 // a = M^-1 ( -k(q) + f(x) + u(t) ) for the lane's slots.  q, v: stage state; out: acceleration.
-template <int M, unsigned FEAT = CRB_F_ALL>
+// ONLY_FORCES: skip stiffness, inputs and the mass solve -> acc = built-in force vector f(x)
+template <int M, unsigned FEAT = CRB_F_ALL, bool ONLY_FORCES = false>
 __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system_t& S, const RhsFlags F0,
                                            const double (&q)[M][3], const double (&v)[M][3],
                                            double t, double (&acc)[M][3]) {
@@ -358,7 +359,8 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
 
 #pragma unroll
   for (int j = 0; j < M; ++j) {
-    if (j == 0) {
+    if (ONLY_FORCES) {
+    } else if (j == 0) {
       if (kLin && L.et[0] == CRB_ELEM_LINEAR) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
       else if (kNl && L.et[0] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
     } else {
@@ -498,7 +500,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   }
 
   // ---- inputs u(t): constant part, impulse, external force (dynamic_beam_model.py:357-362) ----
-  if (F.uconst || F.fext || F.impulse) {
+  if (!ONLY_FORCES && (F.uconst || F.fext || F.impulse)) {
     const long long mo = (long long)L.member * L.n;
     const bool imp_on = F.impulse && (t < S.imp_duration);
     const double amp = imp_on ? S.imp_amp[L.member] : 0.0;
@@ -523,7 +525,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
       for (int d = 0; d < 3; ++d)
         if (L.ri[j][d] < 0) acc[j][d] = 0.0;
   }
-  mass_solve<M>(acc, L.mc, L.levels);
+  if (!ONLY_FORCES) mass_solve<M>(acc, L.mc, L.levels);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -571,24 +571,15 @@ class BatchedDynamicEulerBernoulliBeam:
         return out
 
     def _builtin_forces(self, x, drag, gravity):
-        """Force vector of one built-in component: M * (rhs_with - rhs_without) is avoided by
-        evaluating the component through the kernel with unit mass bypass is not available, so
-        the component is reported through the difference of accelerations mapped back by M."""
+        """compute_forces(x, t) of a built-in component: crb_forces with only that component on."""
         torch = _torch()
-        x, squeeze = self._as_state(x)
-        B = x.shape[0]
-        s1, k1 = self.make_system(B, drag=drag, gravity=gravity)
-        s0, k0 = self.make_system(B)
-        a1 = torch.empty_like(x)
-        a0 = torch.empty_like(x)
-        lib = _lib.load()
+        xs, squeeze = self._as_state(x)
+        B = xs.shape[0]
+        sysm, keep = self.make_system(B, drag=drag, gravity=gravity)
+        out = torch.zeros((B, self.n_free), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(lib.crb_rhs(C.byref(self._plan), C.byref(s1), x.data_ptr(), 0.0, a1.data_ptr(), self._stream()))
-            _lib.check(lib.crb_rhs(C.byref(self._plan), C.byref(s0), x.data_ptr(), 0.0, a0.data_ptr(), self._stream()))
-        n = self.n_free
-        Mmat = torch.from_numpy(self.beam_model.get_mass_matrix(0)).to(self.device)
-        f = (a1[:, n:] - a0[:, n:]) @ Mmat.T
-        return f[0] if squeeze else f
+            _lib.check(_lib.load().crb_forces(C.byref(self._plan), C.byref(sysm), xs.data_ptr(), out.data_ptr(), self._stream()))
+        return out[0] if squeeze else out
 
     # -- reference API ------------------------------------------------------------------------------
     def create_system_func(self, forces_func: Callable = None) -> None:

@@ -140,6 +140,11 @@ int crb_assemble(const crb_plan_t* plan, const double* params, int32_t n_param_s
 int crb_rhs(const crb_plan_t* plan, const crb_system_t* sys, const double* X, double t,
             double* dX, void* stream);
 
+/* F_out[B,n] = sum of the enabled built-in force components at state X (drag, gravity), i.e.
+ * ForceRegistry.create_aggregated_function()(x, t) restricted to the fused components
+ * (models/force_registry.py:51-81, fluid_forces.py:103-142, gravity_forces.py:66-148). */
+int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const double* X, double* F_out, void* stream);
+
 /* Classical fixed-step RK4 (north_star R1), nsteps steps fused in one launch, in place on X.
  * t_k = t0 + k h; inputs evaluated at stage times.  If Y_out != NULL the state after every
  * save_every-th step is stored at Y_out[(k/save_every - 1), B, 2n]. */

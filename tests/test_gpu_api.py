@@ -149,8 +149,8 @@ def test_builtin_force_objects_compute_forces():
     fg = grav.compute_forces(X, 0.0).cpu().numpy()
     for i in range(6):
         x = RHS[name + "/X"][i]
-        assert np.abs(fd[i] - b.drag(x)).max() <= 1e-9 * max(np.abs(b.drag(x)).max(), 1e-30)
-        assert np.abs(fg[i] - b.gravity(x)).max() <= 1e-9 * np.abs(b.gravity(x)).max()
+        assert np.abs(fd[i] - b.drag(x)).max() <= 1e-14 * max(np.abs(b.drag(x)).max(), 1e-30)
+        assert np.abs(fg[i] - b.gravity(x)).max() <= 1e-14 * np.abs(b.gravity(x)).max()
 
 
 def test_rk4_unfused_user_force_and_trajectory_output():

@@ -1,0 +1,101 @@
+"""GPU edge cases: extreme sizes, ragged / single-member ensembles, argument errors, failure status."""
+
+import numpy as np
+import pytest
+
+from helpers import block_err, make_gpu_beam
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _uniform_par(N, B=1, seed=0):
+    from continuum_robot_b200 import ensembles as ens
+
+    m = ens.material()
+    rng = np.random.default_rng(seed)
+    par = np.zeros((B, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = m["E"] * np.exp(0.1 * rng.standard_normal((B, N)))
+    par[:, :, 5], par[:, :, 6] = m["wetted_area"], m["drag_coef"]
+    return par
+
+
+@pytest.mark.parametrize("N,B,nl", [(1, 1, False), (1, 3, True), (2, 1, True), (128, 2, False), (128, 1, True), (97, 5, True)])
+def test_extreme_sizes_match_oracle(N, B, nl):
+    """Single element, single member, the 128-node limit of one lane group, phantom-padded sizes."""
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    par = _uniform_par(N, B, seed=N)
+    et = np.full(N, 1 if nl else 0)
+    beam = make_gpu_beam(par, et, np.array([1] + [0] * N), 1000.0 if nl else 0.0, nl)
+    n = beam.n_free
+    rng = np.random.default_rng(1)
+    x0 = np.concatenate([1e-4 * rng.standard_normal((B, n)), 1e-2 * rng.standard_normal((B, n))], axis=1)
+    X = torch.from_numpy(x0).cuda()
+    h, steps = 5e-6, 6
+    rk4_steps(beam, X, 0.0, h, steps)
+    got = X.cpu().numpy()
+    i = B - 1
+    spec = bo.BeamSpec.uniform(N, elem_type=bo.NONLINEAR if nl else bo.LINEAR)
+    spec.elastic_modulus = par[i, :, 1].copy()
+    b = bo.BeamOracle(spec, bo.ForceSpec(1000.0, nl, (0.0, -9.81, 0.0), nl))
+    ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, np.zeros(n)), x0[i], 0.0, h, steps)
+    assert block_err(got[i], ref, n) < 1e-9
+
+
+def test_size_and_argument_errors():
+    from continuum_robot_b200 import BatchedDynamicEulerBernoulliBeam, solve_ensemble
+    from continuum_robot_b200.integrate import rk4_steps
+
+    with pytest.raises(ValueError, match="limit"):
+        make_gpu_beam(_uniform_par(129), np.zeros(129, dtype=int), np.array([1] + [0] * 129))
+    beam = make_gpu_beam(_uniform_par(4, 3), np.zeros(4, dtype=int), np.array([1, 0, 0, 0, 0]))
+    n = beam.n_free
+    X = torch.zeros(3, 2 * n, dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError, match="positive and finite"):
+        rk4_steps(beam, X, 0.0, -1.0, 3)
+    with pytest.raises(ValueError, match="parameter sets"):
+        rk4_steps(beam, torch.zeros(5, 2 * n, dtype=torch.float64, device="cuda"), 0.0, 1e-5, 1)
+    before = X.clone()
+    rk4_steps(beam, X, 0.0, 1e-5, 0)  # zero steps is a no-op
+    assert torch.equal(X, before)
+    with pytest.raises(ValueError, match="increasing"):
+        solve_ensemble(beam, (1.0, 0.0), X, method="RK4", h=1e-5)
+    with pytest.raises(ValueError, match="rtol"):
+        solve_ensemble(beam, (0.0, 1e-4), X, method="RK45", rtol=0.0)
+    with pytest.raises(ValueError, match="shape"):
+        solve_ensemble(beam, (0.0, 1e-4), X[:, :-1], method="RK45")
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        BatchedDynamicEulerBernoulliBeam({"params": _uniform_par(4), "type": ["linear"] * 4}, device="cpu")
+
+
+def test_rk45_reports_failure_per_member_instead_of_raising():
+    """A member whose state is non-finite fails alone with status -1 (SciPy: 'Required step size is
+    less than spacing between numbers'); the other members finish normally."""
+    from continuum_robot_b200 import solve_ensemble
+
+    beam = make_gpu_beam(_uniform_par(4, 4), np.ones(4, dtype=int), np.array([1, 0, 0, 0, 0]), 1000.0, True)
+    n = beam.n_free
+    X0 = torch.zeros(4, 2 * n, dtype=torch.float64, device="cuda")
+    X0[2, 1] = float("nan")
+    res = solve_ensemble(beam, (0.0, 1e-3), X0, method="RK45", rtol=1e-6, atol=1e-9)
+    st = res.status.cpu().numpy()
+    assert not res.success and st[2] == -1 and np.all(st[[0, 1, 3]] == 0)
+    assert "step size" in res.message
+    assert torch.isfinite(res.y[[0, 1, 3]]).all()
+
+
+def test_rk45_attempt_budget_and_resume():
+    """max_attempts bounds one launch (status 1); relaunching from (x, t, h) reaches t_bound."""
+    from continuum_robot_b200 import solve_ensemble
+
+    beam = make_gpu_beam(_uniform_par(6, 2), np.zeros(6, dtype=int), np.array([1] + [0] * 6), 0.0, True)
+    n = beam.n_free
+    X0 = torch.zeros(2, 2 * n, dtype=torch.float64, device="cuda")
+    full = solve_ensemble(beam, (0.0, 2e-3), X0, method="RK45", rtol=1e-6, atol=1e-9)
+    part = solve_ensemble(beam, (0.0, 2e-3), X0, method="RK45", rtol=1e-6, atol=1e-9, max_attempts=5)
+    assert not part.success and torch.all(part.status == 1) and torch.all(part.t_final < 2e-3)
+    assert torch.all(part.naccept + part.nreject == 5)
+    assert full.success and torch.all(full.naccept + full.nreject > 5)

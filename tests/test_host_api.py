@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     """Every function declared in include/crb.h is exported by libcrb.so (no compute calls)."""
     hdr = open(os.path.join(ROOT, "include", "crb.h")).read()
     names = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(crb_\w+)\s*\(", hdr, flags=re.M))
-    assert names >= {"crb_version", "crb_last_error", "crb_plan", "crb_assemble", "crb_rhs", "crb_rk4", "crb_rk45",
+    assert names >= {"crb_version", "crb_last_error", "crb_plan", "crb_assemble", "crb_rhs", "crb_forces", "crb_rk4", "crb_rk45",
                      "crb_dense_matrices", "crb_gain_fragments"}
     L = _lib()
     lib = L.load()
