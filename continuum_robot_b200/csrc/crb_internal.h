@@ -79,6 +79,10 @@ inline unsigned crb_pick_profile(unsigned need) {
   if ((need & ~CRB_F_PROFILE_B) == 0) return CRB_F_PROFILE_B;
   return CRB_F_ALL;
 }
+// (slots per lane, log2 lanes per member) shapes that get fully specialised profile kernels:
+// N = 20 (3,3); N = 64 (4,4) and (2,5); N = 6 (2,2) and (3,1); N = 10 (3,2); N = 32 (4,3) and (2,4)
+#define CRB_SPECIALISED_SHAPES(X) X(3, 3) X(4, 4) X(2, 5) X(2, 2) X(3, 1) X(3, 2) X(4, 3) X(2, 4)
+
 #define CRB_DISPATCH_PROFILE(need, ...)                                          \
   switch (crb_pick_profile(need)) {                                              \
     case CRB_F_PROFILE_A: { constexpr unsigned FEAT = CRB_F_PROFILE_A; __VA_ARGS__; } break; \

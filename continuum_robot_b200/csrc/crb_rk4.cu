@@ -2,19 +2,28 @@
 #include "crb_internal.h"
 
 // Classical RK4, nsteps fused: state, stage state and the running combination stay in registers.
-template <int M, unsigned FEAT>
+// LV >= 0: lanes per member = 1 << LV known at compile time (constant shuffle widths and
+// shared-memory offsets); LV = -1: generic.
+template <int M, unsigned FEAT, int LV>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
                int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
   const double* mf = stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mpw = 32 / P.g;
-  const int mloc = warp * mpw + lane / P.g;
+  const int Gk = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g;
+  const int mpw = 32 / Gk;
+  const int mloc = warp * mpw + lane / Gk;
   const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
   LaneCtx<M> L;
-  load_lane_ctx<M>(L, P, S, member, lane % P.g, mf,
+  load_lane_ctx<M>(L, P, S, member, lane % Gk, mf,
                    SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  if (LV >= 0) {  // let the compiler see the constants
+    L.G = Gk;
+    L.levels = LV;
+    L.mc.G = Gk;
+    L.mc.scan = L.mc.slot + 2 * CRB_SLOT_PAIRS * (M * Gk);
+  }
   const RhsFlags F = make_flags(S, P);
   double q[M][3], v[M][3];
   load_state<M>(L, X, q, v);
@@ -72,11 +81,23 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const unsigned need = crb_needed_features(plan, sys);
+  const unsigned prof = crb_pick_profile(need);
+#define CRB_RK4_CASE(MM, LL)                                                                                       \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                                   \
+    if (prof == CRB_F_PROFILE_A) {                                                                                  \
+      if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL>, bytes, "crb_rk4")) return rc;                  \
+      crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
+    } else {                                                                                                        \
+      if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_B, LL>, bytes, "crb_rk4")) return rc;                  \
+      crb_rk4_kernel<MM, CRB_F_PROFILE_B, LL><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
+    }                                                                                                               \
+    return 0;                                                                                                       \
+  }
+  CRB_SPECIALISED_SHAPES(CRB_RK4_CASE)
+#undef CRB_RK4_CASE
   CRB_DISPATCH_M(plan->m, {
-    CRB_DISPATCH_PROFILE(need, {
-      if (int rc = set_smem(crb_rk4_kernel<M, FEAT>, bytes, "crb_rk4")) return rc;
-      crb_rk4_kernel<M, FEAT><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every);
-    });
+    if (int rc = set_smem(crb_rk4_kernel<M, CRB_F_ALL, -1>, bytes, "crb_rk4")) return rc;
+    crb_rk4_kernel<M, CRB_F_ALL, -1><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every);
   });
   return 0;
 }

@@ -16,12 +16,25 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   A.max_attempts = max_attempts;
   const DpTab T = make_dp_tab();
   const unsigned need = crb_needed_features(plan, sys);
+  const unsigned prof = crb_pick_profile(need);
+#define CRB_RK45_CASE(MM, LL)                                                                             \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                          \
+    const size_t total = bytes + sizeof(double) * 21 * MM * CRB_THREADS;                                   \
+    if (prof == CRB_F_PROFILE_A) {                                                                         \
+      if (int rc = set_smem(crb_rk45_kernel<MM, CRB_F_PROFILE_A, LL>, total, "crb_rk45")) return rc;       \
+      crb_rk45_kernel<MM, CRB_F_PROFILE_A, LL><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);   \
+    } else {                                                                                               \
+      if (int rc = set_smem(crb_rk45_kernel<MM, CRB_F_PROFILE_B, LL>, total, "crb_rk45")) return rc;       \
+      crb_rk45_kernel<MM, CRB_F_PROFILE_B, LL><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);   \
+    }                                                                                                      \
+    return 0;                                                                                              \
+  }
+  CRB_SPECIALISED_SHAPES(CRB_RK45_CASE)
+#undef CRB_RK45_CASE
   CRB_DISPATCH_M(plan->m, {
     const size_t total = bytes + sizeof(double) * 21 * M * CRB_THREADS;  // kv stage storage
-    CRB_DISPATCH_PROFILE(need, {
-      if (int rc = set_smem(crb_rk45_kernel<M, FEAT>, total, "crb_rk45")) return rc;
-      crb_rk45_kernel<M, FEAT><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);
-    });
+    if (int rc = set_smem(crb_rk45_kernel<M, CRB_F_ALL, -1>, total, "crb_rk45")) return rc;
+    crb_rk45_kernel<M, CRB_F_ALL, -1><<<grid, CRB_THREADS, total, stream>>>(P, *sys, SL, A, T);
   });
   return 0;
 }

@@ -104,19 +104,25 @@ __device__ __forceinline__ double group_sum(double v, int G) {
   return v;
 }
 
-template <int M, unsigned FEAT>
+template <int M, unsigned FEAT, int LV>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   extern __shared__ __align__(16) double smem[];
   const double* mf = stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = P.g, mpw = 32 / G;
+  const int G = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g, mpw = 32 / G;
   const int mloc = warp * mpw + lane / G;
   const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
   LaneCtx<M> L;
   const int mpb = CRB_WARPS_PER_BLOCK * mpw;
   load_lane_ctx<M>(L, P, S, member, lane % G, mf,
                    SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
+  if (LV >= 0) {
+    L.G = G;
+    L.levels = LV;
+    L.mc.G = G;
+    L.mc.scan = L.mc.slot + 2 * CRB_SLOT_PAIRS * (M * G);
+  }
   const RhsFlags F = make_flags(S, P);
   // kv stage storage: [stage 0..6][j][d][thread]
   double* kvs = smem + SL.mfac_doubles + SL.scratch_doubles * mpb + threadIdx.x;
