@@ -31,4 +31,8 @@ def __getattr__(name):
         from . import control
 
         return getattr(control, name)
+    if name in ("tip_displacement", "beam_shapes", "cantilever_frequencies"):
+        from . import outputs
+
+        return getattr(outputs, name)
     raise AttributeError(name)

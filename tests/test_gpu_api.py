@@ -230,3 +230,36 @@ def test_host_pipeline_matches_device_resident_run():
         assert np.array_equal(xh.numpy(), X.cpu().numpy())
     with pytest.raises(ValueError, match="pinned"):
         pipe.run(torch.zeros(B, 2 * beam.n_free, dtype=torch.float64), 0.0, e.h, 1)
+
+
+def test_trajectory_consumers_and_analytic_frequency():
+    """Device-side shape / tip extraction mirror the reference helpers (incl. quirk Q7), and the
+    linear operator reproduces the analytic first cantilever frequency (example_utilities.py:208-240)."""
+    from continuum_robot_b200 import TipImpulse, beam_shapes, cantilever_frequencies, solve_ensemble, tip_displacement
+    from continuum_robot_b200 import ensembles as ens
+
+    m = ens.material()
+    N = 16
+    par = np.zeros((1, N, 7))
+    par[0, :, 0], par[0, :, 1], par[0, :, 2], par[0, :, 3], par[0, :, 4] = m["length"] / 4, m["E"], m["I"], m["rho"], m["A"]
+    par[0, :, 5:] = 1.0
+    beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+    n = beam.n_free
+    X0 = torch.zeros(2, 2 * n, dtype=torch.float64, device="cuda")
+    h, steps = 2e-6, 150000
+    res = solve_ensemble(beam, (0.0, steps * h), X0, method="RK4", h=h, save_every=250,
+                         u=TipImpulse(torch.tensor([0.1, 0.2], dtype=torch.float64, device="cuda"), duration=2e-3))
+    tip = tip_displacement(res.y)
+    assert tip.shape == (2, len(res.t)) and torch.allclose(tip[1], 2 * tip[0], rtol=1e-9, atol=1e-15)  # linearity
+    x, yy = beam_shapes(res.y, N, m["length"] / 4)
+    assert x.shape == yy.shape == (2, len(res.t), N + 1) and torch.all(yy[:, :, 0] == 0)
+    assert torch.equal(yy[:, :, 1:], res.y[:, n + 1 :: 3, :].permute(0, 2, 1))  # velocities, like the reference
+    _, yd = beam_shapes(res.y, N, m["length"] / 4, displacements=True)
+    assert torch.equal(yd[:, :, -1], tip)
+    # dominant frequency of the free response after the impulse vs the analytic first mode
+    sig = tip[0].cpu().numpy()[res.t > 2e-3]
+    dt = 250 * h
+    spec = np.abs(np.fft.rfft((sig - sig.mean()) * np.hanning(len(sig))))
+    f_peak = np.fft.rfftfreq(len(sig), dt)[spec.argmax()]
+    f1 = cantilever_frequencies(N * m["length"] / 4, m["E"], m["I"], m["rho"], m["A"])[0]
+    assert abs(f_peak - f1) <= 1.5 / (len(sig) * dt), (f_peak, f1)
