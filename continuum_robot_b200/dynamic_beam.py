@@ -99,10 +99,10 @@ class TipImpulse:
         self.dof = dof
         self.duration = float(duration)
 
-    def __call__(self, t: float):
+    def as_tensor(self, t: float, n: int):
+        """u(t)[B, n] as a tensor (for code that wants the reference's callable-input form)."""
         torch = _torch()
         amp = self.amplitude
-        n = self._n
         u = torch.zeros(amp.shape[0], n, dtype=torch.float64, device=amp.device)
         if t < self.duration:
             u[:, self.dof] = amp
@@ -335,6 +335,13 @@ class BatchedDynamicEulerBernoulliBeam:
         self.force_registry = ForceRegistry()
         self.input_registry = InputRegistry()
         self._auto_register_forces()
+
+    @property
+    def M_inv(self):
+        """Dense inverse of member 0's mass matrix on the HOST, for inspection only (the reference
+        exposes ``M_inv``, dynamic_beam_model.py:60).  The integration path never forms it: the
+        kernels apply the banded factorisation written by crb_assemble."""
+        return np.linalg.inv(self.beam_model.get_mass_matrix(0))
 
     # -- device assembly ----------------------------------------------------------------------
     def _assemble(self) -> None:

@@ -1,0 +1,105 @@
+"""Parity at BASELINE.json's FULL sizes (config 3: 65,536 members x 32 elements, 1000 RK4 steps;
+config 5: 131,072 members): sampled members against the reference's golden trajectories, plus
+size-independent properties (exact linearity, agreement of independent kernel families)."""
+
+import numpy as np
+import pytest
+
+from helpers import block_err, load, make_gpu_beam
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _cfg3_beam(e):
+    from continuum_robot_b200 import ensembles as ens
+
+    m = ens.material()
+    B, N = e.E.shape
+    par = np.empty((B, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E
+    par[:, :, 5], par[:, :, 6] = m["wetted_area"], m["drag_coef"]
+    return make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+
+
+def test_config3_full_ensemble_against_reference_samples():
+    """The whole 65,536-member ensemble is integrated for 1000 steps exactly as bench.py does
+    (50 fused steps per launch); the 64 members the reference integrated on the CPU must agree
+    <= 1e-9 at steps 250, 500, 750, 1000.  (E differs from the golden run by pandas' CSV rounding,
+    <= 1e-13 relative)"""
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+
+    g = load("cfg3_samples.npz")
+    e = ens.config3()
+    beam = _cfg3_beam(e)
+    n = beam.n_free
+    X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).cuda()
+    idx = torch.from_numpy(g["idx"]).cuda()
+    system = beam.make_system(e.n_members)
+    worst = 0.0
+    for k in range(20):
+        rk4_steps(beam, X, k * 50 * e.h, e.h, 50, system=system)
+        if (k + 1) % 5 == 0:
+            got = X[idx].cpu().numpy()
+            ref = g["Y"][:, (k + 1) // 5 - 1]
+            worst = max(worst, max(block_err(got[i], ref[i], n) for i in range(len(ref))))
+    assert torch.isfinite(X).all()
+    assert worst < 1e-9, worst
+
+
+def test_config3_full_size_linearity_and_kernel_families():
+    """Linear force-free beams: scaling the initial state by 2 scales every trajectory by exactly 2
+    (power-of-two scaling commutes with every FP64 operation of the kernel), and the three
+    independent kernel families (paired / staged / general) agree to <= 1e-11 on all 65,536 members."""
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+
+    e = ens.config3()
+    beam = _cfg3_beam(e)
+    n = beam.n_free
+    x0 = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).cuda()
+    out = {}
+    for mode in ("paired", "staged", "general"):
+        beam.force_staged_kernels = mode == "staged"
+        beam.force_general_kernels = mode == "general"
+        X = x0.clone()
+        rk4_steps(beam, X, 0.0, e.h, 100)
+        out[mode] = X
+    beam.force_staged_kernels = beam.force_general_kernels = False
+    X2 = 2.0 * x0
+    rk4_steps(beam, X2, 0.0, e.h, 100)
+    assert torch.equal(X2, 2.0 * out["paired"])
+    for mode in ("staged", "general"):
+        for sl in (slice(0, n), slice(n, 2 * n)):
+            num = (out[mode][:, sl] - out["paired"][:, sl]).abs().amax(dim=1)
+            den = out["paired"][:, sl].abs().amax(dim=1)
+            assert float((num / den).max()) < 1e-11, mode
+
+
+def test_config5_full_shard_against_reference_samples():
+    """One GPU's shard of config 5 (131,072 members, shared LQR gain on the tensor cores): the 32
+    members of the golden file are planted at the head of the shard and must match <= 1e-9."""
+    from continuum_robot_b200 import FullStateLinear, TipImpulse
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+    from helpers import params_array
+
+    g = load("cfg5_samples.npz")
+    B = 131072
+    e = ens.config5(B)
+    amp = e.impulse_amp.copy()
+    amp[: len(g["amp"])] = g["amp"]
+    beam = make_gpu_beam(params_array(g)[None], g["elem_type"], g["bc"], 0.0, True)
+    n = beam.n_free
+    ctrl = FullStateLinear(torch.from_numpy(g["gain"]).cuda())
+    X = torch.zeros(B, 2 * n, dtype=torch.float64, device="cuda")
+    imp = TipImpulse(torch.from_numpy(amp).cuda())
+    h = float(g["h"])
+    for k in range(4):
+        rk4_steps(beam, X, k * 500 * h, h, 500, u=imp, controller=ctrl)
+        got = X[: len(g["amp"])].cpu().numpy()
+        ref = g["Y"][:, k]
+        assert max(block_err(got[i], ref[i], n) for i in range(len(ref))) < 1e-9
+    assert torch.isfinite(X).all()
