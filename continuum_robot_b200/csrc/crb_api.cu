@@ -233,7 +233,7 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
   // fast path: all-linear, uniform element mass, contiguous plan without phantom slots, no
   // forces and no input other than a tip impulse (BASELINE config 3 shape)
   const bool fast = sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p &&
-                    !sys->drag && sys->grav_mode == 0 && !sys->u_const && !sys->gain && !sys->f_ext &&
+                    !sys->drag && sys->grav_mode == 0 && !sys->gain &&
                     !sys->force_general;
   int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream) : 1;
   if (rc == 1)  // not eligible, or shape not instantiated in the fast family

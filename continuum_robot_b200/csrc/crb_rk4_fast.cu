@@ -11,16 +11,28 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
-  if (!sys->imp_amp && !sys->force_staged) {  // autonomous force-free case: paired operator applications
-    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV>, bytes, "crb_rk4")) return rc;
-    crb_rk4_lin2_kernel<M, LV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, h, nsteps, Y_out, save_every);
-  } else if (sys->imp_amp) {
+  const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
+#define CRB_LIN2(UCV, IMPV)                                                                              \
+  {                                                                                                      \
+    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV>, bytes, "crb_rk4")) return rc;           \
+    crb_rk4_lin2_kernel<M, LV, UCV, IMPV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, \
+                                                                                    Y_out, save_every);  \
+  }
+  if (!sys->force_staged) {  // paired operator applications (forcing piecewise constant in time)
+    if (uc && imp) CRB_LIN2(true, true)
+    else if (uc) CRB_LIN2(true, false)
+    else if (imp) CRB_LIN2(false, true)
+    else CRB_LIN2(false, false)
+  } else if (uc) {
+    return 1;  // the stage-by-stage fast kernel has no constant-force path: use the general kernel
+  } else if (imp) {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
     crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
   } else {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
     crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
   }
+#undef CRB_LIN2
   return 0;
 }
 

@@ -513,9 +513,17 @@ __device__ __forceinline__ void fast_apply2(const FastCtx<M>& C, double (&w)[2][
       for (int d = 0; d < 3; ++d) w[r][j][d] = b[r][j][d];
 }
 
-template <int M, int LV>
+// With a forcing that is piecewise constant in time (constant generalized force UC and / or a
+// tip impulse IMP), c_i = M^-1 u(t_i) at the stage times (c2 = c3):
+//     L = F(q), p = F(v);  a1 = L + c1,  a2 = L + h/2 p + c2;  r1 = F(a1), r2 = F(a2)
+//     a3 = a2 + h^2/4 r1,  a4 = a2 + h/2 p + (c4 - c2) + h^2/2 r2
+//     q+ = q + h v + h^2/6 (a1 + 2 a2) + h^4/24 r1
+//     v+ = v + h/6 (a1 + 5 a2 + h/2 p + c4 - c2) + h^3/12 (r1 + r2)
+// (reduces to the force-free formulas for c = 0).  M^-1 u_const and M^-1 e_k are obtained once per
+// launch by one paired solve.
+template <int M, int LV, bool UC, bool IMP>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
-crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double h, int nsteps,
+crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double t0, double h, int nsteps,
                     double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
   constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
@@ -558,8 +566,38 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
       q[j][d] = xq[3 * j + d];
       v[j][d] = xq[n + 3 * j + d];
     }
-  const double h2 = 0.5 * h * h, h3 = h * h * h / 6.0, h4 = h * h * h * h / 24.0;
+  // forcing in acceleration space: cu = M^-1 (u_const + f_ext), ci = amp * M^-1 e_k
+  double cu[UC ? M : 1][3], ci[IMP ? M : 1][3];
+  if (UC || IMP) {
+    const long long mo = (long long)C.member * n + 3 * s0;
+    const int rel = IMP ? S.imp_dof - 3 * s0 : -1;
+    const double amp = IMP ? S.imp_amp[C.member] : 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double u = 0.0;
+        if (UC && S.u_const) u += S.u_const[mo + 3 * j + d];
+        if (UC && S.f_ext) u += S.f_ext[mo + 3 * j + d];
+        w[0][j][d] = u;
+        w[1][j][d] = (rel == 3 * j + d) ? amp : 0.0;
+      }
+    fast_solve2<M, LV>(w, C);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        if (UC) cu[j][d] = w[0][j][d];
+        if (IMP) ci[j][d] = w[1][j][d];
+      }
+  }
+  const double hh = 0.5 * h, h2 = 0.5 * h * h, h3 = h * h * h / 6.0, h4 = h * h * h * h / 24.0;
+  const double h6 = h / 6.0, hx = h * h / 6.0, h12 = h * h * h / 12.0;
   for (int k = 0; k < nsteps; ++k) {
+    const double t = t0 + k * h;
+    const double g1 = (IMP && t < S.imp_duration) ? 1.0 : 0.0;
+    const double g2 = (IMP && t + hh < S.imp_duration) ? 1.0 : 0.0;
+    const double g4 = (IMP && t + h < S.imp_duration) ? 1.0 : 0.0;
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -570,23 +608,38 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
       fast_apply2<M, LV>(C, w);
-      if (round == 0) {  // w = (a1, p)
+      if (round == 0) {  // w = (L, p)
 #pragma unroll
         for (int j = 0; j < M; ++j)
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            const double a1 = w[0][j][d], p = w[1][j][d];
-            q[j][d] = fma(h3, p, fma(h2, a1, fma(h, v[j][d], q[j][d])));
-            v[j][d] = fma(h2, p, fma(h, a1, v[j][d]));
+            const double Lq = w[0][j][d], p = w[1][j][d];
+            if (!UC && !IMP) {
+              q[j][d] = fma(h3, p, fma(h2, Lq, fma(h, v[j][d], q[j][d])));
+              v[j][d] = fma(h2, p, fma(h, Lq, v[j][d]));
+            } else {
+              const double cuv = UC ? cu[j][d] : 0.0, civ = IMP ? ci[j][d] : 0.0;
+              const double a1 = Lq + fma(g1, civ, cuv);
+              const double a2 = fma(hh, p, Lq) + fma(g2, civ, cuv);
+              q[j][d] = fma(hx, fma(2.0, a2, a1), fma(h, v[j][d], q[j][d]));
+              v[j][d] = fma(h6, fma(5.0, a2, a1) + fma(hh, p, (g4 - g2) * civ), v[j][d]);
+              w[0][j][d] = a1;
+              w[1][j][d] = a2;
+            }
           }
-      } else {  // w = (r, s)
+      } else {  // w = (r, s) or (r1, r2)
 #pragma unroll
         for (int j = 0; j < M; ++j)
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const double r = w[0][j][d], s = w[1][j][d];
-            q[j][d] = fma(h4, r, q[j][d]);
-            v[j][d] = fma(h4, s, fma(h3, r, v[j][d]));
+            if (!UC && !IMP) {
+              q[j][d] = fma(h4, r, q[j][d]);
+              v[j][d] = fma(h4, s, fma(h3, r, v[j][d]));
+            } else {
+              q[j][d] = fma(h4, r, q[j][d]);
+              v[j][d] = fma(h12, r + s, v[j][d]);
+            }
           }
       }
     }

@@ -287,3 +287,62 @@ def test_feedback_tensor_core_path_matches_scalar_path(N):
         return b.rhs(t, x, u + bo.full_state_feedback(K, x, ref))
 
     assert block_err(vals[0][i], bo.rk4_solve(f, x0[i], 0.0, 5e-6, 40), n) < 1e-9
+
+
+@pytest.mark.parametrize("N,B", [(32, 19), (6, 7)])
+def test_rk4_paired_kernel_with_forcing(N, B):
+    """Paired operator form with piecewise-constant forcing: constant generalized force, tip impulse
+    that switches off in the middle of the run (so some steps straddle the switch), and both;
+    against the general kernel (<= 1e-11), the stage-by-stage fast kernel and the oracle (<= 1e-9)."""
+    from continuum_robot_b200 import TipImpulse
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    e = ens.config3(B, N, seed=21)
+    m = ens.material()
+    par = np.zeros((B, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E
+    par[:, :, 5:] = 1.0
+    beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+    n = beam.n_free
+    rng = np.random.default_rng(N)
+    x0 = np.concatenate([e.q0, e.v0], axis=1)
+    U = rng.standard_normal((B, n))
+    amp = np.linspace(0.5, 3.0, B)
+    steps, h = 64, e.h
+    dur = 20.3 * h  # the impulse ends inside step 20: stage times t, t+h/2 are inside, t+h outside
+    for uc, imp in ((True, False), (False, True), (True, True)):
+        def fresh():
+            X = torch.from_numpy(x0).cuda()
+            drag, grav, _ = beam._active_forces()
+            system = beam.make_system(B, u_const=torch.from_numpy(U).cuda() if uc else None,
+                                      impulse=TipImpulse(torch.from_numpy(amp).cuda(), duration=dur) if imp else None)
+            rk4_steps(beam, X, 0.0, h, steps, system=system)
+            return X.cpu().numpy()
+
+        beam.force_general_kernels = beam.force_staged_kernels = False
+        paired = fresh()
+        beam.force_general_kernels = True
+        general = fresh()
+        beam.force_general_kernels = False
+        assert max(block_err(paired[i], general[i], n) for i in range(B)) < 1e-11, (uc, imp)
+        if not uc:
+            beam.force_staged_kernels = True
+            staged = fresh()
+            beam.force_staged_kernels = False
+            assert max(block_err(paired[i], staged[i], n) for i in range(B)) < 1e-11
+        i = B // 2
+        spec = bo.BeamSpec.uniform(N)
+        spec.elastic_modulus = e.E[i].copy()
+        b = bo.BeamOracle(spec)
+
+        def u(t):
+            v = U[i].copy() if uc else np.zeros(n)
+            if imp and t < dur:
+                v[-2] += amp[i]
+            return v
+
+        ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, u), x0[i], 0.0, h, steps)
+        assert block_err(paired[i], ref, n) < 1e-9, (uc, imp)
