@@ -179,6 +179,9 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from continuum_robot_b200.sharding import bind_to_gpu_numa_node
+
+    numa_bound = bind_to_gpu_numa_node(local) if world > 1 else False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, N, S = args.members, args.elements, args.steps_per_launch
@@ -298,6 +301,7 @@ def run_gpu(args):
                     "call": f"HostPipeline.run per {S} fused RK4 steps: H2D state {X.numel() * 8} B (pinned) + kernels + D2H state, "
                             f"{args.e2e_chunks} member chunks on 3 streams", "finite": e2e_ok},
             "gpu_launches": len(chunks(args.steps)),
+            "numa_bound": numa_bound,
             "clocks": clocks,
             "kernel_ms_per_launch": mean_launch,
         }
