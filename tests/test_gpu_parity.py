@@ -346,3 +346,72 @@ def test_rk4_paired_kernel_with_forcing(N, B):
 
         ref = bo.rk4_solve(lambda t, x: b.rhs(t, x, u), x0[i], 0.0, h, steps)
         assert block_err(paired[i], ref, n) < 1e-9, (uc, imp)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_rhs_random_topologies_match_oracle(seed):
+    """Randomised beams (element count, mixed element types, FIXED / PINNED anywhere, non-uniform
+    properties, drag, tilted gravity, per-member parameters) -- RHS vs the oracle, which is itself
+    pinned to the reference on every BC pattern of the golden set.  Tolerance 1e-10 (block inf-norm)."""
+    from oracle import beam_oracle as bo
+
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(1, 14))
+    B = int(rng.integers(1, 6))
+    et = rng.integers(0, 2, N)
+    bc = rng.choice([0, 0, 0, 1, 2], size=N)
+    if rng.random() < 0.6:
+        bc[0] = 1
+    from continuum_robot_b200 import ensembles as ens
+
+    m = ens.material()
+    sc = np.exp(0.3 * rng.standard_normal((B, N, 7)))
+    base = np.array([m["length"], m["E"], m["I"], m["rho"], m["A"], m["wetted_area"], m["drag_coef"]])
+    par = base[None, None, :] * sc
+    if rng.random() < 0.5:  # shared mass / geometry, per-member stiffness only
+        par[:, :, [0, 3, 4, 5, 6]] = par[0:1, :, [0, 3, 4, 5, 6]]
+    fd = float(rng.choice([0.0, 1000.0]))
+    grav = bool(rng.random() < 0.7)
+    gvec = (float(rng.normal()), -9.81, 0.0)
+    slots = int(rng.choice([0, 1, 2, 3]))
+    beam = make_gpu_beam(par, et, np.append(bc, 0), fd, grav, gvec, max_slots_per_lane=slots)
+    n = beam.n_free
+    X = np.concatenate([1e-3 * rng.standard_normal((B, n)), 1e-1 * rng.standard_normal((B, n))], axis=1)
+    U = rng.standard_normal((B, n))
+    Y = beam.get_dynamic_system()(0.1, torch.from_numpy(X).cuda(), torch.from_numpy(U).cuda()).cpu().numpy()
+    for i in range(B):
+        spec = bo.BeamSpec(par[i, :, 0], par[i, :, 1], par[i, :, 2], par[i, :, 3], par[i, :, 4], et, bc, par[i, :, 5], par[i, :, 6])
+        b = bo.BeamOracle(spec, bo.ForceSpec(fd, fd > 0, gvec, grav))
+        assert b.n == n
+        assert block_err(Y[i], b.rhs(0.1, X[i], U[i]), n) < 1e-10, (seed, i, N, list(bc), list(et))
+
+
+def test_rk45_step_sequence_equals_scipy_controller():
+    """GPU RK45 vs the oracle's restated SciPy controller on the same beam: identical accepted /
+    rejected step counts and nfev, outputs equal to ~1e-9 of the tolerance band."""
+    from continuum_robot_b200 import TipImpulse, solve_ensemble
+    from oracle import beam_oracle as bo
+
+    N = 8
+    spec = bo.BeamSpec.uniform(N, elem_type=bo.NONLINEAR)
+    fs = bo.ForceSpec(1000.0, True, (0.0, -9.81, 0.0), True)
+    b = bo.BeamOracle(spec, fs)
+    n = b.n
+    par = np.stack([spec.length, spec.elastic_modulus, spec.moment_inertia, spec.density, spec.cross_area,
+                    spec.wetted_area, spec.drag_coef], axis=1)[None]
+    beam = make_gpu_beam(par, np.ones(N, dtype=int), np.array([1] + [0] * N), 1000.0, True)
+    amps = np.array([0.1, 0.3])
+    te = np.linspace(0.0, 0.004, 9)
+    res = solve_ensemble(beam, (0.0, 0.004), torch.zeros(2, 2 * n, dtype=torch.float64, device="cuda"), method="RK45",
+                         t_eval=te, rtol=1e-6, atol=1e-9, u=TipImpulse(torch.from_numpy(amps).cuda()))
+    for i, amp in enumerate(amps):
+        def u(t, a=amp):
+            v = np.zeros(n)
+            if t < 0.01:
+                v[-2] = a
+            return v
+
+        r = bo.rk45_solve(lambda t, x: b.rhs(t, x, u), (0.0, 0.004), np.zeros(2 * n), t_eval=te, rtol=1e-6, atol=1e-9)
+        assert int(res.nfev[i]) == r.nfev and int(res.naccept[i]) == r.naccept and int(res.nreject[i]) == r.nreject
+        got = res.y[i].cpu().numpy()
+        assert np.all(np.abs(got - r.y) <= 1e-3 * (1e-9 + 1e-6 * np.abs(r.y)))
