@@ -167,6 +167,21 @@ __device__ __forceinline__ void elem_linear(const double4 c, const double (&qa)[
   bB[2] -= fma(c.w, qb[2], R);
 }
 
+// Decimal literals of the reference's nonlinear polynomials (models/segments.py:159-472), kept in
+// constant memory so that every DFMA takes its coefficient as a constant-bank operand (as 64-bit
+// immediates they cost two uniform moves each, 18 % of the issued instructions of the kernel).
+static __constant__ double kNlc[36] = {
+    /* 0 g1 */ 0.0666666666666665, 0.0166666666666667, 0.05,
+    /* 3 g2 */ 0.0666666666666667, 0.6,
+    /* 5 f3 */ 0.0357142857143344, 0.107142857143003, 1.28571428571433, 3.8571428571413, 3.857142857143,
+    /*10    */ 10.2857142857147, 0.1,
+    /*12 f4 */ 0.0285714285714391, 0.0107142857142861, 0.0107142857142719, 0.00714285714286444,
+    /*16    */ 0.0214285714286007, 0.133333333333333, 0.0333333333333333, 0.128571428571433,
+    /*20    */ 0.00357142857143344, 0.128571428571377,
+    /*22 f6 */ 0.00714285714286356, 0.0107142857143003, 0.0107142857142932, 0.021428571428558,
+    /*26    */ 0.0285714285714271, 0.128571428571428,
+    /*28    */ 0, 0, 0, 0, 0, 0, 0, 0};
+
 // nonlinear: c = (EA/L^2, EI/L^2, L, 1/L).  The six polynomials of models/segments.py:159-472
 // rewritten in the scaled variables a = theta1*L, b = theta2*L, d = w1-w2, e = u1-u2 (the
 // monomials group exactly; decimal literals are the reference's).  Node order
@@ -174,6 +189,7 @@ __device__ __forceinline__ void elem_linear(const double4 c, const double (&qa)[
 // segments.py:197-205.
 __device__ __forceinline__ void elem_nonlinear(const double4 c, const double (&qa)[3], const double (&qb)[3],
                                                double (&bA)[3], double (&bB)[3]) {
+  const double* K = kNlc;
   const double al = c.x, de = c.y, L = c.z, iL = c.w;
   const double u1 = qa[0], u2 = qb[0];
   const double a = qa[2] * L, b = qb[2] * L;
@@ -182,47 +198,47 @@ __device__ __forceinline__ void elem_nonlinear(const double4 c, const double (&q
   const double Le = L * e;
   const double a2 = a * a, b2 = b * b, d2 = d * d, ab = a * b;
   // axial pair f1 / f2
-  const double g1 = fma(0.0666666666666665, a, fma(-0.0166666666666667, b, -0.05 * d));
-  const double g2 = fma(0.0166666666666667, a, fma(-0.0666666666666667, b, 0.05 * d));
-  const double g3 = fma(-0.05, a + b, 0.6 * d);
+  const double g1 = fma(K[0], a, fma(-K[1], b, -K[2] * d));
+  const double g2 = fma(K[1], a, fma(-K[3], b, K[2] * d));
+  const double g3 = fma(-K[2], a + b, K[4] * d);
   const double T = fma(a, g1, -b * g2);
   const double f1 = al * (fma(L, u1, -T) - (u2 + d) * g3);
   const double f2 = al * (fma(d, g3, T) - Le);
   // transverse force f3 (= -f5)
   const double apb = a + b;
-  double A3 = 0.0357142857143344 * fma(a2, a, b2 * b);
-  A3 = fma(-0.107142857143003 * ab, apb, A3);
-  A3 = fma(1.28571428571433 * d, a2 + b2, A3);
+  double A3 = K[5] * fma(a2, a, b2 * b);
+  A3 = fma(-K[6] * ab, apb, A3);
+  A3 = fma(K[7] * d, a2 + b2, A3);
   A3 = fma(Le, apb, A3);
-  A3 = fma(-d2, fma(3.8571428571413, a, 3.857142857143 * b), A3);
+  A3 = fma(-d2, fma(K[8], a, K[9] * b), A3);
   A3 = fma(-12.0 * Le, d, A3);
-  A3 = fma(10.2857142857147 * d2, d, A3);
+  A3 = fma(K[10] * d2, d, A3);
   const double D3 = fma(120.0, d, -60.0 * apb);
-  const double f3 = (0.1 * iL) * fma(al, A3, de * D3);
+  const double f3 = (K[11] * iL) * fma(al, A3, de * D3);
   // moment f4 (node 1)
-  double A4 = 0.0285714285714391 * a2 * a;
-  A4 = fma(-0.0107142857142861 * a2, b, A4);
-  A4 = fma(0.0107142857142719 * d, a2 - b2, A4);
-  A4 = fma(0.00714285714286444 * a, b2, A4);
-  A4 = fma(-0.0214285714286007 * ab, d, A4);
-  A4 = fma(Le, fma(-0.133333333333333, a, 0.0333333333333333 * b), A4);
-  A4 = fma(0.128571428571433 * a, d2, A4);
-  A4 = fma(-0.00357142857143344 * b2, b, A4);
-  A4 = fma(0.1 * Le, d, A4);
-  A4 = fma(-0.128571428571377 * d2, d, A4);
+  double A4 = K[12] * a2 * a;
+  A4 = fma(-K[13] * a2, b, A4);
+  A4 = fma(K[14] * d, a2 - b2, A4);
+  A4 = fma(K[15] * a, b2, A4);
+  A4 = fma(-K[16] * ab, d, A4);
+  A4 = fma(Le, fma(-K[17], a, K[18] * b), A4);
+  A4 = fma(K[19] * a, d2, A4);
+  A4 = fma(-K[20] * b2, b, A4);
+  A4 = fma(K[11] * Le, d, A4);
+  A4 = fma(-K[21] * d2, d, A4);
   const double f4 = fma(al, A4, de * fma(4.0, a, fma(2.0, b, -6.0 * d)));
   // moment f6 (node 2)
-  double A6 = -0.00357142857143344 * a2 * a;
-  A6 = fma(0.00714285714286356 * a2, b, A6);
-  A6 = fma(-0.0107142857143003 * a2, d, A6);
-  A6 = fma(-0.0107142857142932 * a, b2, A6);
-  A6 = fma(-0.021428571428558 * ab, d, A6);
-  A6 = fma(Le, fma(0.0333333333333333, a, -0.133333333333333 * b), A6);
-  A6 = fma(0.0285714285714271 * b2, b, A6);
-  A6 = fma(0.0107142857142932 * b2, d, A6);
-  A6 = fma(0.128571428571428 * b, d2, A6);
-  A6 = fma(0.1 * Le, d, A6);
-  A6 = fma(-0.128571428571433 * d2, d, A6);
+  double A6 = -K[20] * a2 * a;
+  A6 = fma(K[22] * a2, b, A6);
+  A6 = fma(-K[23] * a2, d, A6);
+  A6 = fma(-K[24] * a, b2, A6);
+  A6 = fma(-K[25] * ab, d, A6);
+  A6 = fma(Le, fma(K[18], a, -K[17] * b), A6);
+  A6 = fma(K[26] * b2, b, A6);
+  A6 = fma(K[24] * b2, d, A6);
+  A6 = fma(K[27] * b, d2, A6);
+  A6 = fma(K[11] * Le, d, A6);
+  A6 = fma(-K[19] * d2, d, A6);
   const double f6 = fma(al, A6, de * fma(2.0, a, fma(4.0, b, -6.0 * d)));
   bA[0] -= f1;
   bA[1] -= f3;
@@ -361,11 +377,16 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   for (int j = 0; j < M; ++j) {
     if (ONLY_FORCES) {
     } else if (j == 0) {
-      if (kLin && L.et[0] == CRB_ELEM_LINEAR) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
-      else if (kNl && L.et[0] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
+      // single-type feature sets skip the type test: absent elements carry zero coefficients
+      if (kLin && !kNl) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
+      else if (kNl && !kLin) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
+      else if (L.et[0] == CRB_ELEM_LINEAR) elem_linear(L.kc[0], qh, q[0], send, acc[0]);
+      else if (L.et[0] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[0], qh, q[0], send, acc[0]);
     } else {
-      if (kLin && L.et[j] == CRB_ELEM_LINEAR) elem_linear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
-      else if (kNl && L.et[j] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      if (kLin && !kNl) elem_linear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      else if (kNl && !kLin) elem_nonlinear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      else if (L.et[j] == CRB_ELEM_LINEAR) elem_linear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
+      else if (L.et[j] == CRB_ELEM_NONLINEAR) elem_nonlinear(L.kc[j], q[j - 1], q[j], acc[j - 1], acc[j]);
     }
     if (F.grav_slot) {
       // pseudo-segment between slot s-1 and s in REDUCED numbering

@@ -22,7 +22,8 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
     L.G = Gk;
     L.levels = LV;
     L.mc.G = Gk;
-    L.mc.scan = L.mc.slot + 2 * CRB_SLOT_PAIRS * (M * Gk);
+    L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
+    L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * Gk);
   }
   const RhsFlags F = make_flags(S, P);
   double q[M][3], v[M][3];
@@ -83,7 +84,7 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
   const unsigned need = crb_needed_features(plan, sys);
   const unsigned prof = crb_pick_profile(need);
 #define CRB_RK4_CASE(MM, LL)                                                                                       \
-  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                                   \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared) {                                                   \
     if (prof == CRB_F_PROFILE_A) {                                                                                  \
       if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL>, bytes, "crb_rk4")) return rc;                  \
       crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \

@@ -121,7 +121,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
     L.G = G;
     L.levels = LV;
     L.mc.G = G;
-    L.mc.scan = L.mc.slot + 2 * CRB_SLOT_PAIRS * (M * G);
+    L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
+    L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * G);
   }
   const RhsFlags F = make_flags(S, P);
   // kv stage storage: [stage 0..6][j][d][thread]
