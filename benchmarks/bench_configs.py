@@ -80,6 +80,17 @@ def main():
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
             print(json.dumps({"config": "cfg3 general kernel", "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg3m":  # config 3 with PER-MEMBER mass (density varies per member): no shared factors
+            B, steps = 65536, 50
+            e = ens.config3(B, 32)
+            par = params(e, B)
+            par[:, :, 3] *= np.exp(0.1 * np.random.default_rng(5).standard_normal((B, 1)))
+            beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["linear"] * 32})
+            beam.create_system_func(); beam.create_input_func()
+            X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
+            print(json.dumps({"config": "cfg3 with per-member mass (general kernel, factors from L2)",
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg4":  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
             B = 4096
             e = ens.config4(B)

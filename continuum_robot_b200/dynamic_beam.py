@@ -508,7 +508,12 @@ class BatchedDynamicEulerBernoulliBeam:
                 raise ValueError(f"Gain matrix must have shape ({n}, {2 * n}), got {tuple(gain.shape)}")
             gdev = dev64(gain, (n, 2 * n), "gain")
             s.gain = gdev.data_ptr()
-            if int(self._plan.g) == 4:  # shared operator -> FP64 tensor-core fragments (crb_gain_fragments)
+            cache_key = (gdev.data_ptr(), gdev._version)
+            cached = getattr(self, "_gain_frag_cache", None)
+            if int(self._plan.g) == 4 and cached is not None and cached[0] == cache_key:
+                keep.append(cached[1])
+                s.gain_frag = cached[1].data_ptr()
+            elif int(self._plan.g) == 4:  # shared operator -> FP64 tensor-core fragments (crb_gain_fragments)
                 lib = _lib.load()
                 cnt = int(lib.crb_gain_fragments(C.byref(self._plan), None, None))
                 gh = np.ascontiguousarray(gdev.detach().cpu().numpy())
@@ -519,6 +524,7 @@ class BatchedDynamicEulerBernoulliBeam:
                 frd = torch.from_numpy(fr).to(self.device)
                 keep.append(frd)
                 s.gain_frag = frd.data_ptr()
+                self._gain_frag_cache = (cache_key, frd, gdev)  # gdev kept alive so its address stays unique
             if ref is not None:
                 if not isinstance(ref, torch.Tensor):
                     ref = torch.as_tensor(np.asarray(ref, dtype=np.float64))
