@@ -12,9 +12,13 @@
 //    sweep (more DFMA, 2.5x fewer LDS wavefronts than crb_device.cuh::mass_solve).
 //
 //   forward  A: y~_last      (zero incoming)         -> Kogge-Stone scan -> y_last, xhat_in
-//   forward  B: y_s = b_s - O xhat_{s-1},  xhat_s = Sinv_s y_s   (true incoming)
+//   forward  B: y_s = b_s - O Sinv_{s-1} y_{s-1}                  (true incoming; keeps y_s)
 //   backward A: x~_first     (zero incoming)         -> scan -> x_first, x_in
-//   backward B: x_s = xhat_s - Sinv_s (O^T x_{s+1})  (true incoming)
+//   backward B: x_s = Sinv_s (y_s - O^T x_{s+1})                  (true incoming)
+//
+// (10 FP64 operations per slot and sweep; the earlier xhat_s - Sinv_s O^T x_{s+1} form cost 12.)
+// More resident warps do not help: builds capped at 216 / 200 / 168 registers (9 / 10 / 12 warps per
+// SM) measured 10-12 % slower than the 224-register, 8-warp build -- the FP64 pipe is the limiter.
 //
 // Reference behaviour: models/segments.py:32-78, euler_bernoulli_beam.py:163-298,
 // dynamic_beam_model.py:256-272, 343-362 (forces disabled, u = tip impulse or none).
@@ -57,11 +61,11 @@ __device__ __forceinline__ double2 ld_fscan(const FastCtx<M>& C, int level, int 
   return *reinterpret_cast<const double2*>(C.fscan + (((level * 5 + pair) * G + C.g) << 1));
 }
 
-template <int M, int LV>
-__device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& C) {
+// Mass solve of R right-hand sides at once (they share every constant read from shared memory).
+template <int M, int LV, int R>
+__device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const FastCtx<M>& C) {
   constexpr int G = 1 << LV;
   const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
-  // Sinv of the lane's slots stays in registers for the four sweeps
   double s00[M], s01[M], s11[M], su[M];
 #pragma unroll
   for (int j = 0; j < M; ++j) {
@@ -71,89 +75,123 @@ __device__ __forceinline__ void fast_solve(double (&b)[M][3], const FastCtx<M>& 
     s11[j] = c.x;
     su[j] = c.y;
   }
-  // ---- forward A: y~ at the chunk's last slot, zero incoming ----
-  double y0 = b[0][0], y1 = b[0][1], y2 = b[0][2];
+  double y0[R], y1[R], y2[R];
 #pragma unroll
-  for (int j = 1; j < M; ++j) {
-    const double xu = su[j - 1] * y0;
-    const double xw = fma(s00[j - 1], y1, s01[j - 1] * y2);
-    const double xp = fma(s01[j - 1], y1, s11[j - 1] * y2);
-    y0 = fma(-ou, xu, b[j][0]);
-    y1 = fma(-o11, xw, fma(o12, xp, b[j][1]));
-    y2 = fma(-o12, xw, fma(o22, xp, b[j][2]));
-  }
-  double xi0 = 0.0, xi1 = 0.0, xi2 = 0.0;  // xhat of the left neighbour's last slot
-  double cub[LV > 0 ? LV : 1];             // u-scan coefficients of the backward scan (loaded with the forward ones)
+  for (int r = 0; r < R; ++r) { y0[r] = b[r][0][0]; y1[r] = b[r][0][1]; y2[r] = b[r][0][2]; }
+  // ---- forward A ----
+#pragma unroll
+  for (int j = 1; j < M; ++j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double xu = su[j - 1] * y0[r];
+      const double xw = fma(s00[j - 1], y1[r], s01[j - 1] * y2[r]);
+      const double xp = fma(s01[j - 1], y1[r], s11[j - 1] * y2[r]);
+      y0[r] = fma(-ou, xu, b[r][j][0]);
+      y1[r] = fma(-o11, xw, fma(o12, xp, b[r][j][1]));
+      y2[r] = fma(-o12, xw, fma(o22, xp, b[r][j][2]));
+    }
+  double xi0[R], xi1[R], xi2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
+  double cub[LV > 0 ? LV : 1];
   if (G > 1) {
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
       const int d = 1 << l;
-      const double t0 = shfl_up_d(y0, d, G), t1 = shfl_up_d(y1, d, G), t2 = shfl_up_d(y2, d, G);
       const double2 c0 = ld_fscan<M, G>(C, l, 0), c1 = ld_fscan<M, G>(C, l, 1), cu = ld_fscan<M, G>(C, l, 4);
       cub[l] = cu.y;
-      y0 = fma(cu.x, t0, y0);
-      mv2(c0, c1, t1, t2, y1, y2);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double t0 = shfl_up_d(y0[r], d, G), t1 = shfl_up_d(y1[r], d, G), t2 = shfl_up_d(y2[r], d, G);
+        y0[r] = fma(cu.x, t0, y0[r]);
+        mv2(c0, c1, t1, t2, y1[r], y2[r]);
+      }
     }
-    const double xu = su[M - 1] * y0;
-    const double xw = fma(s00[M - 1], y1, s01[M - 1] * y2);
-    const double xp = fma(s01[M - 1], y1, s11[M - 1] * y2);
-    xi0 = shfl_up_d(xu, 1, G);
-    xi1 = shfl_up_d(xw, 1, G);
-    xi2 = shfl_up_d(xp, 1, G);
-    if (C.g == 0) { xi0 = 0.0; xi1 = 0.0; xi2 = 0.0; }
-  }
-  // ---- forward B: true incoming; b[j] <- xhat_j ----
 #pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const double t0 = fma(-ou, xi0, b[j][0]);
-    const double t1 = fma(-o11, xi1, fma(o12, xi2, b[j][1]));
-    const double t2 = fma(-o12, xi1, fma(o22, xi2, b[j][2]));
-    xi0 = su[j] * t0;
-    xi1 = fma(s00[j], t1, s01[j] * t2);
-    xi2 = fma(s01[j], t1, s11[j] * t2);
-    b[j][0] = xi0;
-    b[j][1] = xi1;
-    b[j][2] = xi2;
+    for (int r = 0; r < R; ++r) {
+      const double xu = su[M - 1] * y0[r];
+      const double xw = fma(s00[M - 1], y1[r], s01[M - 1] * y2[r]);
+      const double xp = fma(s01[M - 1], y1[r], s11[M - 1] * y2[r]);
+      xi0[r] = shfl_up_d(xu, 1, G);
+      xi1[r] = shfl_up_d(xw, 1, G);
+      xi2[r] = shfl_up_d(xp, 1, G);
+      if (C.g == 0) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
+    }
   }
-  // ---- backward A: x~ at the chunk's first slot, zero incoming ----
-  double r0 = b[M - 1][0], r1 = b[M - 1][1], r2 = b[M - 1][2];
+  // ---- forward B: true incoming; b[j] <- y_j (the forward-substituted right-hand side) ----
 #pragma unroll
-  for (int j = M - 2; j >= 0; --j) {
-    const double t0 = ou * r0;
-    const double t1 = fma(o11, r1, o12 * r2);
-    const double t2 = -fma(o12, r1, o22 * r2);
-    r0 = fma(-su[j], t0, b[j][0]);
-    r1 = b[j][1] - fma(s00[j], t1, s01[j] * t2);
-    r2 = b[j][2] - fma(s01[j], t1, s11[j] * t2);
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double t0 = fma(-ou, xi0[r], b[r][j][0]);
+      const double t1 = fma(-o11, xi1[r], fma(o12, xi2[r], b[r][j][1]));
+      const double t2 = fma(-o12, xi1[r], fma(o22, xi2[r], b[r][j][2]));
+      b[r][j][0] = t0;
+      b[r][j][1] = t1;
+      b[r][j][2] = t2;
+      if (j < M - 1) {  // xhat_j = Sinv_j y_j feeds the next slot; the last one is only needed by backward A
+        xi0[r] = su[j] * t0;
+        xi1[r] = fma(s00[j], t1, s01[j] * t2);
+        xi2[r] = fma(s01[j], t1, s11[j] * t2);
+      }
+    }
+  // ---- backward A: x~ at the chunk's first slot, zero incoming; x_j = Sinv_j (y_j - O^T x_{j+1}) ----
+  double r0[R], r1[R], r2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    r0[r] = su[M - 1] * b[r][M - 1][0];
+    r1[r] = fma(s00[M - 1], b[r][M - 1][1], s01[M - 1] * b[r][M - 1][2]);
+    r2[r] = fma(s01[M - 1], b[r][M - 1][1], s11[M - 1] * b[r][M - 1][2]);
   }
-  double n0 = 0.0, n1 = 0.0, n2 = 0.0;  // x of the right neighbour's first slot
+#pragma unroll
+  for (int j = M - 2; j >= 0; --j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double t0 = fma(-ou, r0[r], b[r][j][0]);
+      const double t1 = fma(-o11, r1[r], fma(-o12, r2[r], b[r][j][1]));
+      const double t2 = fma(o12, r1[r], fma(o22, r2[r], b[r][j][2]));
+      r0[r] = su[j] * t0;
+      r1[r] = fma(s00[j], t1, s01[j] * t2);
+      r2[r] = fma(s01[j], t1, s11[j] * t2);
+    }
+  double n0[R], n1[R], n2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
   if (G > 1) {
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
       const int d = 1 << l;
-      const double t0 = shfl_down_d(r0, d, G), t1 = shfl_down_d(r1, d, G), t2 = shfl_down_d(r2, d, G);
       const double2 c0 = ld_fscan<M, G>(C, l, 2), c1 = ld_fscan<M, G>(C, l, 3);
-      r0 = fma(cub[l], t0, r0);
-      mv2(c0, c1, t1, t2, r1, r2);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double t0 = shfl_down_d(r0[r], d, G), t1 = shfl_down_d(r1[r], d, G), t2 = shfl_down_d(r2[r], d, G);
+        r0[r] = fma(cub[l], t0, r0[r]);
+        mv2(c0, c1, t1, t2, r1[r], r2[r]);
+      }
     }
-    n0 = shfl_down_d(r0, 1, G);
-    n1 = shfl_down_d(r1, 1, G);
-    n2 = shfl_down_d(r2, 1, G);
-    if (C.g == G - 1) { n0 = 0.0; n1 = 0.0; n2 = 0.0; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      n0[r] = shfl_down_d(r0[r], 1, G);
+      n1[r] = shfl_down_d(r1[r], 1, G);
+      n2[r] = shfl_down_d(r2[r], 1, G);
+      if (C.g == G - 1) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
+    }
   }
   // ---- backward B: true incoming; b[j] <- x_j ----
 #pragma unroll
-  for (int j = M - 1; j >= 0; --j) {
-    const double t0 = ou * n0;
-    const double t1 = fma(o11, n1, o12 * n2);
-    const double t2 = -fma(o12, n1, o22 * n2);
-    n0 = fma(-su[j], t0, b[j][0]);
-    n1 = b[j][1] - fma(s00[j], t1, s01[j] * t2);
-    n2 = b[j][2] - fma(s01[j], t1, s11[j] * t2);
-    b[j][0] = n0;
-    b[j][1] = n1;
-    b[j][2] = n2;
-  }
+  for (int j = M - 1; j >= 0; --j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double t0 = fma(-ou, n0[r], b[r][j][0]);
+      const double t1 = fma(-o11, n1[r], fma(-o12, n2[r], b[r][j][1]));
+      const double t2 = fma(o12, n1[r], fma(o22, n2[r], b[r][j][2]));
+      n0[r] = su[j] * t0;
+      n1[r] = fma(s00[j], t1, s01[j] * t2);
+      n2[r] = fma(s01[j], t1, s11[j] * t2);
+      b[r][j][0] = n0[r];
+      b[r][j][1] = n1[r];
+      b[r][j][2] = n2[r];
+    }
 }
 
 // Linear element force as VALUES: f on node 1 = (fu, V, m1), on node 2 = (-fu, -V, m2)
@@ -189,26 +227,26 @@ __device__ __forceinline__ void fast_accel(const FastCtx<M>& C, double (&w)[M][3
   V[M] = shfl_down_d(V[0], 1, G);
   m1[M] = shfl_down_d(m1[0], 1, G);
   if (C.g == G - 1) { fu[M] = 0.0; V[M] = 0.0; m1[M] = 0.0; }
-  double b[M][3];
+  double b[1][M][3];
 #pragma unroll
   for (int j = 0; j < M; ++j) {
     // b = -(f_node2(element j) + f_node1(element j+1))
-    b[j][0] = fu[j] - fu[j + 1];
-    b[j][1] = V[j] - V[j + 1];
-    b[j][2] = -(m2[j] + m1[j + 1]);
+    b[0][j][0] = fu[j] - fu[j + 1];
+    b[0][j][1] = V[j] - V[j + 1];
+    b[0][j][2] = -(m2[j] + m1[j + 1]);
   }
   if (IMP && C.imp_local >= 0 && t < C.imp_dur) {
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d)
-        if (C.imp_local == 3 * j + d) b[j][d] += C.imp_amp;
+        if (C.imp_local == 3 * j + d) b[0][j][d] += C.imp_amp;
   }
-  fast_solve<M, LV>(b, C);
+  fast_solve_r<M, LV, 1>(b, C);
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) w[j][d] = b[j][d];
+    for (int d = 0; d < 3; ++d) w[j][d] = b[0][j][d];
 }
 
 template <int M, int LV, bool IMP>
@@ -354,128 +392,6 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
 // memory (half the LDS traffic per step) and gives the FP64 pipe two independent dependency
 // chains per lane.
 // ==========================================================================================
-template <int M, int LV>
-__device__ __forceinline__ void fast_solve2(double (&b)[2][M][3], const FastCtx<M>& C) {
-  constexpr int G = 1 << LV;
-  const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
-  double s00[M], s01[M], s11[M], su[M];
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const double2 a = ld_fslot<M, G>(C, 0, j), c = ld_fslot<M, G>(C, 1, j);
-    s00[j] = a.x;
-    s01[j] = a.y;
-    s11[j] = c.x;
-    su[j] = c.y;
-  }
-  double y0[2], y1[2], y2[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) { y0[r] = b[r][0][0]; y1[r] = b[r][0][1]; y2[r] = b[r][0][2]; }
-  // ---- forward A ----
-#pragma unroll
-  for (int j = 1; j < M; ++j)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const double xu = su[j - 1] * y0[r];
-      const double xw = fma(s00[j - 1], y1[r], s01[j - 1] * y2[r]);
-      const double xp = fma(s01[j - 1], y1[r], s11[j - 1] * y2[r]);
-      y0[r] = fma(-ou, xu, b[r][j][0]);
-      y1[r] = fma(-o11, xw, fma(o12, xp, b[r][j][1]));
-      y2[r] = fma(-o12, xw, fma(o22, xp, b[r][j][2]));
-    }
-  double xi0[2] = {0.0, 0.0}, xi1[2] = {0.0, 0.0}, xi2[2] = {0.0, 0.0};
-  double cub[LV > 0 ? LV : 1];
-  if (G > 1) {
-#pragma unroll
-    for (int l = 0; l < LV; ++l) {
-      const int d = 1 << l;
-      const double2 c0 = ld_fscan<M, G>(C, l, 0), c1 = ld_fscan<M, G>(C, l, 1), cu = ld_fscan<M, G>(C, l, 4);
-      cub[l] = cu.y;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const double t0 = shfl_up_d(y0[r], d, G), t1 = shfl_up_d(y1[r], d, G), t2 = shfl_up_d(y2[r], d, G);
-        y0[r] = fma(cu.x, t0, y0[r]);
-        mv2(c0, c1, t1, t2, y1[r], y2[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const double xu = su[M - 1] * y0[r];
-      const double xw = fma(s00[M - 1], y1[r], s01[M - 1] * y2[r]);
-      const double xp = fma(s01[M - 1], y1[r], s11[M - 1] * y2[r]);
-      xi0[r] = shfl_up_d(xu, 1, G);
-      xi1[r] = shfl_up_d(xw, 1, G);
-      xi2[r] = shfl_up_d(xp, 1, G);
-      if (C.g == 0) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
-    }
-  }
-  // ---- forward B ----
-#pragma unroll
-  for (int j = 0; j < M; ++j)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const double t0 = fma(-ou, xi0[r], b[r][j][0]);
-      const double t1 = fma(-o11, xi1[r], fma(o12, xi2[r], b[r][j][1]));
-      const double t2 = fma(-o12, xi1[r], fma(o22, xi2[r], b[r][j][2]));
-      xi0[r] = su[j] * t0;
-      xi1[r] = fma(s00[j], t1, s01[j] * t2);
-      xi2[r] = fma(s01[j], t1, s11[j] * t2);
-      b[r][j][0] = xi0[r];
-      b[r][j][1] = xi1[r];
-      b[r][j][2] = xi2[r];
-    }
-  // ---- backward A ----
-  double r0[2], r1[2], r2[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) { r0[r] = b[r][M - 1][0]; r1[r] = b[r][M - 1][1]; r2[r] = b[r][M - 1][2]; }
-#pragma unroll
-  for (int j = M - 2; j >= 0; --j)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const double t0 = ou * r0[r];
-      const double t1 = fma(o11, r1[r], o12 * r2[r]);
-      const double t2 = -fma(o12, r1[r], o22 * r2[r]);
-      r0[r] = fma(-su[j], t0, b[r][j][0]);
-      r1[r] = b[r][j][1] - fma(s00[j], t1, s01[j] * t2);
-      r2[r] = b[r][j][2] - fma(s01[j], t1, s11[j] * t2);
-    }
-  double n0[2] = {0.0, 0.0}, n1[2] = {0.0, 0.0}, n2[2] = {0.0, 0.0};
-  if (G > 1) {
-#pragma unroll
-    for (int l = 0; l < LV; ++l) {
-      const int d = 1 << l;
-      const double2 c0 = ld_fscan<M, G>(C, l, 2), c1 = ld_fscan<M, G>(C, l, 3);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const double t0 = shfl_down_d(r0[r], d, G), t1 = shfl_down_d(r1[r], d, G), t2 = shfl_down_d(r2[r], d, G);
-        r0[r] = fma(cub[l], t0, r0[r]);
-        mv2(c0, c1, t1, t2, r1[r], r2[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      n0[r] = shfl_down_d(r0[r], 1, G);
-      n1[r] = shfl_down_d(r1[r], 1, G);
-      n2[r] = shfl_down_d(r2[r], 1, G);
-      if (C.g == G - 1) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
-    }
-  }
-  // ---- backward B ----
-#pragma unroll
-  for (int j = M - 1; j >= 0; --j)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const double t0 = ou * n0[r];
-      const double t1 = fma(o11, n1[r], o12 * n2[r]);
-      const double t2 = -fma(o12, n1[r], o22 * n2[r]);
-      n0[r] = fma(-su[j], t0, b[r][j][0]);
-      n1[r] = b[r][j][1] - fma(s00[j], t1, s01[j] * t2);
-      n2[r] = b[r][j][2] - fma(s01[j], t1, s11[j] * t2);
-      b[r][j][0] = n0[r];
-      b[r][j][1] = n1[r];
-      b[r][j][2] = n2[r];
-    }
-}
-
 // w[r] <- -M^-1 K w[r] for r = 0, 1 (two independent operator applications).
 template <int M, int LV>
 __device__ __forceinline__ void fast_apply2(const FastCtx<M>& C, double (&w)[2][M][3]) {
@@ -504,7 +420,7 @@ __device__ __forceinline__ void fast_apply2(const FastCtx<M>& C, double (&w)[2][
       b[r][j][2] = -(m2[j] + m1[j + 1]);
     }
   }
-  fast_solve2<M, LV>(b, C);
+  fast_solve_r<M, LV, 2>(b, C);
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -582,7 +498,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
         w[0][j][d] = u;
         w[1][j][d] = (rel == 3 * j + d) ? amp : 0.0;
       }
-    fast_solve2<M, LV>(w, C);
+    fast_solve_r<M, LV, 2>(w, C);
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
