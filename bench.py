@@ -231,10 +231,11 @@ def run_gpu(args):
     # copies overlap the kernels on three streams) ----
     from continuum_robot_b200.integrate import HostPipeline
 
-    pipe = HostPipeline(beam, B, n_chunks=args.e2e_chunks)
+    pipe = HostPipeline(beam, B, chunk_members=args.e2e_chunk_members)
     for _ in range(3):
         pipe.run(x_host, 0.0, h, min(S, args.steps))
     pipe.synchronize()
+    torch.cuda.synchronize(dev)
     x_host.copy_(torch.from_numpy(x0))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -243,6 +244,7 @@ def run_gpu(args):
     for c in chunks(args.steps):
         pipe.run(x_host, te * h, h, c)
         te += c
+    pipe.wait()  # the current stream waits for the last copy-out before the closing event
     e1.record()
     barrier()
     pipe.synchronize()
@@ -299,7 +301,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": "element-steps/s", "h2d_bytes_per_step": X.numel() * 8 / S,
                     "d2h_bytes_per_step": X.numel() * 8 / S,
                     "call": f"HostPipeline.run per {S} fused RK4 steps: H2D state {X.numel() * 8} B (pinned) + kernels + D2H state, "
-                            f"{args.e2e_chunks} member chunks on 3 streams", "finite": e2e_ok},
+                            f"chunks of {pipe.chunk_members} members (whole kernel waves) on 3 streams, native pipeline crb_rk4_host",
+                    "finite": e2e_ok},
             "gpu_launches": len(chunks(args.steps)),
             "numa_bound": numa_bound,
             "clocks": clocks,
@@ -326,7 +329,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=50)
     ap.add_argument("--cpu-steps", type=int, default=2000, help="RK4 steps per member in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=16)
+    ap.add_argument("--e2e-chunk-members", type=int, default=0, help="members per pipelined chunk (0 = two kernel waves)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -68,8 +68,8 @@ def main():
     B, N, S = 65536, 32, 50
     e, beam, x0 = bench.build_ensemble(0, B, N, dev)
     x_host = torch.from_numpy(x0).pin_memory()
-    for nch in [int(c) for c in os.environ.get("PROBE_CHUNKS", "4,8,14,16,28,32").split(",")]:
-        pipe = HostPipeline(beam, B, n_chunks=nch)
+    for chunk in [int(c) for c in os.environ.get("PROBE_CHUNKS", "0,2368,4736,9472,4096,8192").split(",")]:
+        pipe = HostPipeline(beam, B, chunk_members=chunk)
         for _ in range(3):
             pipe.run(x_host, 0.0, e.h, S)
         pipe.synchronize()
@@ -80,12 +80,13 @@ def main():
         reps = 40
         for k in range(reps):
             pipe.run(x_host, k * S * e.h, e.h, S)
+        pipe.wait()
         b.record()
         torch.cuda.synchronize()
         pipe.synchronize()
         ms = a.elapsed_time(b) / reps
-        print(json.dumps({"n_chunks": len(pipe.ranges), "chunk_members": pipe.ranges[0][1] - pipe.ranges[0][0],
-                          "ms_per_run": ms, "element_steps_per_s": B * N * S / ms * 1e3, "numa_bound": bound}), flush=True)
+        print(json.dumps({"chunk_members": pipe.chunk_members, "ms_per_run": ms,
+                          "element_steps_per_s": B * N * S / ms * 1e3, "numa_bound": bound}), flush=True)
 
 
 if __name__ == "__main__":

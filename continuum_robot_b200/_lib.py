@@ -89,6 +89,14 @@ _SIGNATURES = {
          C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_int32, C.c_void_p],
     ),
+    "crb_rk4_wave_members": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.POINTER(C.c_int32)]),
+    "crb_system_slice": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_int32, C.c_int32, C.POINTER(CrbSystem)]),
+    "crb_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "crb_pipeline_destroy": (C.c_int, [C.c_void_p]),
+    "crb_pipeline_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "crb_pipeline_synchronize": (C.c_int, [C.c_void_p]),
+    "crb_rk4_host": (C.c_int, [C.c_void_p, C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_void_p,
+                               C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
     "crb_gain_fragments": (C.c_int64, [C.POINTER(CrbPlan), C.c_void_p, C.c_void_p]),
     "crb_dense_matrices": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p,
                                      C.c_void_p, C.c_void_p]),

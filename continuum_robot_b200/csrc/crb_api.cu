@@ -222,6 +222,25 @@ extern "C" int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const
   return 0;
 }
 
+// fast path: all-linear, uniform element mass, contiguous plan without phantom slots, no
+// forces and no input other than a constant force / tip impulse (BASELINE config 3 shape)
+static bool rk4_fast_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
+  return sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p && !sys->drag &&
+         sys->grav_mode == 0 && !sys->gain && !sys->force_general && sys->mass_shared;
+}
+
+extern "C" int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* sys, int32_t* out) {
+  if (!plan || !sys || !out) return fail(CRB_E_ARG, "crb_rk4_wave_members: null argument");
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return fail(CRB_E_CUDA, "crb_rk4_wave_members: cannot query the device");
+  const int mpw = 32 / plan->g;
+  // resident blocks per SM follow the register allocation of the kernel families (launch bounds)
+  const int per_sm = rk4_fast_eligible(plan, sys) ? crb_fast_members_per_sm(mpw) : 2 * CRB_WARPS_PER_BLOCK * mpw;
+  *out = sms * per_sm;
+  return 0;
+}
+
 extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                        int32_t nsteps, double* Y_out, int32_t save_every, void* stream) {
   if (int rc = check_system("crb_rk4", plan, sys)) return rc;
@@ -230,11 +249,7 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
   if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_rk4: step h must be positive and finite");
   if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_rk4: save_every must be >= 1 when Y_out is given");
   if (nsteps == 0) return 0;
-  // fast path: all-linear, uniform element mass, contiguous plan without phantom slots, no
-  // forces and no input other than a tip impulse (BASELINE config 3 shape)
-  const bool fast = sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p &&
-                    !sys->drag && sys->grav_mode == 0 && !sys->gain &&
-                    !sys->force_general;
+  const bool fast = rk4_fast_eligible(plan, sys);
   int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream) : 1;
   if (rc == 1)  // not eligible, or shape not instantiated in the fast family
     rc = crb_launch_rk4_general(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream);

@@ -90,6 +90,7 @@ inline unsigned crb_pick_profile(unsigned need) {
     default: { constexpr unsigned FEAT = CRB_F_ALL; __VA_ARGS__; } break;        \
   }
 
+int crb_fast_members_per_sm(int members_per_warp);  // resident members per SM of the fast RK4 family (crb_rk4_fast.cu)
 // launchers implemented in their own translation units (parallel nvcc builds)
 int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                            int nsteps, double* Y_out, int save_every, cudaStream_t stream);

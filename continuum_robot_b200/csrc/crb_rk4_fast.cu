@@ -36,6 +36,8 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   return 0;
 }
 
+int crb_fast_members_per_sm(int members_per_warp) { return CRB_FAST_MINBLOCKS * CRB_FAST_WARPS * members_per_warp; }
+
 int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                         int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
 #define CRB_CASE(MM, LL) \

@@ -91,25 +91,20 @@ def rk4_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, ns
 class HostPipeline:
     """Fixed-step RK4 on a HOST-resident ensemble: ``x_host[B, 2n]`` (pinned) is advanced in place.
 
-    The ensemble is cut into member chunks; chunk c+1 is copied host->device and chunk c-1
-    device->host while chunk c integrates (three CUDA streams, PCIe is full duplex), so a call
-    costs about max(copy-in, compute, copy-out) instead of their sum.  Members are independent,
-    so chunking changes nothing numerically.
+    Thin wrapper of the native pipeline (``crb_rk4_host``, csrc/crb_host.cu): the ensemble is cut into
+    member chunks of whole kernel waves; chunk c+1 is copied host->device and chunk c-1 device->host
+    while chunk c integrates (three CUDA streams, PCIe is full duplex), and consecutive ``run`` calls
+    overlap chunk by chunk, so a sequence of calls costs about max(copy-in, compute, copy-out)
+    instead of their sum.  Members are independent, so chunking changes nothing numerically.
+
+    ``chunk_members=0`` picks two full waves of the kernel the library dispatches (measured best).
     """
 
-    def __init__(self, beam: BatchedDynamicEulerBernoulliBeam, n_members: int, n_chunks: int = 8, *, u=None,
+    def __init__(self, beam: BatchedDynamicEulerBernoulliBeam, n_members: int, chunk_members: int = 0, *, u=None,
                  controller=None):
         import torch
 
-        self.beam, self.B = beam, int(n_members)
-        self.n2 = 2 * beam.n_free
-        n_chunks = max(1, min(int(n_chunks), self.B))
-        step = -(-self.B // n_chunks)
-        step = -(-step // 32) * 32  # whole warps of members per chunk
-        self.ranges = [(lo, min(lo + step, self.B)) for lo in range(0, self.B, step)]
-        dev = beam.device
-        self.X = torch.empty((self.B, self.n2), dtype=torch.float64, device=dev)
-        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.B = int(n_members)
         drag, grav, user = beam._active_forces()
         if user or beam._forces_func is not None:
             raise TypeError("HostPipeline supports built-in forces only")
@@ -117,51 +112,57 @@ class HostPipeline:
         uc = None if impulse is not None else u
         gain, ref = _feedback(controller)
         beam = self.beam = _feedback_layout(beam, controller)
-        self.systems = [beam.make_system(self.B, drag=drag, gravity=grav, u_const=uc, impulse=impulse, gain=gain,
-                                         ref=ref, member_range=r) for r in self.ranges]
-        self.ev_out = [None] * len(self.ranges)
+        self.n2 = 2 * beam.n_free
+        self.X = torch.empty((self.B, self.n2), dtype=torch.float64, device=beam.device)  # device workspace
+        self.system = beam.make_system(self.B, drag=drag, gravity=grav, u_const=uc, impulse=impulse, gain=gain, ref=ref)
+        lib = _lib.load()
+        with torch.cuda.device(beam.device):
+            wave = C.c_int32(0)
+            _lib.check(lib.crb_rk4_wave_members(C.byref(beam._plan), C.byref(self.system[0]), C.byref(wave)))
+            self.chunk_members = int(chunk_members) if chunk_members and chunk_members > 0 else 2 * int(wave.value)
+            self._handle = C.c_void_p()
+            _lib.check(lib.crb_pipeline_create(C.byref(self._handle)))
 
     def run(self, x_host, t0: float, h: float, nsteps: int):
-        """Enqueue H2D -> nsteps fused RK4 steps -> D2H for every chunk; returns immediately
-        (call ``synchronize()`` or wait on the current stream, which is made to depend on the result)."""
+        """Enqueue H2D -> nsteps fused RK4 steps -> D2H for every chunk and return immediately.  The work
+        is ordered after the current stream; call ``wait()`` (stream-ordered) or ``synchronize()`` (host)
+        before reading ``x_host``."""
         import torch
 
-        if x_host.device.type != "cpu" or not x_host.is_pinned() or tuple(x_host.shape) != (self.B, self.n2):
-            raise ValueError("x_host must be a pinned CPU tensor of shape [B, 2n]")
-        beam, lib = self.beam, _lib.load()
-        cur = torch.cuda.current_stream(beam.device)
-        start = torch.cuda.Event()
-        start.record(cur)
-        self.s_in.wait_event(start)
-        for c, ((lo, hi), (sysm, _keep)) in enumerate(zip(self.ranges, self.systems)):
-            with torch.cuda.stream(self.s_in):
-                if self.ev_out[c] is not None:
-                    self.s_in.wait_event(self.ev_out[c])  # previous call's copy-out of this chunk
-                self.X[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
-                e_in = torch.cuda.Event()
-                e_in.record(self.s_in)
-            with torch.cuda.stream(self.s_cmp):
-                self.s_cmp.wait_event(e_in)
-                with torch.cuda.device(beam.device):
-                    rc = lib.crb_rk4(C.byref(beam._plan), C.byref(sysm), self.X[lo:hi].data_ptr(), float(t0), float(h),
-                                     int(nsteps), None, 0, self.s_cmp.cuda_stream)
-                _lib.check(rc)
-                e_cmp = torch.cuda.Event()
-                e_cmp.record(self.s_cmp)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(e_cmp)
-                x_host[lo:hi].copy_(self.X[lo:hi], non_blocking=True)
-                e_out = torch.cuda.Event()
-                e_out.record(self.s_out)
-                self.ev_out[c] = e_out
-        cur.wait_event(self.ev_out[-1])
-        for e in self.ev_out[:-1]:
-            cur.wait_event(e)
+        if x_host.device.type != "cpu" or not x_host.is_pinned() or tuple(x_host.shape) != (self.B, self.n2) \
+                or x_host.dtype != torch.float64 or not x_host.is_contiguous():
+            raise ValueError("x_host must be a pinned, contiguous float64 CPU tensor of shape [B, 2n]")
+        beam = self.beam
+        with torch.cuda.device(beam.device):
+            rc = _lib.load().crb_rk4_host(self._handle, C.byref(beam._plan), C.byref(self.system[0]), x_host.data_ptr(),
+                                          self.X.data_ptr(), self.chunk_members, float(t0), float(h), int(nsteps),
+                                          beam._stream())
+        _lib.check(rc)
         return x_host
 
+    def wait(self):
+        """Make the current CUDA stream wait for every outstanding chunk."""
+        import torch
+
+        with torch.cuda.device(self.beam.device):
+            _lib.check(_lib.load().crb_pipeline_wait(self._handle, self.beam._stream()))
+
     def synchronize(self):
-        for s in (self.s_in, self.s_cmp, self.s_out):
-            s.synchronize()
+        import torch
+
+        with torch.cuda.device(self.beam.device):
+            _lib.check(_lib.load().crb_pipeline_synchronize(self._handle))
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            _lib.load().crb_pipeline_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _rk4_unfused(beam, X, t0, h, nsteps, u, controller, Y_out, save_every):

@@ -151,6 +151,32 @@ int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const double* X,
 int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
             int32_t nsteps, double* Y_out, int32_t save_every, void* stream);
 
+/* Members one full wave of the RK4 kernel chosen for (plan, sys) integrates at once on the current
+ * device (SMs x resident members per SM): the natural chunk size for pipelined calls. */
+int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* sys, int32_t* out);
+
+/* Sub-ensemble [lo, lo+count) of a system: every per-member device pointer is offset. */
+int crb_system_slice(const crb_plan_t* plan, const crb_system_t* sys, int32_t lo, int32_t count,
+                     crb_system_t* out);
+
+/* Host-resident ensembles.  The reference keeps each beam's state in host memory and fans whole
+ * simulations out over processes (examples/example_utilities.py:116-170,
+ * examples/beam_comparison_gravity.py:72-73); crb_rk4_host is that contract for an ensemble:
+ * X_host[B,2n] (pinned host memory) is advanced in place by nsteps RK4 steps.  Members are cut into
+ * chunks (chunk_members, 0 = two kernel waves); chunk c+1 is copied in and chunk c-1 copied out while
+ * chunk c integrates, on three streams owned by the pipeline handle (the handle owns streams and
+ * events only -- X_dev[B,2n] is caller-owned device workspace).  The call returns immediately; its
+ * work is ordered after everything enqueued on `stream` so far.  Consecutive calls on the same
+ * buffers and chunking overlap chunk by chunk.  crb_pipeline_wait makes `stream` wait for all
+ * outstanding copies; crb_pipeline_synchronize blocks the host. */
+typedef struct crb_pipeline crb_pipeline_t;
+int crb_pipeline_create(crb_pipeline_t** out);
+int crb_pipeline_destroy(crb_pipeline_t* p);
+int crb_pipeline_wait(crb_pipeline_t* p, void* stream);
+int crb_pipeline_synchronize(crb_pipeline_t* p);
+int crb_rk4_host(crb_pipeline_t* p, const crb_plan_t* plan, const crb_system_t* sys, double* X_host,
+                 double* X_dev, int32_t chunk_members, double t0, double h, int32_t nsteps, void* stream);
+
 /* Adaptive Dormand-Prince 5(4) with SciPy's controller (scipy/integrate/_ivp/rk.py:86-180),
  * one independent (t, h) per member.  Replaces solve_ivp(method="RK45") as called at
  * examples/pyodide_example/pyodide_example.py:69-75 and throughout the reference's tests.

@@ -223,10 +223,19 @@ def test_host_pipeline_matches_device_resident_run():
         rk4_steps(beam, X, 0.0, e.h, 30, u=u)
         rk4_steps(beam, X, 30 * e.h, e.h, 30, u=u)
         xh = torch.from_numpy(x0.copy()).pin_memory()
-        pipe = HostPipeline(beam, B, n_chunks=3, u=u)
+        for chunk in (72, 0, 203, 1000):  # ragged chunks, library default (one wave), exact, larger than B
+            xh = torch.from_numpy(x0.copy()).pin_memory()
+            pipe = HostPipeline(beam, B, chunk_members=chunk, u=u)
+            pipe.run(xh, 0.0, e.h, 30)
+            pipe.run(xh, 30 * e.h, e.h, 30)  # overlaps the first call chunk by chunk
+            pipe.synchronize()
+            assert np.array_equal(xh.numpy(), X.cpu().numpy()), chunk
+        # stream-ordered completion: wait() makes the current stream see the result
+        xh = torch.from_numpy(x0.copy()).pin_memory()
         pipe.run(xh, 0.0, e.h, 30)
         pipe.run(xh, 30 * e.h, e.h, 30)
-        torch.cuda.synchronize()
+        pipe.wait()
+        torch.cuda.current_stream().synchronize()
         assert np.array_equal(xh.numpy(), X.cpu().numpy())
     with pytest.raises(ValueError, match="pinned"):
         pipe.run(torch.zeros(B, 2 * beam.n_free, dtype=torch.float64), 0.0, e.h, 1)
