@@ -124,9 +124,13 @@ def main():
             ctrl = FullStateLinear(torch.from_numpy(K).to(dev))
             X = torch.zeros(B, 2 * n, dtype=torch.float64, device=dev)
             imp = TipImpulse(torch.from_numpy(e.impulse_amp).to(dev))
-            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp, controller=ctrl))
-            print(json.dumps({"config": "cfg5 LQR rollout 131072 x 6 el, RK4", "m": beam._plan.m, "g": beam._plan.g,
-                              "element_steps_per_s": B * 6 * steps / (ms * 1e-3), "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}))
+            for general in (False, True):  # shared-operator tensor-core kernel, then the banded per-member kernel
+                beam.force_general_kernels = general
+                X.zero_()
+                ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp, controller=ctrl))
+                print(json.dumps({"config": "cfg5 LQR rollout 131072 x 6 el, RK4, " + ("banded kernel + DMMA feedback" if general else "shared-operator DMMA kernel"),
+                                  "element_steps_per_s": B * 6 * steps / (ms * 1e-3), "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}))
+            beam.force_general_kernels = False
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 100
+CRB_VERSION = 101
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -65,6 +65,8 @@ class CrbSystem(C.Structure):
         ("force_general", C.c_int32),
         ("force_staged", C.c_int32),
         ("um", C.c_double * 4),
+        ("shared_op", C.c_void_p),
+        ("shared_op_doubles", C.c_int64),
     ]
 
 
@@ -98,6 +100,8 @@ _SIGNATURES = {
     "crb_rk4_host": (C.c_int, [C.c_void_p, C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_void_p,
                                C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
     "crb_gain_fragments": (C.c_int64, [C.POINTER(CrbPlan), C.c_void_p, C.c_void_p]),
+    "crb_shared_operator": (C.c_int64, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p,
+                                        C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p]),
     "crb_dense_matrices": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p,
                                      C.c_void_p, C.c_void_p]),
 }

@@ -249,6 +249,12 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
   if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_rk4: step h must be positive and finite");
   if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_rk4: save_every must be >= 1 when Y_out is given");
   if (nsteps == 0) return 0;
+  if (crb_shared_eligible(plan, sys)) {  // one design + gain shared by all members: dense tensor-core contraction
+    if (int rc = crb_launch_rk4_shared(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream)) return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   const bool fast = rk4_fast_eligible(plan, sys);
   int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream) : 1;
   if (rc == 1)  // not eligible, or shape not instantiated in the fast family

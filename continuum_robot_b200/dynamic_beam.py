@@ -525,11 +525,50 @@ class BatchedDynamicEulerBernoulliBeam:
                 keep.append(frd)
                 s.gain_frag = frd.data_ptr()
                 self._gain_frag_cache = (cache_key, frd, gdev)  # gdev kept alive so its address stays unique
+            rdev = None
             if ref is not None:
                 if not isinstance(ref, torch.Tensor):
                     ref = torch.as_tensor(np.asarray(ref, dtype=np.float64))
-                s.ref = dev64(ref.reshape(-1), (2 * n,), "reference").data_ptr()
+                rdev = dev64(ref.reshape(-1), (2 * n,), "reference")
+                s.ref = rdev.data_ptr()
+            # one design + one gain shared by every member: the closed-loop RHS is a dense contraction
+            # with member-independent operators (crb_shared_operator -> FP64 tensor cores)
+            if (self._mass_shared and self._stiff_shared and self._all_linear and drag is None and u_const is None
+                    and f_ext is None and n <= 24 and (gravity is None or self.n_elements <= 8)
+                    and not self.force_general_kernels):
+                blob = self._shared_operator(gdev, rdev, (s.gx, s.gy) if gravity is not None else None,
+                                             int(s.imp_dof) if impulse is not None else -1)
+                keep.append(blob)
+                s.shared_op = blob.data_ptr()
+                s.shared_op_doubles = blob.numel()
         return s, keep
+
+    def _shared_operator(self, gdev, rdev, grav_xy, imp_dof: int):
+        """Device copy of the shared-operator blob for (gain, ref, gravity vector, impulse DOF); cached on
+        the operator's content."""
+        torch = _torch()
+        gh = np.ascontiguousarray(gdev.detach().cpu().numpy())
+        rh = np.ascontiguousarray(rdev.detach().cpu().numpy()) if rdev is not None else None
+        key = (gh.tobytes(), rh.tobytes() if rh is not None else None, grav_xy, imp_dof)
+        cache = self.__dict__.setdefault("_shared_op_cache", {})
+        if key not in cache:
+            if len(cache) >= 8:
+                cache.clear()
+            lib = _lib.load()
+            par = np.ascontiguousarray(self._params_np[0])
+            gx, gy = grav_xy if grav_xy is not None else (0.0, 0.0)
+            args = (C.byref(self._plan), par.ctypes.data_as(C.c_void_p), self._etype.tobytes(), self._bc.tobytes(),
+                    gh.ctypes.data_as(C.c_void_p), rh.ctypes.data_as(C.c_void_p) if rh is not None else None,
+                    float(gx), float(gy), int(grav_xy is not None), int(imp_dof))
+            cnt = int(lib.crb_shared_operator(*args, None))
+            if cnt < 0:
+                _lib.check(cnt)
+            out = np.empty(cnt, dtype=np.float64)
+            got = int(lib.crb_shared_operator(*args, out.ctypes.data_as(C.c_void_p)))
+            if got != cnt:
+                _lib.check(got if got < 0 else -1)
+            cache[key] = torch.from_numpy(out).to(self.device)
+        return cache[key]
 
     def _stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream

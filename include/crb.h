@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 100
+#define CRB_VERSION 101
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 
@@ -109,6 +109,11 @@ typedef struct crb_system_t {
   int32_t force_general;    /* 1: always use the general kernels (testing / comparison) */
   int32_t force_staged;     /* 1: fast path keeps the stage-by-stage kernel (no paired operator form) */
   double um[4];             /* uniform-mass coupling block: 54 mu, 13 L mu, 3 L^2 mu, 70 mu, mu = rho A L / 420 */
+  /* shared-operator form (crb_shared_operator): device copy of the operator blob, or NULL.  When set,
+   * crb_rk4 evaluates the whole closed-loop RHS as a dense FP64 tensor-core contraction; gain / ref /
+   * gravity vector / imp_dof are the ones the blob was built with. */
+  const double* shared_op;
+  int64_t shared_op_doubles;
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */
@@ -195,6 +200,19 @@ int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double*
  * nt < (3m+1)/2 (n-tile = own position DOFs 2nt, 2nt+1 of each lane).  Returns the number of doubles
  * written (out may be NULL to query), or a negative error code. */
 int64_t crb_gain_fragments(const crb_plan_t* plan, const double* gain_host, double* out_host);
+
+/* Host only.  Shared-operator form of the RHS for ensembles whose members share ONE linear design,
+ * gravity setting and feedback gain (BASELINE config 5, examples/lqr_control.py:87-130):
+ *   a = W [q;v] + (M^-1 Gc) cos(P q) + (M^-1 Gs) sin(P q) + c0 + imp(t) M^-1 e_k,
+ *   W = [-M^-1 (K + G_q) | -M^-1 G_v],  c0 = M^-1 G r   (dynamic_beam_model.py:256-272, 343-362,
+ *   control/full_state_linear.py:58, gravity_forces.py:97-146 in reduced indices),
+ * re-tiled as mma.sync.m8n8k4.f64 B fragments.  gain_host [n,2n] / ref_host [2n] may be NULL,
+ * imp_dof = -1 for none.  Requires n_free <= 24 (and <= 8 segments with gravity).  Returns the
+ * number of doubles (out_host NULL = query) or a negative error code; the caller copies the blob to
+ * the device and sets crb_system_t.shared_op / shared_op_doubles. */
+int64_t crb_shared_operator(const crb_plan_t* plan, const double* params_host, const uint8_t* elem_type_host,
+                            const uint8_t* bc_host, const double* gain_host, const double* ref_host,
+                            double gx, double gy, int32_t gravity_on, int32_t imp_dof, double* out_host);
 
 /* Dense BC-reduced matrices for one parameter set (host convenience for LQR synthesis;
  * replaces get_mass_matrix / get_stiffness_matrix, euler_bernoulli_beam.py:357-361,422-511).

@@ -415,3 +415,73 @@ def test_rk45_step_sequence_equals_scipy_controller():
         assert int(res.nfev[i]) == r.nfev and int(res.naccept[i]) == r.naccept and int(res.nreject[i]) == r.nreject
         got = res.y[i].cpu().numpy()
         assert np.all(np.abs(got - r.y) <= 1e-3 * (1e-9 + 1e-6 * np.abs(r.y)))
+
+
+def test_lqr_rollout_config5_banded_path():
+    """Same golden rollout through the per-member banded kernel (feedback on the tensor cores only):
+    the path taken when designs differ per member."""
+    from continuum_robot_b200 import FullStateLinear, TipImpulse
+    from continuum_robot_b200.integrate import rk4_steps
+
+    g = load("cfg5_samples.npz")
+    beam = make_gpu_beam(params_array(g)[None], g["elem_type"], g["bc"], 0.0, True)
+    beam.force_general_kernels = True
+    n, B, h = beam.n_free, len(g["amp"]), float(g["h"])
+    ctrl = FullStateLinear(torch.from_numpy(g["gain"]).cuda())
+    X = torch.zeros(B, 2 * n, dtype=torch.float64, device="cuda")
+    rk4_steps(beam, X, 0.0, h, 500, u=TipImpulse(torch.from_numpy(g["amp"]).cuda()), controller=ctrl)
+    got = X.cpu().numpy()
+    assert max(block_err(got[i], g["Y"][i, 0], n) for i in range(B)) < 1e-9
+
+
+@pytest.mark.parametrize("N,bc0,gravity,with_ref,with_imp", [
+    (6, 1, True, False, True), (6, 1, False, True, False), (3, 1, True, True, True), (8, 1, True, False, False),
+    (4, 2, True, True, True), (1, 1, True, False, True), (5, 1, False, False, False),
+])
+def test_shared_operator_path_matches_banded_path_and_oracle(N, bc0, gravity, with_ref, with_imp):
+    """Shared-operator RK4 (dense FP64 tensor-core contraction, crb_shared_operator) vs the banded
+    per-member kernel and vs the CPU oracle: gains with a non-zero reference, FIXED and PINNED roots,
+    gravity on/off, impulse on/off, 1..8 elements (<= 1e-9 block inf-norm over 300 steps)."""
+    from continuum_robot_b200 import FullStateLinear, TipImpulse
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    rng = np.random.default_rng(100 + N)
+    m = ens.material()
+    par = np.zeros((1, N, 7))
+    par[0, :, 0] = m["length"] * (1 + 0.1 * rng.random(N))
+    par[0, :, 1], par[0, :, 2], par[0, :, 3], par[0, :, 4] = m["E"], m["I"], m["rho"] * (1 + 0.2 * rng.random(N)), m["A"]
+    par[0, :, 5], par[0, :, 6] = m["wetted_area"], m["drag_coef"]
+    bc = np.array([bc0] + [0] * N)
+    et = np.zeros(N, dtype=int)
+    beam = make_gpu_beam(par, et, bc, 0.0, gravity, (1.5, -9.81, 0.0))
+    n, B, h, steps = beam.n_free, 37, 2e-6, 300
+    # (stiffness-like and damping-like feedback small enough that the closed loop stays tame over the run)
+    gain = np.concatenate([50.0 * rng.standard_normal((n, n)), 0.05 * rng.standard_normal((n, n))], axis=1)
+    ref = 1e-3 * rng.standard_normal(2 * n) if with_ref else None
+    ctrl = FullStateLinear(torch.from_numpy(gain).cuda(), reference=torch.from_numpy(ref).cuda() if with_ref else None)
+    amp = rng.uniform(1.0, 5.0, B)
+    imp = TipImpulse(torch.from_numpy(amp).cuda(), duration=2.5e-4) if with_imp else None
+    x0 = np.concatenate([1e-3 * rng.standard_normal((B, n)), 1e-1 * rng.standard_normal((B, n))], axis=1)
+    Xs = torch.from_numpy(x0).cuda()
+    rk4_steps(beam, Xs, 0.0, h, steps, u=imp, controller=ctrl)
+    beam.force_general_kernels = True
+    Xb = torch.from_numpy(x0).cuda()
+    rk4_steps(beam, Xb, 0.0, h, steps, u=imp, controller=ctrl)
+    beam.force_general_kernels = False
+    gs, gb = Xs.cpu().numpy(), Xb.cpu().numpy()
+    assert not np.array_equal(gs, gb)  # two different kernels really ran
+    assert max(block_err(gs[i], gb[i], n) for i in range(B)) < 1e-9
+    spec = bo.BeamSpec(par[0, :, 0], par[0, :, 1], par[0, :, 2], par[0, :, 3], par[0, :, 4], et, bc, par[0, :, 5], par[0, :, 6])
+    orc = bo.BeamOracle(spec, bo.ForceSpec(gravity_vector=(1.5, -9.81, 0.0), enable_gravity_effects=gravity))
+    r = np.zeros(2 * n) if ref is None else ref
+    for i in (0, B - 1):
+        def f(t, x, i=i):
+            u = gain @ (r - x)
+            if with_imp and t < 2.5e-4:
+                u = u.copy()
+                u[n - 2] += amp[i]
+            return orc.rhs(t, x, u)
+        want = bo.rk4_solve(f, x0[i], 0.0, h, steps)
+        assert block_err(gs[i], want, n) < 1e-9, (i, block_err(gs[i], want, n))
