@@ -89,7 +89,7 @@ def main():
             beam.create_system_func(); beam.create_input_func()
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
-            print(json.dumps({"config": "cfg3 with per-member mass (general kernel, factors from L2)",
+            print(json.dumps({"config": "cfg3 with per-member mass (paired fast kernel, per-member factor sets in shared memory)",
                               "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg4":  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
             B = 4096

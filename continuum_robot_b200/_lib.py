@@ -65,6 +65,7 @@ class CrbSystem(C.Structure):
         ("force_general", C.c_int32),
         ("force_staged", C.c_int32),
         ("um", C.c_double * 4),
+        ("um_members", C.c_void_p),
         ("shared_op", C.c_void_p),
         ("shared_op_doubles", C.c_int64),
     ]

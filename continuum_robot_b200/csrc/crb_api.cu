@@ -226,7 +226,7 @@ extern "C" int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const
 // forces and no input other than a constant force / tip impulse (BASELINE config 3 shape)
 static bool rk4_fast_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
   return sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p && !sys->drag &&
-         sys->grav_mode == 0 && !sys->gain && !sys->force_general && sys->mass_shared;
+         sys->grav_mode == 0 && !sys->gain && !sys->force_general && (sys->mass_shared || sys->um_members);
 }
 
 extern "C" int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* sys, int32_t* out) {

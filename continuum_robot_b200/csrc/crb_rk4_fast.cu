@@ -2,23 +2,23 @@
 #include "crb_internal.h"
 #include "crb_rk4_fast.cuh"
 
-template <int M, int LV>
+template <int M, int LV, bool PM>
 static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
                   double* Y_out, int save_every, cudaStream_t stream) {
-  const size_t bytes = sizeof(double) * (4 * plan->p + 10 * (plan->levels > 0 ? plan->levels : 1) * plan->g);
-  if (!sys->mass_shared) return 1;  // the fast family stages ONE shared compact factor set
   const int mpb = CRB_FAST_WARPS * (32 >> LV);
+  // compact factor copy: ONE shared set, or (PM) one region per member of the block
+  const size_t bytes = sizeof(double) * (4 * plan->p + 10 * (plan->levels > 0 ? plan->levels : 1) * plan->g) * (PM ? mpb : 1);
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
 #define CRB_LIN2(UCV, IMPV)                                                                              \
   {                                                                                                      \
-    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV>, bytes, "crb_rk4")) return rc;           \
-    crb_rk4_lin2_kernel<M, LV, UCV, IMPV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, \
-                                                                                    Y_out, save_every);  \
+    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM>, bytes, "crb_rk4")) return rc;       \
+    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, \
+                                                                                        Y_out, save_every); \
   }
-  if (!sys->force_staged) {  // paired operator applications (forcing piecewise constant in time)
+  if (!sys->force_staged || PM) {  // paired operator applications (forcing piecewise constant in time)
     if (uc && imp) CRB_LIN2(true, true)
     else if (uc) CRB_LIN2(true, false)
     else if (imp) CRB_LIN2(false, true)
@@ -40,8 +40,16 @@ int crb_fast_members_per_sm(int members_per_warp) { return CRB_FAST_MINBLOCKS * 
 
 int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                         int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
+  if (!sys->mass_shared) {  // per-member mass factors: per-member coupling blocks are required
+    if (!sys->um_members || sys->force_staged) return 1;
+#define CRB_CASE_PM(MM, LL) \
+  if (plan->m == MM && plan->levels == LL) return launch<MM, LL, true>(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
+    CRB_CASE_PM(4, 3) CRB_CASE_PM(4, 4) CRB_CASE_PM(4, 2) CRB_CASE_PM(3, 2) CRB_CASE_PM(3, 3) CRB_CASE_PM(3, 1) CRB_CASE_PM(4, 5)
+#undef CRB_CASE_PM
+    return 1;
+  }
 #define CRB_CASE(MM, LL) \
-  if (plan->m == MM && plan->levels == LL) return launch<MM, LL>(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
+  if (plan->m == MM && plan->levels == LL) return launch<MM, LL, false>(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
   CRB_CASE(4, 3) CRB_CASE(4, 4) CRB_CASE(4, 5) CRB_CASE(4, 2)
   CRB_CASE(3, 1) CRB_CASE(3, 2) CRB_CASE(3, 3) CRB_CASE(2, 0) CRB_CASE(2, 1) CRB_CASE(4, 0) CRB_CASE(3, 0) CRB_CASE(1, 0) CRB_CASE(4, 1)
 #undef CRB_CASE

@@ -437,28 +437,44 @@ __device__ __forceinline__ void fast_apply2(const FastCtx<M>& C, double (&w)[2][
 //     v+ = v + h/6 (a1 + 5 a2 + h/2 p + c4 - c2) + h^3/12 (r1 + r2)
 // (reduces to the force-free formulas for c = 0).  M^-1 u_const and M^-1 e_k are obtained once per
 // launch by one paired solve.
-template <int M, int LV, bool UC, bool IMP>
+// PM: every member has its OWN mass factors (density / area / length differ per member, still uniform
+// along each beam): each lane group stages its member's compact factor copy in its own shared-memory
+// region and takes the coupling block from um_members[member] instead of the kernel arguments.
+template <int M, int LV, bool UC, bool IMP, bool PM>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double t0, double h, int nsteps,
                     double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
   constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
   constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
-  {
-    const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
-    for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
-    __syncthreads();
-  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + warp * mpw + lane / G;
+  const int mloc = warp * mpw + lane / G;
+  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
   FastCtx<M> C;
   C.g = lane % G;
   C.n = P.n_free;
   C.active = member < S.n_members;
   C.member = C.active ? member : S.n_members - 1;
-  C.um = um;
-  C.fslot = smem;
-  C.fscan = smem + 4 * M * G;
+  {
+    const long long off = 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+    if (PM) {
+      const double* src = S.mfac + (long long)C.member * P.mfac_doubles + off;
+      double* dst = smem + mloc * FAST_DOUBLES;
+      for (int k = C.g; k < FAST_DOUBLES; k += G) dst[k] = src[k];
+    } else {
+      const double* src = S.mfac + off;
+      for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+    }
+    __syncthreads();
+  }
+  if (PM) {
+    const double4 u4 = *reinterpret_cast<const double4*>(S.um_members + 4ll * C.member);
+    C.um.o11 = u4.x; C.um.o12 = u4.y; C.um.o22 = u4.z; C.um.ou = u4.w;
+  } else {
+    C.um = um;
+  }
+  C.fslot = smem + (PM ? mloc * FAST_DOUBLES : 0);
+  C.fscan = C.fslot + 4 * M * G;
   C.imp_amp = 0.0;
   C.imp_dur = 0.0;
   C.imp_local = -1;
