@@ -311,10 +311,11 @@ crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n
     for (int s = 0; s < Pn; ++s) {
       const int g = s / m, j = s - g * m;
       const M2 Sinv = ld_m2(mf, 4, s, m, G);
-      fs[(((0 * m + j) * G + g) << 1) + 0] = Sinv.a;
-      fs[(((0 * m + j) * G + g) << 1) + 1] = Sinv.b;
-      fs[(((1 * m + j) * G + g) << 1) + 0] = Sinv.d;
-      fs[(((1 * m + j) * G + g) << 1) + 1] = mf[mf_addr(21, s, m, G)];
+      const double live = s < P.p_act ? 1.0 : 0.0;  // phantom slots: Sinv = 0 decouples them in the uniform-mass solve
+      fs[(((0 * m + j) * G + g) << 1) + 0] = live * Sinv.a;
+      fs[(((0 * m + j) * G + g) << 1) + 1] = live * Sinv.b;
+      fs[(((1 * m + j) * G + g) << 1) + 0] = live * Sinv.d;
+      fs[(((1 * m + j) * G + g) << 1) + 1] = live * mf[mf_addr(21, s, m, G)];
     }
     for (int l = 0; l < P.levels; ++l)
       for (int g = 0; g < G; ++g) {

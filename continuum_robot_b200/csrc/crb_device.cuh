@@ -146,6 +146,177 @@ __device__ __forceinline__ void mass_solve(double (&b)[M][3], const MassConsts<M
 }
 
 // ------------------------------------------------------------------------------------------
+// Uniform-mass solve (used by the fast kernels of crb_rk4_fast.cuh and by the shape-specialised
+// general kernels).  The element coupling block O of the consistent mass matrix
+// (models/segments.py:64-78) is identical for every element of a uniform-mass beam, so only Sinv
+// (4 doubles / slot) and the scan products are read from shared memory (the "compact copy" that
+// crb_assemble appends to every factor set); boundary corrections are recomputed by a second
+// local sweep instead of stored spike vectors (2.5x fewer LDS wavefronts than mass_solve):
+//
+//   forward  A: y~_last      (zero incoming)         -> Kogge-Stone scan -> y_last, xhat_in
+//   forward  B: y_s = b_s - O Sinv_{s-1} y_{s-1}                  (true incoming; keeps y_s)
+//   backward A: x~_first     (zero incoming)         -> scan -> x_first, x_in
+//   backward B: x_s = Sinv_s (y_s - O^T x_{s+1})                  (true incoming)
+//
+// Phantom slots (beyond the last node) carry Sinv = 0 in the compact copy, which decouples them.
+// Requires a plan without constrained DOFs inside active slots (has_mask == 0).
+// ------------------------------------------------------------------------------------------
+struct UniformMass {
+  double o11, o12, o22, ou;  // 54 mu, 13 L mu, 3 L^2 mu, 70 mu   (mu = rho A L / 420)
+};
+
+
+// what the uniform-mass solve needs from a lane
+struct FastMass {
+  int g;                // lane within the member
+  const double* fslot;  // compact Sinv copy   [pair 0..1][j][g] double2 (shared memory)
+  const double* fscan;  // compact scan copy   [level][pair 0..4][g] double2
+  UniformMass um;
+};
+
+template <int M, int G, typename CT>
+__device__ __forceinline__ double2 ld_fslot(const CT& C, int pair, int j) {
+  return *reinterpret_cast<const double2*>(C.fslot + (((pair * M + j) * G + C.g) << 1));
+}
+template <int M, int G, typename CT>
+__device__ __forceinline__ double2 ld_fscan(const CT& C, int level, int pair) {
+  return *reinterpret_cast<const double2*>(C.fscan + (((level * 5 + pair) * G + C.g) << 1));
+}
+
+// Mass solve of R right-hand sides at once (they share every constant read from shared memory).
+template <int M, int LV, int R, typename CT>
+__device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const CT& C) {
+  constexpr int G = 1 << LV;
+  const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
+  double s00[M], s01[M], s11[M], su[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const double2 a = ld_fslot<M, G, CT>(C, 0, j), c = ld_fslot<M, G, CT>(C, 1, j);
+    s00[j] = a.x;
+    s01[j] = a.y;
+    s11[j] = c.x;
+    su[j] = c.y;
+  }
+  double y0[R], y1[R], y2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { y0[r] = b[r][0][0]; y1[r] = b[r][0][1]; y2[r] = b[r][0][2]; }
+  // ---- forward A ----
+#pragma unroll
+  for (int j = 1; j < M; ++j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double xu = su[j - 1] * y0[r];
+      const double xw = fma(s00[j - 1], y1[r], s01[j - 1] * y2[r]);
+      const double xp = fma(s01[j - 1], y1[r], s11[j - 1] * y2[r]);
+      y0[r] = fma(-ou, xu, b[r][j][0]);
+      y1[r] = fma(-o11, xw, fma(o12, xp, b[r][j][1]));
+      y2[r] = fma(-o12, xw, fma(o22, xp, b[r][j][2]));
+    }
+  double xi0[R], xi1[R], xi2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
+  double cub[LV > 0 ? LV : 1];
+  if (G > 1) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+      const int d = 1 << l;
+      const double2 c0 = ld_fscan<M, G, CT>(C, l, 0), c1 = ld_fscan<M, G, CT>(C, l, 1), cu = ld_fscan<M, G, CT>(C, l, 4);
+      cub[l] = cu.y;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double t0 = shfl_up_d(y0[r], d, G), t1 = shfl_up_d(y1[r], d, G), t2 = shfl_up_d(y2[r], d, G);
+        y0[r] = fma(cu.x, t0, y0[r]);
+        mv2(c0, c1, t1, t2, y1[r], y2[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double xu = su[M - 1] * y0[r];
+      const double xw = fma(s00[M - 1], y1[r], s01[M - 1] * y2[r]);
+      const double xp = fma(s01[M - 1], y1[r], s11[M - 1] * y2[r]);
+      xi0[r] = shfl_up_d(xu, 1, G);
+      xi1[r] = shfl_up_d(xw, 1, G);
+      xi2[r] = shfl_up_d(xp, 1, G);
+      if (C.g == 0) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
+    }
+  }
+  // ---- forward B: true incoming; b[j] <- y_j (the forward-substituted right-hand side) ----
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double t0 = fma(-ou, xi0[r], b[r][j][0]);
+      const double t1 = fma(-o11, xi1[r], fma(o12, xi2[r], b[r][j][1]));
+      const double t2 = fma(-o12, xi1[r], fma(o22, xi2[r], b[r][j][2]));
+      b[r][j][0] = t0;
+      b[r][j][1] = t1;
+      b[r][j][2] = t2;
+      if (j < M - 1) {  // xhat_j = Sinv_j y_j feeds the next slot; the last one is only needed by backward A
+        xi0[r] = su[j] * t0;
+        xi1[r] = fma(s00[j], t1, s01[j] * t2);
+        xi2[r] = fma(s01[j], t1, s11[j] * t2);
+      }
+    }
+  // ---- backward A: x~ at the chunk's first slot, zero incoming; x_j = Sinv_j (y_j - O^T x_{j+1}) ----
+  double r0[R], r1[R], r2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    r0[r] = su[M - 1] * b[r][M - 1][0];
+    r1[r] = fma(s00[M - 1], b[r][M - 1][1], s01[M - 1] * b[r][M - 1][2]);
+    r2[r] = fma(s01[M - 1], b[r][M - 1][1], s11[M - 1] * b[r][M - 1][2]);
+  }
+#pragma unroll
+  for (int j = M - 2; j >= 0; --j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double t0 = fma(-ou, r0[r], b[r][j][0]);
+      const double t1 = fma(-o11, r1[r], fma(-o12, r2[r], b[r][j][1]));
+      const double t2 = fma(o12, r1[r], fma(o22, r2[r], b[r][j][2]));
+      r0[r] = su[j] * t0;
+      r1[r] = fma(s00[j], t1, s01[j] * t2);
+      r2[r] = fma(s01[j], t1, s11[j] * t2);
+    }
+  double n0[R], n1[R], n2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
+  if (G > 1) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+      const int d = 1 << l;
+      const double2 c0 = ld_fscan<M, G, CT>(C, l, 2), c1 = ld_fscan<M, G, CT>(C, l, 3);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double t0 = shfl_down_d(r0[r], d, G), t1 = shfl_down_d(r1[r], d, G), t2 = shfl_down_d(r2[r], d, G);
+        r0[r] = fma(cub[l], t0, r0[r]);
+        mv2(c0, c1, t1, t2, r1[r], r2[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      n0[r] = shfl_down_d(r0[r], 1, G);
+      n1[r] = shfl_down_d(r1[r], 1, G);
+      n2[r] = shfl_down_d(r2[r], 1, G);
+      if (C.g == G - 1) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
+    }
+  }
+  // ---- backward B: true incoming; b[j] <- x_j ----
+#pragma unroll
+  for (int j = M - 1; j >= 0; --j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double t0 = fma(-ou, n0[r], b[r][j][0]);
+      const double t1 = fma(-o11, n1[r], fma(-o12, n2[r], b[r][j][1]));
+      const double t2 = fma(o12, n1[r], fma(o22, n2[r], b[r][j][2]));
+      n0[r] = su[j] * t0;
+      n1[r] = fma(s00[j], t1, s01[j] * t2);
+      n2[r] = fma(s01[j], t1, s11[j] * t2);
+      b[r][j][0] = n0[r];
+      b[r][j][1] = n1[r];
+      b[r][j][2] = n2[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Element forces.  `c` = 4 coefficients written by crb_assemble for the element's type.
 // Both accumulate  bA -= f[0:3]  (node 1) and  bB -= f[3:6]  (node 2).
 // ------------------------------------------------------------------------------------------
@@ -265,6 +436,7 @@ struct LaneCtx {
   double drag[M];        // drag factor of own slot (0 = none)
   double gl[M], gt[M];   // gravity half masses: two-ended pseudo-segment left of slot, tail
   MassConsts<M> mc;
+  FastMass fm;           // uniform-mass solve constants (shape-specialised kernels)
   double* scratch;       // shared-memory scratch of this member (2n doubles) or nullptr
 };
 
@@ -345,7 +517,8 @@ static __device__ __noinline__ void grav_pair(double phi, double hm, double gx, 
 
 // a = M^-1 ( -k(q) + f(x) + u(t) ) for the lane's slots.  q, v: stage state; out: acceleration.
 // ONLY_FORCES: skip stiffness, inputs and the mass solve -> acc = built-in force vector f(x)
-template <int M, unsigned FEAT = CRB_F_ALL, bool ONLY_FORCES = false>
+// LVU >= 0: uniform-mass solve with 1 << LVU lanes per member (L.fm); LVU = -1: stored-spike mass_solve (L.mc)
+template <int M, unsigned FEAT = CRB_F_ALL, bool ONLY_FORCES = false, int LVU = -1>
 __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system_t& S, const RhsFlags F0,
                                            const double (&q)[M][3], const double (&v)[M][3],
                                            double t, double (&acc)[M][3]) {
@@ -546,7 +719,22 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
       for (int d = 0; d < 3; ++d)
         if (L.ri[j][d] < 0) acc[j][d] = 0.0;
   }
-  if (!ONLY_FORCES) mass_solve<M>(acc, L.mc, L.levels);
+  if (!ONLY_FORCES) {
+    if constexpr (LVU >= 0) {
+      double b[1][M][3];
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) b[0][j][d] = acc[j][d];
+      fast_solve_r<M, (LVU >= 0 ? LVU : 0), 1>(b, L.fm);
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) acc[j][d] = b[0][j][d];
+    } else {
+      mass_solve<M>(acc, L.mc, L.levels);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -566,6 +754,23 @@ __device__ __forceinline__ const double* stage_mfac(const crb_system_t& S, const
   for (int k = threadIdx.x; k < (int)P.mfac_doubles; k += blockDim.x) smem[k] = S.mfac[k];
   __syncthreads();
   return smem;
+}
+
+// Shape-specialised kernels: stage only the compact (Sinv + scan products) copy of the shared factor set.
+template <int M, int LV>
+__device__ __forceinline__ void stage_compact(const crb_system_t& S, double* smem, FastMass& fm, int g) {
+  constexpr int G = 1 << LV, LVE = LV > 0 ? LV : 1;
+  constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
+  const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+  for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+  __syncthreads();
+  fm.g = g;
+  fm.fslot = smem;
+  fm.fscan = smem + 4 * M * G;
+  fm.um.o11 = S.um[0];
+  fm.um.o12 = S.um[1];
+  fm.um.o22 = S.um[2];
+  fm.um.ou = S.um[3];
 }
 
 template <int M>

@@ -9,7 +9,11 @@ __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
                int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  const double* mf = stage_mfac(S, P, smem);
+  // Shape-specialised LINEAR kernels (profile A) use the uniform-mass solve on the compact factor copy
+  // (measured +30 % on config 3's shape: they are shared-memory bound with the stored-spike solve); the
+  // nonlinear profile is FP64-bound and keeps the stored spikes (the re-sweep costs 6-7 % there).
+  constexpr bool UMS = LV >= 0 && FEAT == CRB_F_PROFILE_A;
+  const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Gk = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g;
   const int mpw = 32 / Gk;
@@ -21,9 +25,13 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   if (LV >= 0) {  // let the compiler see the constants
     L.G = Gk;
     L.levels = LV;
-    L.mc.G = Gk;
-    L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
-    L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * Gk);
+    if (UMS) {
+      stage_compact<M, (LV >= 0 ? LV : 0)>(S, smem, L.fm, lane % Gk);
+    } else {
+      L.mc.G = Gk;
+      L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
+      L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * Gk);
+    }
   }
   const RhsFlags F = make_flags(S, P);
   double q[M][3], v[M][3];
@@ -45,7 +53,7 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
       const double ts = t + (st == 0 ? 0.0 : (st == 3 ? h : hh));
-      beam_accel<M, FEAT>(L, S, F, qs, vs, ts, a);
+      beam_accel<M, FEAT, false, (UMS ? LV : -1)>(L, S, F, qs, vs, ts, a);
       const double wgt = (st == 0 || st == 3) ? h6 : h3;  // b = (1/6, 1/3, 1/3, 1/6)
       const double cn = st == 2 ? h : hh;                 // next stage: x + c k
 #pragma unroll
@@ -84,7 +92,9 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
   const unsigned need = crb_needed_features(plan, sys);
   const unsigned prof = crb_pick_profile(need);
 #define CRB_RK4_CASE(MM, LL)                                                                                       \
-  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared) {                                                   \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared &&                               \
+      (prof == CRB_F_PROFILE_B || crb_specialised_ok(plan, sys))) {                                                 \
+    const SmemLayout SL = prof == CRB_F_PROFILE_A ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
     if (prof == CRB_F_PROFILE_A) {                                                                                  \
       if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL>, bytes, "crb_rk4")) return rc;                  \
       crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \

@@ -108,7 +108,11 @@ template <int M, unsigned FEAT, int LV>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   extern __shared__ __align__(16) double smem[];
-  const double* mf = stage_mfac(S, P, smem);
+  // Shape-specialised LINEAR kernels (profile A) use the uniform-mass solve on the compact factor copy
+  // (measured +30 % on config 3's shape: they are shared-memory bound with the stored-spike solve); the
+  // nonlinear profile is FP64-bound and keeps the stored spikes (the re-sweep costs 6-7 % there).
+  constexpr bool UMS = LV >= 0 && FEAT == CRB_F_PROFILE_A;
+  const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g, mpw = 32 / G;
   const int mloc = warp * mpw + lane / G;
@@ -120,9 +124,13 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   if (LV >= 0) {
     L.G = G;
     L.levels = LV;
-    L.mc.G = G;
-    L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
-    L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * G);
+    if (UMS) {
+      stage_compact<M, (LV >= 0 ? LV : 0)>(S, smem, L.fm, lane % G);
+    } else {
+      L.mc.G = G;
+      L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
+      L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * G);
+    }
   }
   const RhsFlags F = make_flags(S, P);
   // kv stage storage: [stage 0..6][j][d][thread]
@@ -209,7 +217,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   };
 
   while (true) {
-    beam_accel<M, FEAT>(L, S, F, qs, vs, ts, a);
+    beam_accel<M, FEAT, false, (UMS ? LV : -1)>(L, S, F, qs, vs, ts, a);
     if (phase == 0) {
       nfev += 1;
 #pragma unroll

@@ -33,10 +33,6 @@
 #endif
 #define CRB_FAST_THREADS (32 * CRB_FAST_WARPS)
 
-struct UniformMass {
-  double o11, o12, o22, ou;  // 54 mu, 13 L mu, 3 L^2 mu, 70 mu   (mu = rho A L / 420)
-};
-
 template <int M>
 struct FastCtx {
   int g;
@@ -51,148 +47,6 @@ struct FastCtx {
   double imp_amp, imp_dur;
   int imp_local;
 };
-
-template <int M, int G>
-__device__ __forceinline__ double2 ld_fslot(const FastCtx<M>& C, int pair, int j) {
-  return *reinterpret_cast<const double2*>(C.fslot + (((pair * M + j) * G + C.g) << 1));
-}
-template <int M, int G>
-__device__ __forceinline__ double2 ld_fscan(const FastCtx<M>& C, int level, int pair) {
-  return *reinterpret_cast<const double2*>(C.fscan + (((level * 5 + pair) * G + C.g) << 1));
-}
-
-// Mass solve of R right-hand sides at once (they share every constant read from shared memory).
-template <int M, int LV, int R>
-__device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const FastCtx<M>& C) {
-  constexpr int G = 1 << LV;
-  const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
-  double s00[M], s01[M], s11[M], su[M];
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const double2 a = ld_fslot<M, G>(C, 0, j), c = ld_fslot<M, G>(C, 1, j);
-    s00[j] = a.x;
-    s01[j] = a.y;
-    s11[j] = c.x;
-    su[j] = c.y;
-  }
-  double y0[R], y1[R], y2[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) { y0[r] = b[r][0][0]; y1[r] = b[r][0][1]; y2[r] = b[r][0][2]; }
-  // ---- forward A ----
-#pragma unroll
-  for (int j = 1; j < M; ++j)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double xu = su[j - 1] * y0[r];
-      const double xw = fma(s00[j - 1], y1[r], s01[j - 1] * y2[r]);
-      const double xp = fma(s01[j - 1], y1[r], s11[j - 1] * y2[r]);
-      y0[r] = fma(-ou, xu, b[r][j][0]);
-      y1[r] = fma(-o11, xw, fma(o12, xp, b[r][j][1]));
-      y2[r] = fma(-o12, xw, fma(o22, xp, b[r][j][2]));
-    }
-  double xi0[R], xi1[R], xi2[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
-  double cub[LV > 0 ? LV : 1];
-  if (G > 1) {
-#pragma unroll
-    for (int l = 0; l < LV; ++l) {
-      const int d = 1 << l;
-      const double2 c0 = ld_fscan<M, G>(C, l, 0), c1 = ld_fscan<M, G>(C, l, 1), cu = ld_fscan<M, G>(C, l, 4);
-      cub[l] = cu.y;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const double t0 = shfl_up_d(y0[r], d, G), t1 = shfl_up_d(y1[r], d, G), t2 = shfl_up_d(y2[r], d, G);
-        y0[r] = fma(cu.x, t0, y0[r]);
-        mv2(c0, c1, t1, t2, y1[r], y2[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double xu = su[M - 1] * y0[r];
-      const double xw = fma(s00[M - 1], y1[r], s01[M - 1] * y2[r]);
-      const double xp = fma(s01[M - 1], y1[r], s11[M - 1] * y2[r]);
-      xi0[r] = shfl_up_d(xu, 1, G);
-      xi1[r] = shfl_up_d(xw, 1, G);
-      xi2[r] = shfl_up_d(xp, 1, G);
-      if (C.g == 0) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
-    }
-  }
-  // ---- forward B: true incoming; b[j] <- y_j (the forward-substituted right-hand side) ----
-#pragma unroll
-  for (int j = 0; j < M; ++j)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double t0 = fma(-ou, xi0[r], b[r][j][0]);
-      const double t1 = fma(-o11, xi1[r], fma(o12, xi2[r], b[r][j][1]));
-      const double t2 = fma(-o12, xi1[r], fma(o22, xi2[r], b[r][j][2]));
-      b[r][j][0] = t0;
-      b[r][j][1] = t1;
-      b[r][j][2] = t2;
-      if (j < M - 1) {  // xhat_j = Sinv_j y_j feeds the next slot; the last one is only needed by backward A
-        xi0[r] = su[j] * t0;
-        xi1[r] = fma(s00[j], t1, s01[j] * t2);
-        xi2[r] = fma(s01[j], t1, s11[j] * t2);
-      }
-    }
-  // ---- backward A: x~ at the chunk's first slot, zero incoming; x_j = Sinv_j (y_j - O^T x_{j+1}) ----
-  double r0[R], r1[R], r2[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    r0[r] = su[M - 1] * b[r][M - 1][0];
-    r1[r] = fma(s00[M - 1], b[r][M - 1][1], s01[M - 1] * b[r][M - 1][2]);
-    r2[r] = fma(s01[M - 1], b[r][M - 1][1], s11[M - 1] * b[r][M - 1][2]);
-  }
-#pragma unroll
-  for (int j = M - 2; j >= 0; --j)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double t0 = fma(-ou, r0[r], b[r][j][0]);
-      const double t1 = fma(-o11, r1[r], fma(-o12, r2[r], b[r][j][1]));
-      const double t2 = fma(o12, r1[r], fma(o22, r2[r], b[r][j][2]));
-      r0[r] = su[j] * t0;
-      r1[r] = fma(s00[j], t1, s01[j] * t2);
-      r2[r] = fma(s01[j], t1, s11[j] * t2);
-    }
-  double n0[R], n1[R], n2[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
-  if (G > 1) {
-#pragma unroll
-    for (int l = 0; l < LV; ++l) {
-      const int d = 1 << l;
-      const double2 c0 = ld_fscan<M, G>(C, l, 2), c1 = ld_fscan<M, G>(C, l, 3);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const double t0 = shfl_down_d(r0[r], d, G), t1 = shfl_down_d(r1[r], d, G), t2 = shfl_down_d(r2[r], d, G);
-        r0[r] = fma(cub[l], t0, r0[r]);
-        mv2(c0, c1, t1, t2, r1[r], r2[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      n0[r] = shfl_down_d(r0[r], 1, G);
-      n1[r] = shfl_down_d(r1[r], 1, G);
-      n2[r] = shfl_down_d(r2[r], 1, G);
-      if (C.g == G - 1) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
-    }
-  }
-  // ---- backward B: true incoming; b[j] <- x_j ----
-#pragma unroll
-  for (int j = M - 1; j >= 0; --j)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double t0 = fma(-ou, n0[r], b[r][j][0]);
-      const double t1 = fma(-o11, n1[r], fma(-o12, n2[r], b[r][j][1]));
-      const double t2 = fma(o12, n1[r], fma(o22, n2[r], b[r][j][2]));
-      n0[r] = su[j] * t0;
-      n1[r] = fma(s00[j], t1, s01[j] * t2);
-      n2[r] = fma(s01[j], t1, s11[j] * t2);
-      b[r][j][0] = n0[r];
-      b[r][j][1] = n1[r];
-      b[r][j][2] = n2[r];
-    }
-}
 
 // Linear element force as VALUES: f on node 1 = (fu, V, m1), on node 2 = (-fu, -V, m2)
 // (models/segments.py:32-62); c = (EA/L, 12EI/L^3, 6EI/L^2, 2EI/L).
