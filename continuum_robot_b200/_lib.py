@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 101
+CRB_VERSION = 102
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -61,11 +61,8 @@ class CrbSystem(C.Structure):
         ("f_ext", C.c_void_p),
         ("all_linear", C.c_int32),
         ("all_nonlinear", C.c_int32),
-        ("uniform_mass", C.c_int32),
         ("force_general", C.c_int32),
         ("force_staged", C.c_int32),
-        ("um", C.c_double * 4),
-        ("um_members", C.c_void_p),
         ("shared_op", C.c_void_p),
         ("shared_op_doubles", C.c_int64),
     ]

@@ -66,7 +66,7 @@ extern "C" int crb_plan(int32_t n_elements, const uint8_t* bc, int32_t max_slots
   out->contiguous = contiguous;
   out->has_mask = !contiguous;
   out->mfac_doubles = 2ll * CRB_SLOT_PAIRS * out->p + 2ll * CRB_SCAN_PAIRS * (levels > 0 ? levels : 1) * g +
-                      4ll * out->p + 10ll * (levels > 0 ? levels : 1) * g;  // + compact copy for the fast kernels
+                      crb_compact_doubles(out->m, g, levels);  // + compact copy (crb_device.cuh::fast_solve_r)
   out->kcoef_doubles = 4ll * out->p;
   return 0;
 }
@@ -222,11 +222,11 @@ extern "C" int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const
   return 0;
 }
 
-// fast path: all-linear, uniform element mass, contiguous plan without phantom slots, no
-// forces and no input other than a constant force / tip impulse (BASELINE config 3 shape)
+// fast path: all-linear, contiguous plan without phantom slots, no forces and no input other than
+// a constant force / tip impulse (BASELINE config 3 shape); any mass distribution, shared or per member
 static bool rk4_fast_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
-  return sys->all_linear && sys->uniform_mass && plan->contiguous && plan->p_act == plan->p && !sys->drag &&
-         sys->grav_mode == 0 && !sys->gain && !sys->force_general && (sys->mass_shared || sys->um_members);
+  return sys->all_linear && plan->contiguous && plan->p_act == plan->p && !sys->drag && sys->grav_mode == 0 &&
+         !sys->gain && !sys->force_general;
 }
 
 extern "C" int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* sys, int32_t* out) {

@@ -301,21 +301,28 @@ crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n
       sc[sc_addr(l, 10, g, G)] = cbu;
     }
   }
-  // ---- compact copy for the uniform-mass fast kernels (crb_rk4_fast.cuh):
-  //   slot part  [pair 0..1][j][g]:  (s00, s01), (s11, sinv_u)
+  // ---- compact copy for the compact solve (crb_device.cuh::fast_solve_r):
+  //   slot part  [pair 0..3][j][g]: (s00, s01), (s11, sinv_u), (t00, t01), (t10, t11) with T = -Lm,
+  //              then [jj][g]: (tu_{2jj}, tu_{2jj+1}) with tu = -lu
   //   scan part  [level][pair 0..4][g]: C fwd (2 pairs), C bwd (2 pairs), (cu_fwd, cu_bwd)
   {
     const int lv = P.levels > 0 ? P.levels : 1;
     double* fs = sc + 2 * CRB_SCAN_PAIRS * lv * G;
-    double* fc = fs + 4 * Pn;
+    double* fc = fs + crb_compact_slot_doubles(m, G);
     for (int s = 0; s < Pn; ++s) {
       const int g = s / m, j = s - g * m;
       const M2 Sinv = ld_m2(mf, 4, s, m, G);
-      const double live = s < P.p_act ? 1.0 : 0.0;  // phantom slots: Sinv = 0 decouples them in the uniform-mass solve
+      const M2 Lm = ld_m2(mf, 0, s, m, G);
+      const double live = s < P.p_act ? 1.0 : 0.0;  // phantom slots: Sinv = 0 keeps their solution at exactly 0
       fs[(((0 * m + j) * G + g) << 1) + 0] = live * Sinv.a;
       fs[(((0 * m + j) * G + g) << 1) + 1] = live * Sinv.b;
       fs[(((1 * m + j) * G + g) << 1) + 0] = live * Sinv.d;
       fs[(((1 * m + j) * G + g) << 1) + 1] = live * mf[mf_addr(21, s, m, G)];
+      fs[(((2 * m + j) * G + g) << 1) + 0] = -Lm.a;
+      fs[(((2 * m + j) * G + g) << 1) + 1] = -Lm.b;
+      fs[(((3 * m + j) * G + g) << 1) + 0] = -Lm.c;
+      fs[(((3 * m + j) * G + g) << 1) + 1] = -Lm.d;
+      fs[(((4 * m + (j >> 1)) * G + g) << 1) + (j & 1)] = -mf[mf_addr(20, s, m, G)];
     }
     for (int l = 0; l < P.levels; ++l)
       for (int g = 0; g < G; ++g) {

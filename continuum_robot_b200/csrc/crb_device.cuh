@@ -146,32 +146,34 @@ __device__ __forceinline__ void mass_solve(double (&b)[M][3], const MassConsts<M
 }
 
 // ------------------------------------------------------------------------------------------
-// Uniform-mass solve (used by the fast kernels of crb_rk4_fast.cuh and by the shape-specialised
-// general kernels).  The element coupling block O of the consistent mass matrix
-// (models/segments.py:64-78) is identical for every element of a uniform-mass beam, so only Sinv
-// (4 doubles / slot) and the scan products are read from shared memory (the "compact copy" that
-// crb_assemble appends to every factor set); boundary corrections are recomputed by a second
-// local sweep instead of stored spike vectors (2.5x fewer LDS wavefronts than mass_solve):
+// Compact mass solve (fast kernels of crb_rk4_fast.cuh and the shape-specialised linear general
+// kernels).  Same block-LDL^T factors as mass_solve, but the partition (SPIKE) corrections are
+// RECOMPUTED by a second local sweep instead of being read as stored spike vectors: per slot only
+// Sinv (4 doubles) and T = -Lm (5 doubles, the unit-lower block coupling a slot to its left
+// neighbour) come from shared memory -- 4.5 LDS.128 per slot and solve instead of 13 -- and every
+// sweep is a chain of pure DFMAs (5 per slot):
 //
-//   forward  A: y~_last      (zero incoming)         -> Kogge-Stone scan -> y_last, xhat_in
-//   forward  B: y_s = b_s - O Sinv_{s-1} y_{s-1}                  (true incoming; keeps y_s)
-//   backward A: x~_first     (zero incoming)         -> scan -> x_first, x_in
-//   backward B: x_s = Sinv_s (y_s - O^T x_{s+1})                  (true incoming)
+//   forward  A: y~_j = b_j + T_j y~_{j-1}  (zero incoming)  -> Kogge-Stone scan -> y_last of every lane
+//   forward  B: y_j  = b_j + T_j y_{j-1}   (true incoming y from the left lane)
+//   diagonal  : xhat_j = Sinv_j y_j
+//   backward A: x~_j = xhat_j + T_{j+1}^T x~_{j+1}  (zero incoming) -> scan -> x_first of every lane
+//   backward B: x_j  = xhat_j + T_{j+1}^T x_{j+1}   (the right lane sends T_0^T x_first)
 //
-// Phantom slots (beyond the last node) carry Sinv = 0 in the compact copy, which decouples them.
-// Requires a plan without constrained DOFs inside active slots (has_mask == 0).
+// The factors are the true ones, so non-uniform mass, phantom slots (T = 0) and identity rows of
+// constrained DOFs are handled like in mass_solve.  "Compact copy" layout appended by crb_assemble
+// to every factor set:  slot part [pair 0..3][j][g] double2 = (s00,s01) (s11,sinv_u) (t00,t01) (t10,t11),
+// then [jj < ceil(M/2)][g] double2 = (tu_{2jj}, tu_{2jj+1});  scan part [level][pair 0..4][g] double2.
 // ------------------------------------------------------------------------------------------
-struct UniformMass {
-  double o11, o12, o22, ou;  // 54 mu, 13 L mu, 3 L^2 mu, 70 mu   (mu = rho A L / 420)
-};
+__host__ __device__ constexpr int crb_compact_slot_doubles(int m, int g) { return 2 * g * (4 * m + (m + 1) / 2); }
+__host__ __device__ constexpr int crb_compact_doubles(int m, int g, int levels) {
+  return crb_compact_slot_doubles(m, g) + 10 * (levels > 0 ? levels : 1) * g;
+}
 
-
-// what the uniform-mass solve needs from a lane
+// what the compact solve needs from a lane
 struct FastMass {
   int g;                // lane within the member
-  const double* fslot;  // compact Sinv copy   [pair 0..1][j][g] double2 (shared memory)
-  const double* fscan;  // compact scan copy   [level][pair 0..4][g] double2
-  UniformMass um;
+  const double* fslot;  // slot part of the compact copy (shared memory)
+  const double* fscan;  // scan part
 };
 
 template <int M, int G, typename CT>
@@ -187,35 +189,39 @@ __device__ __forceinline__ double2 ld_fscan(const CT& C, int level, int pair) {
 template <int M, int LV, int R, typename CT>
 __device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const CT& C) {
   constexpr int G = 1 << LV;
-  const double o11 = C.um.o11, o12 = C.um.o12, o22 = C.um.o22, ou = C.um.ou;
-  double s00[M], s01[M], s11[M], su[M];
+  // T_j = -Lm of the lane's own slots stays in registers for the four sweeps
+  double t00[M], t01[M], t10[M], t11[M], tu[M + 1];
 #pragma unroll
   for (int j = 0; j < M; ++j) {
-    const double2 a = ld_fslot<M, G, CT>(C, 0, j), c = ld_fslot<M, G, CT>(C, 1, j);
-    s00[j] = a.x;
-    s01[j] = a.y;
-    s11[j] = c.x;
-    su[j] = c.y;
+    const double2 a = ld_fslot<M, G, CT>(C, 2, j), c = ld_fslot<M, G, CT>(C, 3, j);
+    t00[j] = a.x;
+    t01[j] = a.y;
+    t10[j] = c.x;
+    t11[j] = c.y;
+  }
+#pragma unroll
+  for (int jj = 0; jj < (M + 1) / 2; ++jj) {
+    const double2 u = ld_fslot<M, G, CT>(C, 4, jj);  // address ((4 M + jj) G + g): the tu block follows pair 3
+    tu[2 * jj] = u.x;
+    tu[2 * jj + 1] = u.y;
   }
   double y0[R], y1[R], y2[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) { y0[r] = b[r][0][0]; y1[r] = b[r][0][1]; y2[r] = b[r][0][2]; }
-  // ---- forward A ----
+  // ---- forward A: y~ at the chunk's last slot, zero incoming ----
 #pragma unroll
   for (int j = 1; j < M; ++j)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double xu = su[j - 1] * y0[r];
-      const double xw = fma(s00[j - 1], y1[r], s01[j - 1] * y2[r]);
-      const double xp = fma(s01[j - 1], y1[r], s11[j - 1] * y2[r]);
-      y0[r] = fma(-ou, xu, b[r][j][0]);
-      y1[r] = fma(-o11, xw, fma(o12, xp, b[r][j][1]));
-      y2[r] = fma(-o12, xw, fma(o22, xp, b[r][j][2]));
+      const double p1 = y1[r], p2 = y2[r];
+      y0[r] = fma(tu[j], y0[r], b[r][j][0]);
+      y1[r] = fma(t00[j], p1, fma(t01[j], p2, b[r][j][1]));
+      y2[r] = fma(t10[j], p1, fma(t11[j], p2, b[r][j][2]));
     }
-  double xi0[R], xi1[R], xi2[R];
+  double xi0[R], xi1[R], xi2[R];  // y of the left neighbour's last slot
 #pragma unroll
   for (int r = 0; r < R; ++r) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
-  double cub[LV > 0 ? LV : 1];
+  double cub[LV > 0 ? LV : 1];  // u-scan coefficients of the backward scan (loaded with the forward ones)
   if (G > 1) {
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
@@ -224,59 +230,48 @@ __device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const CT& C) 
       cub[l] = cu.y;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const double t0 = shfl_up_d(y0[r], d, G), t1 = shfl_up_d(y1[r], d, G), t2 = shfl_up_d(y2[r], d, G);
-        y0[r] = fma(cu.x, t0, y0[r]);
-        mv2(c0, c1, t1, t2, y1[r], y2[r]);
+        const double s0 = shfl_up_d(y0[r], d, G), s1 = shfl_up_d(y1[r], d, G), s2 = shfl_up_d(y2[r], d, G);
+        y0[r] = fma(cu.x, s0, y0[r]);
+        mv2(c0, c1, s1, s2, y1[r], y2[r]);
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double xu = su[M - 1] * y0[r];
-      const double xw = fma(s00[M - 1], y1[r], s01[M - 1] * y2[r]);
-      const double xp = fma(s01[M - 1], y1[r], s11[M - 1] * y2[r]);
-      xi0[r] = shfl_up_d(xu, 1, G);
-      xi1[r] = shfl_up_d(xw, 1, G);
-      xi2[r] = shfl_up_d(xp, 1, G);
+      xi0[r] = shfl_up_d(y0[r], 1, G);
+      xi1[r] = shfl_up_d(y1[r], 1, G);
+      xi2[r] = shfl_up_d(y2[r], 1, G);
       if (C.g == 0) { xi0[r] = 0.0; xi1[r] = 0.0; xi2[r] = 0.0; }
     }
   }
-  // ---- forward B: true incoming; b[j] <- y_j (the forward-substituted right-hand side) ----
+  // ---- forward B (true incoming), then the block-diagonal solve: b[j] <- xhat_j = Sinv_j y_j ----
 #pragma unroll
-  for (int j = 0; j < M; ++j)
+  for (int j = 0; j < M; ++j) {
+    const double2 sa = ld_fslot<M, G, CT>(C, 0, j), sc = ld_fslot<M, G, CT>(C, 1, j);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double t0 = fma(-ou, xi0[r], b[r][j][0]);
-      const double t1 = fma(-o11, xi1[r], fma(o12, xi2[r], b[r][j][1]));
-      const double t2 = fma(-o12, xi1[r], fma(o22, xi2[r], b[r][j][2]));
-      b[r][j][0] = t0;
-      b[r][j][1] = t1;
-      b[r][j][2] = t2;
-      if (j < M - 1) {  // xhat_j = Sinv_j y_j feeds the next slot; the last one is only needed by backward A
-        xi0[r] = su[j] * t0;
-        xi1[r] = fma(s00[j], t1, s01[j] * t2);
-        xi2[r] = fma(s01[j], t1, s11[j] * t2);
-      }
+      const double p1 = xi1[r], p2 = xi2[r];
+      xi0[r] = fma(tu[j], xi0[r], b[r][j][0]);
+      xi1[r] = fma(t00[j], p1, fma(t01[j], p2, b[r][j][1]));
+      xi2[r] = fma(t10[j], p1, fma(t11[j], p2, b[r][j][2]));
+      b[r][j][0] = sc.y * xi0[r];
+      b[r][j][1] = fma(sa.x, xi1[r], sa.y * xi2[r]);
+      b[r][j][2] = fma(sa.y, xi1[r], sc.x * xi2[r]);
     }
-  // ---- backward A: x~ at the chunk's first slot, zero incoming; x_j = Sinv_j (y_j - O^T x_{j+1}) ----
+  }
+  // ---- backward A: x~ at the chunk's first slot, zero incoming ----
   double r0[R], r1[R], r2[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    r0[r] = su[M - 1] * b[r][M - 1][0];
-    r1[r] = fma(s00[M - 1], b[r][M - 1][1], s01[M - 1] * b[r][M - 1][2]);
-    r2[r] = fma(s01[M - 1], b[r][M - 1][1], s11[M - 1] * b[r][M - 1][2]);
-  }
+  for (int r = 0; r < R; ++r) { r0[r] = b[r][M - 1][0]; r1[r] = b[r][M - 1][1]; r2[r] = b[r][M - 1][2]; }
 #pragma unroll
   for (int j = M - 2; j >= 0; --j)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double t0 = fma(-ou, r0[r], b[r][j][0]);
-      const double t1 = fma(-o11, r1[r], fma(-o12, r2[r], b[r][j][1]));
-      const double t2 = fma(o12, r1[r], fma(o22, r2[r], b[r][j][2]));
-      r0[r] = su[j] * t0;
-      r1[r] = fma(s00[j], t1, s01[j] * t2);
-      r2[r] = fma(s01[j], t1, s11[j] * t2);
+      const double p1 = r1[r], p2 = r2[r];
+      r0[r] = fma(tu[j + 1], r0[r], b[r][j][0]);
+      r1[r] = fma(t00[j + 1], p1, fma(t10[j + 1], p2, b[r][j][1]));
+      r2[r] = fma(t01[j + 1], p1, fma(t11[j + 1], p2, b[r][j][2]));
     }
-  double n0[R], n1[R], n2[R];
+  double n0[R], n1[R], n2[R];  // T_0^T x_first of the right neighbour
 #pragma unroll
   for (int r = 0; r < R; ++r) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
   if (G > 1) {
@@ -286,30 +281,40 @@ __device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const CT& C) 
       const double2 c0 = ld_fscan<M, G, CT>(C, l, 2), c1 = ld_fscan<M, G, CT>(C, l, 3);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const double t0 = shfl_down_d(r0[r], d, G), t1 = shfl_down_d(r1[r], d, G), t2 = shfl_down_d(r2[r], d, G);
-        r0[r] = fma(cub[l], t0, r0[r]);
-        mv2(c0, c1, t1, t2, r1[r], r2[r]);
+        const double s0 = shfl_down_d(r0[r], d, G), s1 = shfl_down_d(r1[r], d, G), s2 = shfl_down_d(r2[r], d, G);
+        r0[r] = fma(cub[l], s0, r0[r]);
+        mv2(c0, c1, s1, s2, r1[r], r2[r]);
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      n0[r] = shfl_down_d(r0[r], 1, G);
-      n1[r] = shfl_down_d(r1[r], 1, G);
-      n2[r] = shfl_down_d(r2[r], 1, G);
+      const double z0 = tu[0] * r0[r];
+      const double z1 = fma(t00[0], r1[r], t10[0] * r2[r]);
+      const double z2 = fma(t01[0], r1[r], t11[0] * r2[r]);
+      n0[r] = shfl_down_d(z0, 1, G);
+      n1[r] = shfl_down_d(z1, 1, G);
+      n2[r] = shfl_down_d(z2, 1, G);
       if (C.g == G - 1) { n0[r] = 0.0; n1[r] = 0.0; n2[r] = 0.0; }
     }
   }
   // ---- backward B: true incoming; b[j] <- x_j ----
 #pragma unroll
-  for (int j = M - 1; j >= 0; --j)
+  for (int r = 0; r < R; ++r) {
+    n0[r] += b[r][M - 1][0];
+    n1[r] += b[r][M - 1][1];
+    n2[r] += b[r][M - 1][2];
+    b[r][M - 1][0] = n0[r];
+    b[r][M - 1][1] = n1[r];
+    b[r][M - 1][2] = n2[r];
+  }
+#pragma unroll
+  for (int j = M - 2; j >= 0; --j)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double t0 = fma(-ou, n0[r], b[r][j][0]);
-      const double t1 = fma(-o11, n1[r], fma(-o12, n2[r], b[r][j][1]));
-      const double t2 = fma(o12, n1[r], fma(o22, n2[r], b[r][j][2]));
-      n0[r] = su[j] * t0;
-      n1[r] = fma(s00[j], t1, s01[j] * t2);
-      n2[r] = fma(s01[j], t1, s11[j] * t2);
+      const double p1 = n1[r], p2 = n2[r];
+      n0[r] = fma(tu[j + 1], n0[r], b[r][j][0]);
+      n1[r] = fma(t00[j + 1], p1, fma(t10[j + 1], p2, b[r][j][1]));
+      n2[r] = fma(t01[j + 1], p1, fma(t11[j + 1], p2, b[r][j][2]));
       b[r][j][0] = n0[r];
       b[r][j][1] = n1[r];
       b[r][j][2] = n2[r];
@@ -756,21 +761,17 @@ __device__ __forceinline__ const double* stage_mfac(const crb_system_t& S, const
   return smem;
 }
 
-// Shape-specialised kernels: stage only the compact (Sinv + scan products) copy of the shared factor set.
+// Shape-specialised kernels: stage only the compact copy of the shared factor set.
 template <int M, int LV>
 __device__ __forceinline__ void stage_compact(const crb_system_t& S, double* smem, FastMass& fm, int g) {
   constexpr int G = 1 << LV, LVE = LV > 0 ? LV : 1;
-  constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
+  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
   const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
   for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
   __syncthreads();
   fm.g = g;
   fm.fslot = smem;
-  fm.fscan = smem + 4 * M * G;
-  fm.um.o11 = S.um[0];
-  fm.um.o12 = S.um[1];
-  fm.um.o22 = S.um[2];
-  fm.um.ou = S.um[3];
+  fm.fscan = smem + crb_compact_slot_doubles(M, G);
 }
 
 template <int M>

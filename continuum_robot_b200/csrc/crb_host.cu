@@ -99,7 +99,6 @@ extern "C" int crb_system_slice(const crb_plan_t* plan, const crb_system_t* sys,
   out->n_members = count;
   const long long n = plan->n_free, P = plan->p, N = plan->n_elements;
   if (!sys->mass_shared && sys->mfac) out->mfac = sys->mfac + lo * plan->mfac_doubles;
-  if (!sys->mass_shared && sys->um_members) out->um_members = sys->um_members + lo * 4ll;
   if (!sys->stiff_shared && sys->kcoef) out->kcoef = sys->kcoef + lo * P * 4;
   if (!sys->force_shared) {
     if (sys->drag) out->drag = sys->drag + lo * P;

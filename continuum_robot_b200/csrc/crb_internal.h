@@ -45,16 +45,11 @@ inline SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, s
 // shape-specialised kernels stage only the compact copy (Sinv + scan products) of the shared factor set
 inline SmemLayout smem_layout_compact(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
   SmemLayout SL = smem_layout(plan, sys, bytes);
-  SL.mfac_doubles = 4 * plan->p + 10 * (plan->levels > 0 ? plan->levels : 1) * plan->g;
+  SL.mfac_doubles = crb_compact_doubles(plan->m, plan->g, plan->levels);
   const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
   *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
   return SL;
 }
-// ... and serve plans whose mass is shared, uniform along the beam and free of constrained DOFs in active slots
-inline bool crb_specialised_ok(const crb_plan_t* plan, const crb_system_t* sys) {
-  return sys->mass_shared && sys->uniform_mass && !plan->has_mask ;
-}
-
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* who) {
   if (bytes > 48 * 1024) {

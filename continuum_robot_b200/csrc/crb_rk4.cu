@@ -92,8 +92,7 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
   const unsigned need = crb_needed_features(plan, sys);
   const unsigned prof = crb_pick_profile(need);
 #define CRB_RK4_CASE(MM, LL)                                                                                       \
-  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared &&                               \
-      (prof == CRB_F_PROFILE_B || crb_specialised_ok(plan, sys))) {                                                 \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared) {                               \
     const SmemLayout SL = prof == CRB_F_PROFILE_A ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
     if (prof == CRB_F_PROFILE_A) {                                                                                  \
       if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL>, bytes, "crb_rk4")) return rc;                  \

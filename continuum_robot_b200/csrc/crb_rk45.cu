@@ -18,8 +18,7 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   const unsigned need = crb_needed_features(plan, sys);
   const unsigned prof = crb_pick_profile(need);
 #define CRB_RK45_CASE(MM, LL)                                                                             \
-  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared &&                      \
-      (prof == CRB_F_PROFILE_B || crb_specialised_ok(plan, sys))) {                                        \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared) {                      \
     const SmemLayout SL = prof == CRB_F_PROFILE_A ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
     const size_t total = bytes + sizeof(double) * 21 * MM * CRB_THREADS;                                   \
     if (prof == CRB_F_PROFILE_A) {                                                                         \

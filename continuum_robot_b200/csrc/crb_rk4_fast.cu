@@ -7,15 +7,14 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
                   double* Y_out, int save_every, cudaStream_t stream) {
   const int mpb = CRB_FAST_WARPS * (32 >> LV);
   // compact factor copy: ONE shared set, or (PM) one region per member of the block
-  const size_t bytes = sizeof(double) * (4 * plan->p + 10 * (plan->levels > 0 ? plan->levels : 1) * plan->g) * (PM ? mpb : 1);
+  const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
-  const UniformMass um = {sys->um[0], sys->um[1], sys->um[2], sys->um[3]};
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
 #define CRB_LIN2(UCV, IMPV)                                                                              \
   {                                                                                                      \
     if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM>, bytes, "crb_rk4")) return rc;       \
-    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, \
+    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
                                                                                         Y_out, save_every); \
   }
   if (!sys->force_staged || PM) {  // paired operator applications (forcing piecewise constant in time)
@@ -27,10 +26,10 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
     return 1;  // the stage-by-stage fast kernel has no constant-force path: use the general kernel
   } else if (imp) {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
+    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
   } else {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, um, X, t0, h, nsteps, Y_out, save_every);
+    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
   }
 #undef CRB_LIN2
   return 0;
@@ -40,8 +39,8 @@ int crb_fast_members_per_sm(int members_per_warp) { return CRB_FAST_MINBLOCKS * 
 
 int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                         int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
-  if (!sys->mass_shared) {  // per-member mass factors: per-member coupling blocks are required
-    if (!sys->um_members || sys->force_staged) return 1;
+  if (!sys->mass_shared) {  // per-member mass factors: paired kernel with one factor region per member
+    if (sys->force_staged) return 1;
 #define CRB_CASE_PM(MM, LL) \
   if (plan->m == MM && plan->levels == LL) return launch<MM, LL, true>(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
     CRB_CASE_PM(4, 3) CRB_CASE_PM(4, 4) CRB_CASE_PM(4, 2) CRB_CASE_PM(3, 2) CRB_CASE_PM(3, 3) CRB_CASE_PM(3, 1) CRB_CASE_PM(4, 5)

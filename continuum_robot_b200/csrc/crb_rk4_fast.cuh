@@ -1,27 +1,20 @@
-// crb_rk4_fast.cuh -- fused fixed-step RK4 for all-linear beams with uniform element mass
+// crb_rk4_fast.cuh -- fused fixed-step RK4 for all-linear beams without built-in forces
 // (BASELINE config 3 shape).  Same lane-group decomposition as crb_device.cuh, specialised so
 // that the FP64 pipe, not shared-memory bandwidth, is the limiter:
 //
-//  * Nystrom form of the classical RK4 tableau (the RHS of a linear undamped beam needs only the
-//    stage positions): 5 live vectors per DOF (Q0 = q + h/2 v, v, S = a1+a2+a3, A = a1+2a2+2a3+a4,
-//    work) instead of 7 -- algebraically the same update as k1..k4 of north_star row R1.
-//  * mass solve without stored spike vectors: the element coupling block O of the consistent mass
-//    matrix (models/segments.py:64-78) is identical for every element of a uniform-mass beam, so
-//    it travels as immediate kernel arguments and only Sinv (4 doubles / slot) plus the scan
-//    products are read from shared memory; boundary corrections are recomputed by a second local
-//    sweep (more DFMA, 2.5x fewer LDS wavefronts than crb_device.cuh::mass_solve).
+//  * mass solve = crb_device.cuh::fast_solve_r (compact factor copy, recomputed partition
+//    corrections, pure-DFMA sweeps), applied to TWO right-hand sides at once in the paired kernel;
+//  * crb_rk4_fast_kernel: Nystrom form of the classical RK4 tableau (the RHS of a linear undamped
+//    beam needs only the stage positions): 5 live vectors per DOF (Q0 = q + h/2 v, v,
+//    S = a1+a2+a3, A = a1+2a2+2a3+a4, work) instead of 7 -- algebraically the same update as
+//    k1..k4 of north_star row R1;
+//  * crb_rk4_lin2_kernel: paired operator applications (see below), the default.
 //
-//   forward  A: y~_last      (zero incoming)         -> Kogge-Stone scan -> y_last, xhat_in
-//   forward  B: y_s = b_s - O Sinv_{s-1} y_{s-1}                  (true incoming; keeps y_s)
-//   backward A: x~_first     (zero incoming)         -> scan -> x_first, x_in
-//   backward B: x_s = Sinv_s (y_s - O^T x_{s+1})                  (true incoming)
-//
-// (10 FP64 operations per slot and sweep; the earlier xhat_s - Sinv_s O^T x_{s+1} form cost 12.)
 // More resident warps do not help: builds capped at 216 / 200 / 168 registers (9 / 10 / 12 warps per
-// SM) measured 10-12 % slower than the 224-register, 8-warp build -- the FP64 pipe is the limiter.
+// SM) measured 10-12 % slower than the 8-warp build -- the FP64 pipe is the limiter.
 //
 // Reference behaviour: models/segments.py:32-78, euler_bernoulli_beam.py:163-298,
-// dynamic_beam_model.py:256-272, 343-362 (forces disabled, u = tip impulse or none).
+// dynamic_beam_model.py:256-272, 343-362 (forces disabled, u = constant force / tip impulse / none).
 #pragma once
 #include "crb_device.cuh"
 
@@ -40,9 +33,8 @@ struct FastCtx {
   bool active;
   int n;
   double4 kc[M];
-  const double* fslot;  // compact Sinv copy   [pair 0..1][j][g] double2 (shared memory)
-  const double* fscan;  // compact scan copy   [level][pair 0..4][g] double2
-  UniformMass um;
+  const double* fslot;  // compact factor copy, slot part (shared memory)
+  const double* fscan;  // compact factor copy, scan part
   // impulse: amplitude (0 if none) and the (slot, dof) it acts on, as a flat local index or -1
   double imp_amp, imp_dur;
   int imp_local;
@@ -105,12 +97,12 @@ __device__ __forceinline__ void fast_accel(const FastCtx<M>& C, double (&w)[M][3
 
 template <int M, int LV, bool IMP>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
-crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double t0, double h,
+crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h,
                     int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
   constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
-  // stage the compact (Sinv + scan) copy of the shared mass factors: 4 P + 10 LV G doubles
-  constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
+  // stage the compact copy of the shared mass factors
+  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
   {
     const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
     for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
@@ -123,9 +115,8 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
   C.n = P.n_free;
   C.active = member < S.n_members;
   C.member = C.active ? member : S.n_members - 1;
-  C.um = um;
   C.fslot = smem;
-  C.fscan = smem + 4 * M * G;
+  C.fscan = smem + crb_compact_slot_doubles(M, G);
   const int s0 = C.g * M;
   {
     const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
@@ -291,16 +282,15 @@ __device__ __forceinline__ void fast_apply2(const FastCtx<M>& C, double (&w)[2][
 //     v+ = v + h/6 (a1 + 5 a2 + h/2 p + c4 - c2) + h^3/12 (r1 + r2)
 // (reduces to the force-free formulas for c = 0).  M^-1 u_const and M^-1 e_k are obtained once per
 // launch by one paired solve.
-// PM: every member has its OWN mass factors (density / area / length differ per member, still uniform
-// along each beam): each lane group stages its member's compact factor copy in its own shared-memory
-// region and takes the coupling block from um_members[member] instead of the kernel arguments.
+// PM: every member has its OWN mass factors (density / area / lengths differ per member): each lane group stages its member's compact factor copy in its own shared-memory
+// region.
 template <int M, int LV, bool UC, bool IMP, bool PM>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
-crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict__ X, double t0, double h, int nsteps,
+crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
                     double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
   constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
-  constexpr int FAST_DOUBLES = 4 * M * G + 10 * LVE * G;
+  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mloc = warp * mpw + lane / G;
   const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
@@ -321,14 +311,8 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, UniformMass um, double* __restrict_
     }
     __syncthreads();
   }
-  if (PM) {
-    const double4 u4 = *reinterpret_cast<const double4*>(S.um_members + 4ll * C.member);
-    C.um.o11 = u4.x; C.um.o12 = u4.y; C.um.o22 = u4.z; C.um.ou = u4.w;
-  } else {
-    C.um = um;
-  }
   C.fslot = smem + (PM ? mloc * FAST_DOUBLES : 0);
-  C.fscan = C.fslot + 4 * M * G;
+  C.fscan = C.fslot + crb_compact_slot_doubles(M, G);
   C.imp_amp = 0.0;
   C.imp_dur = 0.0;
   C.imp_local = -1;

@@ -356,17 +356,9 @@ class BatchedDynamicEulerBernoulliBeam:
         # dispatch hints for the fast kernels: all-linear beam, one (rho A L, L) for every element
         self._all_linear = bool(np.all(self._etype == 0))
         L0, rho0, A0 = par[0, 0, 0], par[0, 0, 3], par[0, 0, 4]
-        # (uniform along each beam; members may differ -- then the per-member coupling blocks go to the device)
-        self._uniform_mass = bool(all(np.all(par[:, :, c] == par[:, :1, c]) for c in (0, 3, 4)))
-        mu = rho0 * A0 * L0 / 420
-        self._um = (54 * mu, 13 * L0 * mu, 3 * L0 * L0 * mu, 70 * mu)
-        self._d_um = None
         self.force_general_kernels = False
         self.force_staged_kernels = False
         self._mass_shared = shared([0, 3, 4])
-        if self._uniform_mass and not self._mass_shared:
-            Lm, mum = par[:, 0, 0], par[:, 0, 3] * par[:, 0, 4] * par[:, 0, 0] / 420
-            self._d_um = torch.from_numpy(np.ascontiguousarray(np.stack([54 * mum, 13 * Lm * mum, 3 * Lm * Lm * mum, 70 * mum], axis=1))).to(self.device)
         self._stiff_shared = shared([0, 1, 2, 4])
         self._force_shared = shared([0, 3, 4, 5, 6])
         dev = self.device
@@ -460,18 +452,13 @@ class BatchedDynamicEulerBernoulliBeam:
         P = int(self._plan.p)
         s.mfac = self._d_mfac.data_ptr() + (0 if self._mass_shared else 8 * lo * int(self._plan.mfac_doubles))
         s.kcoef = self._d_kcoef.data_ptr() + (0 if self._stiff_shared else 8 * lo * P * 4)
-        if self._d_um is not None:
-            s.um_members = self._d_um.data_ptr() + 8 * lo * 4
         fo = 0 if self._force_shared else lo
         s.elem_type = self._d_etype.data_ptr()
         s.red_index = self._d_red.data_ptr()
         s.all_linear = int(self._all_linear)
         s.all_nonlinear = int(bool(np.all(self._etype == 1)))
-        s.uniform_mass = int(self._uniform_mass)
         s.force_general = int(self.force_general_kernels)
         s.force_staged = int(self.force_staged_kernels)
-        for k in range(4):
-            s.um[k] = float(self._um[k])
         if drag is not None:
             if drag.fluid_density != self.force_params.fluid_density:
                 raise ValueError("FluidDragForce.fluid_density differs from the assembled ForceParams.fluid_density")

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 101
+#define CRB_VERSION 102
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 
@@ -105,13 +105,8 @@ typedef struct crb_system_t {
   /* dispatch hints filled by the host layer from the parameter table */
   int32_t all_linear;       /* 1: every element is CRB_ELEM_LINEAR */
   int32_t all_nonlinear;    /* 1: every element is CRB_ELEM_NONLINEAR */
-  int32_t uniform_mass;     /* 1: rho*A*L and L identical for every element of a member (and of every member if
-                               mass_shared) */
   int32_t force_general;    /* 1: always use the general kernels (testing / comparison) */
   int32_t force_staged;     /* 1: fast path keeps the stage-by-stage kernel (no paired operator form) */
-  double um[4];             /* uniform-mass coupling block: 54 mu, 13 L mu, 3 L^2 mu, 70 mu, mu = rho A L / 420 */
-  const double* um_members; /* [B,4] per-member coupling blocks (same 4 values as um) when !mass_shared and each
-                               member's beam is uniform along its length; NULL otherwise */
   /* shared-operator form (crb_shared_operator): device copy of the operator blob, or NULL.  When set,
    * crb_rk4 evaluates the whole closed-loop RHS as a dense FP64 tensor-core contraction; gain / ref /
    * gravity vector / imp_dof are the ones the blob was built with. */

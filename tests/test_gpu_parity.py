@@ -489,8 +489,8 @@ def test_shared_operator_path_matches_banded_path_and_oracle(N, bc0, gravity, wi
 
 @pytest.mark.parametrize("N,with_imp", [(32, False), (32, True), (16, False), (12, True)])
 def test_per_member_mass_fast_path(N, with_imp):
-    """Ensembles whose members differ in density / area / element length (each beam still uniform
-    along its length) take the paired fast kernel with per-member mass factors: compared with the
+    """Ensembles whose members differ in density / area / element length (also along the beam: the
+    N = 16 case is tapered) take the paired fast kernel with per-member mass factors: compared with the
     general kernel on the whole ensemble and with the CPU oracle on sampled members (<= 1e-9)."""
     from continuum_robot_b200 import HostPipeline, TipImpulse
     from continuum_robot_b200 import ensembles as ens
@@ -507,10 +507,13 @@ def test_per_member_mass_fast_path(N, with_imp):
     par[:, :, 2] = m["I"]
     par[:, :, 3] = (m["rho"] * np.exp(0.2 * rng.standard_normal(B)))[:, None]
     par[:, :, 4] = (m["A"] * (1 + 0.1 * rng.random(B)))[:, None]
+    if N == 16:  # tapered beams: density and element length vary ALONG the beam as well
+        par[:, :, 3] *= np.linspace(1.0, 0.6, N)[None, :]
+        par[:, :, 0] *= np.linspace(1.1, 0.9, N)[None, :]
     par[:, :, 5:] = 1.0
     et, bc = np.zeros(N, dtype=int), np.array([1] + [0] * N)
     beam = make_gpu_beam(par, et, bc)
-    assert not beam._mass_shared and beam._uniform_mass
+    assert not beam._mass_shared
     n, h = beam.n_free, 1e-5
     amp = rng.uniform(0.05, 0.5, B)
     imp = TipImpulse(torch.from_numpy(amp).cuda(), duration=5e-4) if with_imp else None
