@@ -108,9 +108,10 @@ template <int M, unsigned FEAT, int LV>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   extern __shared__ __align__(16) double smem[];
-  // Shape-specialised LINEAR kernels (profile A) use the uniform-mass solve on the compact factor copy
-  // (measured +30 % on config 3's shape: they are shared-memory bound with the stored-spike solve); the
-  // nonlinear profile is FP64-bound and keeps the stored spikes (the re-sweep costs 6-7 % there).
+  // Shape-specialised LINEAR kernels (profile A) use the compact mass solve (fast_solve_r) on the compact
+  // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
+  // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
+  // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
   constexpr bool UMS = LV >= 0 && FEAT == CRB_F_PROFILE_A;
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
