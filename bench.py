@@ -295,8 +295,9 @@ def run_gpu(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": which,
-                "note": "algorithmic 96 B per element-step; launches fuse steps so DRAM traffic is far below it and the "
-                        "kernel is FP64-pipe bound (see DESIGN.md / profiles/)",
+                "note": "algorithmic 96 B per element-step; launches fuse steps so DRAM traffic is far below it; the "
+                        "kernel is bound by the shared-memory/shuffle (LSU) pipe at 79 % with the FP64 pipe at 60 % "
+                        "(see DESIGN.md / profiles/)",
             },
             "e2e": {"value": e2e_val, "unit": "element-steps/s", "h2d_bytes_per_step": X.numel() * 8 / S,
                     "d2h_bytes_per_step": X.numel() * 8 / S,
