@@ -262,3 +262,125 @@ def test_gain_fragments_layout():
     assert not fr[:, :, 4 * 6:].any()  # destination lane 3 owns only phantom slots (6 active of 8)
     rc, p2 = _plan(6, [1] + [0] * 6, 0)
     assert lib.crb_gain_fragments(C.byref(p2), None, None) < 0 and b"4 lanes" in lib.crb_last_error()
+
+
+@pytest.mark.parametrize("N,bc0,gravity,with_ref,imp", [(6, 1, True, True, True), (3, 2, True, False, False), (8, 1, False, True, True), (1, 1, True, False, True)])
+def test_shared_operator_blob_matches_numpy(N, bc0, gravity, with_ref, imp):
+    """crb_shared_operator (host only): de-tile the mma B fragments and compare W, c0, M^-1 e_k and the
+    gravity operators with a NumPy restatement built from the oracle's M, K (dynamic_beam_model.py:256-272,
+    full_state_linear.py:58, gravity_forces.py:97-146)."""
+    L = _lib()
+    lib = L.load()
+    rng = np.random.default_rng(N)
+    spec = bo.BeamSpec.uniform(N)
+    spec.length = spec.length * (1 + 0.1 * rng.random(N))
+    spec.density = spec.density * (1 + 0.2 * rng.random(N))
+    spec.bc = np.array([bc0] + [0] * (N - 1))
+    rc, plan = _plan(N, list(spec.bc) + [0])
+    assert rc == 0
+    n = plan.n_free
+    par = np.ascontiguousarray(np.stack([spec.length, spec.elastic_modulus, spec.moment_inertia, spec.density, spec.cross_area,
+                                         np.ones(N), np.ones(N)], axis=1))
+    et = bytes(int(t) for t in spec.elem_type)
+    bcb = bytes(int(b) for b in list(spec.bc) + [0])
+    gain = rng.standard_normal((n, 2 * n))
+    ref = rng.standard_normal(2 * n) if with_ref else None
+    imp_dof = n - 2 if imp and n >= 2 else (0 if imp else -1)
+    gx, gy = 1.5, -9.81
+    args = (C.byref(plan), par.ctypes.data_as(C.c_void_p), et, bcb, gain.ctypes.data_as(C.c_void_p),
+            ref.ctypes.data_as(C.c_void_p) if with_ref else None, gx, gy, int(gravity), imp_dof)
+    cnt = lib.crb_shared_operator(*args, None)
+    assert cnt > 0
+    blob = np.zeros(cnt)
+    assert lib.crb_shared_operator(*args, blob.ctypes.data_as(C.c_void_p)) == cnt
+    KQ, NT, GKP = int(blob[2]), int(blob[3]), int(blob[4])
+    assert (int(blob[1]), KQ, NT, GKP, int(blob[7])) == (n, (n + 3) // 4, ((n + 3) // 4 + 1) // 2, (N + 3) // 4 if gravity else 0, cnt)
+    o = 8
+    wq = blob[o:o + 32 * KQ * NT].reshape(KQ, NT, 32); o += 32 * KQ * NT
+    wv = blob[o:o + 32 * KQ * NT].reshape(KQ, NT, 32); o += 32 * KQ * NT
+    pf = blob[o:o + 32 * KQ].reshape(KQ, 32); o += 32 * KQ
+    gc = blob[o:o + 32 * GKP * NT].reshape(GKP, NT, 32); o += 32 * GKP * NT
+    gs = blob[o:o + 32 * GKP * NT].reshape(GKP, NT, 32); o += 32 * GKP * NT
+    c0 = blob[o:o + 4 * KQ][:n]; o += 4 * KQ
+    mi = blob[o:o + 4 * KQ][:n]
+    # de-tile: lane -> (k = lane % 4, column 2 jo + e = lane // 4); output DOF 4 (2 nt + e) + jo
+    W = np.zeros((n, 2 * n)); P = np.zeros((N, n)); Gc = np.zeros((n, N)); Gs = np.zeros((n, N))
+    for lane in range(32):
+        k, ncol = lane % 4, lane // 4
+        jo, e = ncol // 2, ncol % 2
+        for i in range(KQ):
+            c = 4 * i + k
+            for nt in range(NT):
+                out = 4 * (2 * nt + e) + jo
+                if out < n and c < n:
+                    W[out, c], W[out, n + c] = wq[i, nt, lane], wv[i, nt, lane]
+                else:
+                    assert wq[i, nt, lane] == 0 and wv[i, nt, lane] == 0
+            seg = 4 * e + jo
+            if seg < N and c < n:
+                P[seg, c] = pf[i, lane]
+        for p in range(GKP):
+            seg = 4 * p + k
+            for nt in range(NT):
+                out = 4 * (2 * nt + e) + jo
+                if seg < N and out < n:
+                    Gc[out, seg], Gs[out, seg] = gc[p, nt, lane], gs[p, nt, lane]
+    orc = bo.BeamOracle(spec, bo.ForceSpec(gravity_vector=(gx, gy, 0.0), enable_gravity_effects=gravity))
+    K = np.zeros((n, n))
+    for j in range(n):
+        e_j = np.zeros(n); e_j[j] = 1.0
+        K[:, j] = orc.stiffness(e_j)
+    Minv = np.linalg.inv(orc.M)
+    Wref = np.concatenate([-Minv @ (K + gain[:, :n]), -Minv @ gain[:, n:]], axis=1)
+    assert np.abs(W - Wref).max() <= 1e-11 * np.abs(Wref).max()
+    if with_ref:
+        assert np.abs(c0 - Minv @ (gain @ ref)).max() <= 1e-11 * np.abs(Minv @ (gain @ ref)).max()
+    else:
+        assert np.all(c0 == 0)
+    if imp_dof >= 0:
+        assert np.abs(mi - Minv[:, imp_dof]).max() <= 1e-11 * np.abs(Minv[:, imp_dof]).max()
+    if gravity:
+        # the operators reproduce the oracle's gravity force for random rotations: M^-1 f = Gc cos(P q) + Gs sin(P q)
+        q = 0.3 * rng.standard_normal(n)
+        x = np.concatenate([q, np.zeros(n)])
+        want = Minv @ orc.gravity(x)
+        got = Gc @ np.cos(P @ q) + Gs @ np.sin(P @ q)
+        assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+    # argument errors are reported, not raised
+    assert lib.crb_shared_operator(C.byref(plan), None, et, bcb, None, None, gx, gy, 0, -1, blob.ctypes.data_as(C.c_void_p)) < 0
+    assert lib.crb_shared_operator(C.byref(plan), par.ctypes.data_as(C.c_void_p), et, bcb, None, None, gx, gy, 0, n, None) < 0
+
+
+def test_shared_operator_size_limits():
+    lib = _lib().load()
+    rc, plan = _plan(9, [1] + [0] * 9)  # n_free = 27 > 24
+    assert rc == 0
+    assert lib.crb_shared_operator(C.byref(plan), None, None, None, None, None, 0.0, 0.0, 0, -1, None) < 0
+    assert b"n_free" in lib.crb_last_error()
+
+
+def test_system_slice_offsets_per_member_pointers():
+    """crb_system_slice (host only): per-member arrays are offset, shared ones are not."""
+    L = _lib()
+    lib = L.load()
+    rc, plan = _plan(32, [1] + [0] * 32)
+    assert rc == 0
+    s = L.CrbSystem()
+    s.n_members = 1000
+    s.mass_shared, s.stiff_shared, s.force_shared = 1, 0, 0
+    base = 1 << 20
+    s.mfac, s.kcoef, s.drag, s.grav, s.seg_half_mass = base, 2 * base, 3 * base, 4 * base, 5 * base
+    s.u_const, s.f_ext, s.imp_amp, s.elem_type, s.red_index = 6 * base, 7 * base, 8 * base, 9 * base, 10 * base
+    out = L.CrbSystem()
+    assert lib.crb_system_slice(C.byref(plan), C.byref(s), 100, 50, C.byref(out)) == 0
+    P, n, N = plan.p, plan.n_free, plan.n_elements
+    assert out.n_members == 50 and out.mfac == base and out.elem_type == 9 * base and out.red_index == 10 * base
+    assert out.kcoef == 2 * base + 8 * 100 * P * 4
+    assert out.drag == 3 * base + 8 * 100 * P and out.grav == 4 * base + 8 * 100 * P * 2
+    assert out.seg_half_mass == 5 * base + 8 * 100 * N
+    assert out.u_const == 6 * base + 8 * 100 * n and out.f_ext == 7 * base + 8 * 100 * n and out.imp_amp == 8 * base + 8 * 100
+    s.mass_shared = 0
+    assert lib.crb_system_slice(C.byref(plan), C.byref(s), 7, 1, C.byref(out)) == 0
+    assert out.mfac == base + 8 * 7 * plan.mfac_doubles
+    assert lib.crb_system_slice(C.byref(plan), C.byref(s), 990, 20, C.byref(out)) < 0
+    assert b"outside" in lib.crb_last_error()
