@@ -756,7 +756,9 @@ struct SmemLayout {
 
 __device__ __forceinline__ const double* stage_mfac(const crb_system_t& S, const KPlan& P, double* smem) {
   if (!S.mass_shared) return nullptr;
-  for (int k = threadIdx.x; k < (int)P.mfac_doubles; k += blockDim.x) smem[k] = S.mfac[k];
+  // the stored-spike part of the factor set (the compact copy behind it is staged by stage_compact)
+  const int count = 2 * CRB_SLOT_PAIRS * P.p + 2 * CRB_SCAN_PAIRS * (P.levels > 0 ? P.levels : 1) * P.g;
+  for (int k = threadIdx.x; k < count; k += blockDim.x) smem[k] = S.mfac[k];
   __syncthreads();
   return smem;
 }

@@ -34,7 +34,7 @@ inline KPlan kplan_of(const crb_plan_t* p) {
 
 inline SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
   SmemLayout SL;
-  SL.mfac_doubles = sys->mass_shared ? (int)plan->mfac_doubles : 0;
+  SL.mfac_doubles = sys->mass_shared ? 2 * CRB_SLOT_PAIRS * plan->p + 2 * CRB_SCAN_PAIRS * (plan->levels > 0 ? plan->levels : 1) * plan->g : 0;
   SL.scratch_doubles = ((sys->gain && !(sys->gain_frag && plan->g == 4)) || sys->grav_mode == 2)
                            ? 2 * plan->n_free + 2 * plan->n_elements : 0;  // reduced state + per-segment gravity
   const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);

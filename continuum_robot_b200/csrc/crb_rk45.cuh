@@ -11,6 +11,8 @@
 // squared tableau  q_s = q + h c_s v + h^2 sum_l (A A)_{sl} kv_l, identical to SciPy's
 // y + h sum_j a_sj K_j up to rounding.
 #pragma once
+#include <type_traits>
+
 #include "crb_device.cuh"
 
 struct Rk45Args {
@@ -104,9 +106,13 @@ __device__ __forceinline__ double group_sum(double v, int G) {
   return v;
 }
 
-template <int M, unsigned FEAT, int LV>
-__global__ void __launch_bounds__(CRB_THREADS)
+// WPB warps per block: members take different numbers of attempts, and a block lives as long as its
+// slowest member, so the adaptive kernel runs with small blocks (2 warps; the hardware block scheduler
+// then balances the ragged ensemble) where the fixed-step kernels use 4.
+template <int M, unsigned FEAT, int LV, int WPB>
+__global__ void __launch_bounds__(32 * WPB)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
+  constexpr int THREADS = 32 * WPB;
   extern __shared__ __align__(16) double smem[];
   // Shape-specialised LINEAR kernels (profile A) use the compact mass solve (fast_solve_r) on the compact
   // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
@@ -117,9 +123,9 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g, mpw = 32 / G;
   const int mloc = warp * mpw + lane / G;
-  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  const int member = blockIdx.x * (WPB * mpw) + mloc;
   LaneCtx<M> L;
-  const int mpb = CRB_WARPS_PER_BLOCK * mpw;
+  const int mpb = WPB * mpw;
   load_lane_ctx<M>(L, P, S, member, lane % G, mf,
                    SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
   if (LV >= 0) {
@@ -136,7 +142,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   const RhsFlags F = make_flags(S, P);
   // kv stage storage: [stage 0..6][j][d][thread]
   double* kvs = smem + SL.mfac_doubles + SL.scratch_doubles * mpb + threadIdx.x;
-  auto KV = [&](int s, int j, int d) -> double& { return kvs[((s * M + j) * 3 + d) * CRB_THREADS]; };
+  auto KV = [&](int s, int j, int d) -> double& { return kvs[((s * M + j) * 3 + d) * THREADS]; };
   const double inv_size = 1.0 / (2.0 * L.n);
 
   double q[M][3], v[M][3], qs[M][3], vs[M][3], a[M][3];
@@ -173,14 +179,18 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
       vs[j][d] = v[j][d];
     }
 
-  // stage inputs of stage s from the stored accelerations (position rows use the squared tableau)
-  auto prep_stage = [&](int s) {
+  // stage inputs of stage s from the stored accelerations (position rows use the squared tableau).
+  // One fully unrolled copy per stage: tableau entries become constant-bank operands and the stage
+  // storage offsets immediates (the rolled form spent a third of its instructions on index arithmetic).
+  auto prep_stage_c = [&](auto sc) {
+    constexpr int s = decltype(sc)::value;
     const double hc = h * T.c[s];
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         double sv = 0.0, sq = 0.0;
+#pragma unroll
         for (int l = 0; l < s; ++l) {
           const double k = KV(l, j, d);
           sv = fma(T.a[s][l], k, sv);
@@ -190,6 +200,16 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
         qs[j][d] = fma(h2, sq, fma(hc, v[j][d], q[j][d]));
       }
     ts = t + T.c[s] * h;
+  };
+  auto prep_stage = [&](int s) {
+    switch (s) {
+      case 1: prep_stage_c(std::integral_constant<int, 1>{}); break;
+      case 2: prep_stage_c(std::integral_constant<int, 2>{}); break;
+      case 3: prep_stage_c(std::integral_constant<int, 3>{}); break;
+      case 4: prep_stage_c(std::integral_constant<int, 4>{}); break;
+      case 5: prep_stage_c(std::integral_constant<int, 5>{}); break;
+      default: prep_stage_c(std::integral_constant<int, 6>{}); break;
+    }
   };
   // start of an attempt (rk.py:111-140); returns false when the warp is done or out of budget
   auto begin_attempt = [&]() -> bool {

@@ -12,6 +12,7 @@ examples/pyodide_example/pyodide_example.py:69-75) with a batched call whose res
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -255,8 +256,9 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
     impulse = u if isinstance(u, TipImpulse) else None
     uc = None if impulse is not None else u
     gain, ref = _feedback(controller)
-    if beam.n_elements <= 64:
-        beam = beam.with_slots(2)  # the adaptive kernel keeps 7 stage vectors: 2 slots per lane avoid spills
+    rk45_slots = int(os.environ.get("CRB_RK45_SLOTS", "2"))
+    if beam.n_elements <= 64 and rk45_slots > 0:
+        beam = beam.with_slots(rk45_slots)  # the adaptive kernel keeps 7 stage vectors: 2 slots per lane avoid spills
     sysm, keep = beam.make_system(B, drag=drag, gravity=grav, u_const=uc, impulse=impulse, gain=gain, ref=ref)
     dev = beam.device
     t = torch.full((B,), t0, dtype=torch.float64, device=dev)
