@@ -171,9 +171,13 @@ __host__ __device__ constexpr int crb_compact_doubles(int m, int g, int levels) 
 
 // what the compact solve needs from a lane
 struct FastMass {
+  static constexpr int kPin = 0;   // slots whose 2x2 T block lives in registers for the whole launch
+  static constexpr int kPinU = 0;  // 1: the tu values too
+  static constexpr int kPinS = 0;  // slots whose Sinv lives in registers
   int g;                // lane within the member
   const double* fslot;  // slot part of the compact copy (shared memory)
   const double* fscan;  // scan part
+  double pin[1][4], pinu[1], pins[1][4];  // unused (nothing pinned)
 };
 
 template <int M, int G, typename CT>
@@ -192,18 +196,30 @@ __device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const CT& C) 
   // T_j = -Lm of the lane's own slots stays in registers for the four sweeps
   double t00[M], t01[M], t10[M], t11[M], tu[M + 1];
 #pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const double2 a = ld_fslot<M, G, CT>(C, 2, j), c = ld_fslot<M, G, CT>(C, 3, j);
-    t00[j] = a.x;
-    t01[j] = a.y;
-    t10[j] = c.x;
-    t11[j] = c.y;
+  for (int jj = 0; jj < (M + 1) / 2; ++jj) {
+    if (CT::kPinU) {
+      tu[2 * jj] = C.pinu[CT::kPinU ? 2 * jj : 0];
+      tu[2 * jj + 1] = C.pinu[CT::kPinU ? 2 * jj + 1 : 0];
+    } else {
+      const double2 u = ld_fslot<M, G, CT>(C, 4, jj);  // address ((4 M + jj) G + g): the tu block follows pair 3
+      tu[2 * jj] = u.x;
+      tu[2 * jj + 1] = u.y;
+    }
   }
 #pragma unroll
-  for (int jj = 0; jj < (M + 1) / 2; ++jj) {
-    const double2 u = ld_fslot<M, G, CT>(C, 4, jj);  // address ((4 M + jj) G + g): the tu block follows pair 3
-    tu[2 * jj] = u.x;
-    tu[2 * jj + 1] = u.y;
+  for (int j = 0; j < M; ++j) {
+    if (j < CT::kPin) {  // pinned in registers by the kernel (saves 2 LDS.128 per slot and solve)
+      t00[j] = C.pin[j < CT::kPin ? j : 0][0];
+      t01[j] = C.pin[j < CT::kPin ? j : 0][1];
+      t10[j] = C.pin[j < CT::kPin ? j : 0][2];
+      t11[j] = C.pin[j < CT::kPin ? j : 0][3];
+    } else {
+      const double2 a = ld_fslot<M, G, CT>(C, 2, j), c = ld_fslot<M, G, CT>(C, 3, j);
+      t00[j] = a.x;
+      t01[j] = a.y;
+      t10[j] = c.x;
+      t11[j] = c.y;
+    }
   }
   double y0[R], y1[R], y2[R];
 #pragma unroll
@@ -246,7 +262,14 @@ __device__ __forceinline__ void fast_solve_r(double (&b)[R][M][3], const CT& C) 
   // ---- forward B (true incoming), then the block-diagonal solve: b[j] <- xhat_j = Sinv_j y_j ----
 #pragma unroll
   for (int j = 0; j < M; ++j) {
-    const double2 sa = ld_fslot<M, G, CT>(C, 0, j), sc = ld_fslot<M, G, CT>(C, 1, j);
+    double2 sa, sc;
+    if (j < CT::kPinS) {
+      sa = make_double2(C.pins[j < CT::kPinS ? j : 0][0], C.pins[j < CT::kPinS ? j : 0][1]);
+      sc = make_double2(C.pins[j < CT::kPinS ? j : 0][2], C.pins[j < CT::kPinS ? j : 0][3]);
+    } else {
+      sa = ld_fslot<M, G, CT>(C, 0, j);
+      sc = ld_fslot<M, G, CT>(C, 1, j);
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const double p1 = xi1[r], p2 = xi2[r];
