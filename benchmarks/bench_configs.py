@@ -80,6 +80,16 @@ def main():
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
             print(json.dumps({"config": "cfg3 general kernel", "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg3i":  # config 3 with a per-member tip impulse (the reference examples' input): IMP variant
+            B, steps = 65536, 50
+            e = ens.config3(B, 32)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, B), "type": ["linear"] * 32})
+            beam.create_system_func(); beam.create_input_func()
+            X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
+            imp = TipImpulse(torch.from_numpy(np.random.default_rng(3).uniform(0.05, 0.5, B)).to(dev), duration=1.0)
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
+            print(json.dumps({"config": "cfg3 + tip impulse (paired fast kernel, forcing variant)",
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg3m":  # config 3 with PER-MEMBER mass (density varies per member): no shared factors
             B, steps = 65536, 50
             e = ens.config3(B, 32)

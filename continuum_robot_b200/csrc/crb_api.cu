@@ -241,6 +241,22 @@ extern "C" int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* 
   return 0;
 }
 
+static int rk4_dispatch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int32_t nsteps,
+                        double* Y_out, int32_t save_every, cudaStream_t stream) {
+  int rc;
+  if (crb_shared_eligible(plan, sys)) {  // one design + gain shared by all members: dense tensor-core contraction
+    rc = crb_launch_rk4_shared(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
+  } else {
+    rc = rk4_fast_eligible(plan, sys) ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream) : 1;
+    if (rc == 1)  // not eligible, or shape not instantiated in the fast family
+      rc = crb_launch_rk4_general(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
+  }
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                        int32_t nsteps, double* Y_out, int32_t save_every, void* stream) {
   if (int rc = check_system("crb_rk4", plan, sys)) return rc;
@@ -249,20 +265,31 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
   if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_rk4: step h must be positive and finite");
   if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_rk4: save_every must be >= 1 when Y_out is given");
   if (nsteps == 0) return 0;
-  if (crb_shared_eligible(plan, sys)) {  // one design + gain shared by all members: dense tensor-core contraction
-    if (int rc = crb_launch_rk4_shared(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream)) return rc;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));
-    return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sys->imp_amp) {
+    // The impulse (examples/example_utilities.py:144-148: a force while t < duration) is the only
+    // time-dependent term.  Steps that start at or after the end of the window see no input at any
+    // stage, so they run as the input-free system (cheaper kernel variants, e.g. the force-free paired
+    // kernel).  k_off = first such step, plus one step of margin so that the gate is never decided
+    // differently by host and device rounding of t0 + k h.
+    long long k_off = 0;
+    if (t0 < sys->imp_duration) {
+      k_off = (long long)std::ceil((sys->imp_duration - t0) / h);
+      while (k_off > 0 && t0 + (double)(k_off - 1) * h >= sys->imp_duration) --k_off;
+      while (t0 + (double)k_off * h < sys->imp_duration) ++k_off;
+      ++k_off;
+    }
+    if (Y_out) k_off = (k_off + save_every - 1) / save_every * save_every;  // split on a frame boundary (later is always valid)
+    if (k_off < nsteps) {
+      crb_system_t quiet = *sys;
+      quiet.imp_amp = nullptr;
+      if (k_off > 0)
+        if (int rc = rk4_dispatch(plan, sys, X, t0, h, (int32_t)k_off, Y_out, save_every, st)) return rc;
+      double* Y2 = Y_out ? Y_out + (k_off / save_every) * (long long)sys->n_members * 2 * plan->n_free : nullptr;
+      return rk4_dispatch(plan, &quiet, X, t0 + (double)k_off * h, h, nsteps - (int32_t)k_off, Y2, save_every, st);
+    }
   }
-  const bool fast = rk4_fast_eligible(plan, sys);
-  int rc = fast ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream) : 1;
-  if (rc == 1)  // not eligible, or shape not instantiated in the fast family
-    rc = crb_launch_rk4_general(plan, sys, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream);
-  if (rc) return rc;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_rk4: launch failed: %s", cudaGetErrorString(e));
-  return 0;
+  return rk4_dispatch(plan, sys, X, t0, h, nsteps, Y_out, save_every, st);
 }
 
 // ------------------------------------------------------------------------------------------

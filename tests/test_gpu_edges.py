@@ -99,3 +99,54 @@ def test_rk45_attempt_budget_and_resume():
     assert not part.success and torch.all(part.status == 1) and torch.all(part.t_final < 2e-3)
     assert torch.all(part.naccept + part.nreject == 5)
     assert full.success and torch.all(full.naccept + full.nreject > 5)
+
+
+@pytest.mark.parametrize("save_every", [0, 7])
+def test_impulse_window_split_is_exact(save_every):
+    """crb_rk4 runs the steps after the impulse window as the input-free system (separate launch of the
+    cheaper kernel variant).  The result must equal stepping launch by launch across the window end,
+    where every launch is decided on its own (bitwise for the states saved on the way and at the end)."""
+    from continuum_robot_b200 import TipImpulse
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    B, N, h, steps = 67, 32, 2e-5, 84
+    e = ens.config3(B, N, seed=21)
+    m = ens.material()
+    par = np.zeros((B, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E
+    par[:, :, 5:] = 1.0
+    beam = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
+    n = beam.n_free
+    amp = np.linspace(0.1, 1.0, B)
+    imp = TipImpulse(torch.from_numpy(amp).cuda(), duration=30.5 * h)  # window ends inside step 30
+    x0 = np.concatenate([e.q0, e.v0], axis=1)
+    X = torch.from_numpy(x0).cuda()
+    nfr = steps // save_every if save_every else 0
+    Y = torch.zeros(nfr, B, 2 * n, dtype=torch.float64, device="cuda") if nfr else None
+    rk4_steps(beam, X, 0.0, h, steps, u=imp, Y_out=Y, save_every=save_every)
+    # reference: one launch per step with the impulse object (each launch inside or outside the window)
+    Xs = torch.from_numpy(x0).cuda()
+    frames = []
+    for k in range(steps):
+        rk4_steps(beam, Xs, k * h, h, 1, u=imp)
+        if save_every and (k + 1) % save_every == 0:
+            frames.append(Xs.clone())
+    assert max(block_err(X.cpu().numpy()[i], Xs.cpu().numpy()[i], n) for i in range(B)) < 1e-13
+    if nfr:
+        got, want = Y.cpu().numpy(), torch.stack(frames).cpu().numpy()
+        assert max(block_err(got[f, i], want[f, i], n) for f in range(nfr) for i in range(0, B, 11)) < 1e-13
+    # and the CPU oracle
+    i = 5
+    spec = bo.BeamSpec.uniform(N)
+    spec.elastic_modulus = e.E[i].copy()
+    orc = bo.BeamOracle(spec)
+    def f(t, x):
+        u = np.zeros(n)
+        if t < 30.5 * h:
+            u[n - 2] = amp[i]
+        return orc.rhs(t, x, u)
+    want = bo.rk4_solve(f, x0[i], 0.0, h, steps)
+    assert block_err(X.cpu().numpy()[i], want, n) < 1e-9
