@@ -10,8 +10,8 @@
 //    k1..k4 of north_star row R1;
 //  * crb_rk4_lin2_kernel: paired operator applications (see below), the default.
 //
-// More resident warps do not help: builds capped at 216 / 200 / 168 registers (9 / 10 / 12 warps per
-// SM) measured 10-12 % slower than the 8-warp build -- the FP64 pipe is the limiter.
+// More resident warps do not help: builds capped at 216 / 200 registers (9 / 10 warps per SM) measured
+// 18-45 % slower than the 8-warp build, with the stored-spike-free T-form just as with the earlier forms.
 //
 // Reference behaviour: models/segments.py:32-78, euler_bernoulli_beam.py:163-298,
 // dynamic_beam_model.py:256-272, 343-362 (forces disabled, u = constant force / tip impulse / none).
