@@ -80,6 +80,18 @@ def main():
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
             print(json.dumps({"config": "cfg3 general kernel", "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg3mid":  # config 3 with the implicit midpoint rule (h = 10 x the RK4 step)
+            from continuum_robot_b200 import midpoint_steps
+            B, steps = 65536, 50
+            e = ens.config3(B, 32)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, B), "type": ["linear"] * 32})
+            beam.create_system_func(); beam.create_input_func()
+            X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
+            hm = 10 * e.h
+            ms = timed(lambda: midpoint_steps(beam, X, 0.0, hm, steps))
+            print(json.dumps({"config": "cfg3 implicit midpoint, h = 2e-4 (per-member factors of M + h^2/4 K)",
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms,
+                              "simulated_seconds_per_second_per_member": steps * hm / (ms * 1e-3)}))
         if name == "cfg3i":  # config 3 with a per-member tip impulse (the reference examples' input): IMP variant
             B, steps = 65536, 50
             e = ens.config3(B, 32)

@@ -23,7 +23,7 @@ def __getattr__(name):
         from . import dynamic_beam
 
         return getattr(dynamic_beam, name)
-    if name in ("solve_ensemble", "rk4_steps", "EnsembleResult", "HostPipeline"):
+    if name in ("solve_ensemble", "rk4_steps", "midpoint_steps", "EnsembleResult", "HostPipeline"):
         from . import integrate
 
         return getattr(integrate, name)

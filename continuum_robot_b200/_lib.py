@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 102
+CRB_VERSION = 103
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -89,6 +89,10 @@ _SIGNATURES = {
          C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_int32, C.c_void_p],
     ),
+    "crb_assemble_shifted": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32,
+                                       C.c_double, C.c_void_p, C.c_void_p]),
+    "crb_midpoint": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_int32, C.c_void_p, C.c_double,
+                               C.c_double, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "crb_rk4_wave_members": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.POINTER(C.c_int32)]),
     "crb_system_slice": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_int32, C.c_int32, C.POINTER(CrbSystem)]),
     "crb_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p)]),

@@ -109,10 +109,32 @@ extern "C" int crb_assemble(const crb_plan_t* plan, const double* params, int32_
   const int block = 128;
   const int grid = (nthreads + block - 1) / block;
   crb_assemble_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(kplan_of(plan), T, params, n_param_sets, n_mass,
-                                                               n_stiff, n_force, fluid_density, mfac, kcoef,
+                                                               n_stiff, n_force, fluid_density, 0.0, mfac, kcoef,
                                                                elem_type_slots, drag, grav, seg_half_mass);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_assemble: launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int crb_assemble_shifted(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
+                                    const uint8_t* elem_type_host, const uint8_t* bc_host, int32_t n_sets,
+                                    double shift, double* afac, void* stream) {
+  (void)bc_host;
+  if (!plan || !params || !elem_type_host || !afac) return fail(CRB_E_ARG, "crb_assemble_shifted: null argument");
+  if (n_param_sets < 1) return fail(CRB_E_ARG, "crb_assemble_shifted: n_param_sets must be >= 1");
+  if (n_sets != 1 && n_sets != n_param_sets) return fail(CRB_E_ARG, "crb_assemble_shifted: n_sets must be 1 or n_param_sets");
+  if (!(shift >= 0.0) || !std::isfinite(shift)) return fail(CRB_E_ARG, "crb_assemble_shifted: shift must be finite and >= 0");
+  for (int e = 0; e < plan->n_elements; ++e)
+    if (elem_type_host[e] != CRB_ELEM_LINEAR)
+      return fail(CRB_E_ARG, "crb_assemble_shifted: element %d is not linear (M + shift K needs a stiffness matrix)", e);
+  AsmTopo T;
+  if (int rc = fill_topo(plan, elem_type_host, &T)) return rc;
+  const int block = 128;
+  const int grid = (n_sets + block - 1) / block;
+  crb_assemble_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(kplan_of(plan), T, params, n_param_sets, n_sets, 0, 0, 0.0,
+                                                               shift, afac, nullptr, nullptr, nullptr, nullptr, nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_assemble_shifted: launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -290,6 +312,25 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
     }
   }
   return rk4_dispatch(plan, sys, X, t0, h, nsteps, Y_out, save_every, st);
+}
+
+extern "C" int crb_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* afac, int32_t afac_shared,
+                            double* X, double t0, double h, int32_t nsteps, double* Y_out, int32_t save_every,
+                            void* stream) {
+  if (int rc = check_system("crb_midpoint", plan, sys)) return rc;
+  if (!X || !afac) return fail(CRB_E_ARG, "crb_midpoint: null state / factor pointer");
+  if (nsteps < 0) return fail(CRB_E_ARG, "crb_midpoint: nsteps must be >= 0");
+  if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_midpoint: step h must be positive and finite");
+  if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_midpoint: save_every must be >= 1 when Y_out is given");
+  if (!(sys->all_linear && plan->contiguous && plan->p_act == plan->p && !sys->drag && sys->grav_mode == 0 && !sys->gain))
+    return fail(CRB_E_ARG, "crb_midpoint: needs an all-linear beam without drag / gravity / feedback on a contiguous "
+                           "plan without phantom slots (the implicit step solves with M + h^2/4 K)");
+  if (nsteps == 0) return 0;
+  if (int rc = crb_launch_midpoint(plan, sys, afac, afac_shared, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream))
+    return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CRB_E_CUDA, "crb_midpoint: launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ __device__ __forceinline__ M2 ld_m2(const double* mf, int base, int s, int m, in
 
 __global__ void __launch_bounds__(128)
 crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n_param_sets,
-                    int n_mass, int n_stiff, int n_force, double fluid_density,
+                    int n_mass, int n_stiff, int n_force, double fluid_density, double shift,
                     double* __restrict__ mfac, double* __restrict__ kcoef,
                     uint8_t* __restrict__ etype_out, double* __restrict__ drag,
                     double* __restrict__ grav, double* __restrict__ seg_half_mass) {
@@ -155,6 +155,18 @@ crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n
     mu = q[CRB_P_RHO] * q[CRB_P_AREA] * L / 420;
   };
 
+  // shift != 0: factor M + shift * K instead of M (implicit midpoint, shift = h^2 / 4); linear element
+  // stiffness blocks of models/segments.py:32-62 in the same node-block form as the mass blocks
+  auto stiff_of = [&](int e, double& ka, double& c1, double& c2, double& c3) {
+    const double* q = par + e * CRB_NPARAM;
+    const double L = q[CRB_P_LENGTH];
+    const double EI = q[CRB_P_E] * q[CRB_P_I];
+    ka = shift * (q[CRB_P_E] * q[CRB_P_AREA] / L);
+    c1 = shift * (EI / L);
+    c2 = shift * (EI / (L * L));
+    c3 = shift * (EI / (L * L * L));
+  };
+
   M2 Sinv_prev = {0, 0, 0, 0};
   double sinvu_prev = 0.0;
   for (int s = 0; s < Pn; ++s) {
@@ -176,6 +188,22 @@ crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n
         O = {54 * mu, -13 * L * mu, 13 * L * mu, -3 * L * L * mu};
         Ou = 70 * mu;
       }
+      if (shift != 0.0) {
+        double ka, c1, c2, c3;
+        stiff_of(el, ka, c1, c2, c3);
+        D.a += 12 * c3;
+        D.b += 6 * c2;
+        D.c += 6 * c2;
+        D.d += 4 * c1;
+        Du += ka;
+        if (s >= 1) {
+          O.a += -12 * c3;
+          O.b += 6 * c2;
+          O.c += -6 * c2;
+          O.d += 2 * c1;
+          Ou += -ka;
+        }
+      }
     }
     if (er >= 0) {
       double mu, L;
@@ -185,6 +213,15 @@ crb_assemble_kernel(KPlan P, AsmTopo T, const double* __restrict__ params, int n
       D.c += -22 * L * mu;
       D.d += 4 * L * L * mu;
       Du += 140 * mu;
+      if (shift != 0.0) {
+        double ka, c1, c2, c3;
+        stiff_of(er, ka, c1, c2, c3);
+        D.a += 12 * c3;
+        D.b += -6 * c2;
+        D.c += -6 * c2;
+        D.d += 4 * c1;
+        Du += ka;
+      }
     }
     // boundary conditions: constrained DOFs become identity rows / columns
     const bool fu = fb & 1, fw = fb & 2, fp = fb & 4;

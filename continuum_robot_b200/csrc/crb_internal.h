@@ -107,6 +107,8 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
                            int nsteps, double* Y_out, int save_every, cudaStream_t stream);
 int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h,
                         int nsteps, double* Y_out, int save_every, cudaStream_t stream);
+int crb_launch_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* afac, int afac_shared, double* X,
+                        double t0, double h, int nsteps, double* Y_out, int save_every, cudaStream_t stream);
 int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t, double* h_abs,
                     double t_bound, double rtol, double atol, const double* t_eval, int n_eval, double* Y_eval,
                     int* status, long long* counters, int max_attempts, cudaStream_t stream);

@@ -54,3 +54,40 @@ int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double*
 #undef CRB_CASE
   return 1;  // shape not instantiated: the caller falls back to the general kernel
 }
+
+// ------------------------------------------------------------------------------------------
+// implicit midpoint
+// ------------------------------------------------------------------------------------------
+template <int M, int LV, bool PM>
+static int launch_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* afac, double* X, double t0,
+                           double h, int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
+  const int mpb = CRB_FAST_WARPS * (32 >> LV);
+  const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
+#define CRB_MID(UCV, IMPV)                                                                                \
+  {                                                                                                      \
+    if (int rc = set_smem(crb_midpoint_kernel<M, LV, UCV, IMPV, PM>, bytes, "crb_midpoint")) return rc;  \
+    crb_midpoint_kernel<M, LV, UCV, IMPV, PM><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, afac, X, t0, h, nsteps, \
+                                                                                        Y_out, save_every); \
+  }
+  if (uc) CRB_MID(true, true)   // forcing variant handles both (imp_amp may be NULL)
+  else if (imp) CRB_MID(false, true)
+  else CRB_MID(false, false)
+#undef CRB_MID
+  return 0;
+}
+
+int crb_launch_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* afac, int afac_shared, double* X,
+                        double t0, double h, int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
+#define CRB_CASE_MID(MM, LL)                                                                                        \
+  if (plan->m == MM && plan->levels == LL)                                                                          \
+    return afac_shared ? launch_midpoint<MM, LL, false>(plan, sys, afac, X, t0, h, nsteps, Y_out, save_every, stream) \
+                       : launch_midpoint<MM, LL, true>(plan, sys, afac, X, t0, h, nsteps, Y_out, save_every, stream);
+  CRB_CASE_MID(4, 3) CRB_CASE_MID(4, 4) CRB_CASE_MID(4, 5) CRB_CASE_MID(4, 2) CRB_CASE_MID(4, 1) CRB_CASE_MID(4, 0)
+  CRB_CASE_MID(3, 1) CRB_CASE_MID(3, 2) CRB_CASE_MID(3, 3) CRB_CASE_MID(3, 0) CRB_CASE_MID(2, 0) CRB_CASE_MID(2, 1)
+  CRB_CASE_MID(1, 0)
+#undef CRB_CASE_MID
+  return crb_fail(CRB_E_LIMIT, "crb_midpoint: lane layout m=%d, levels=%d is not instantiated", plan->m, plan->levels);
+}

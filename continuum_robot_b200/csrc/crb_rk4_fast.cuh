@@ -90,7 +90,7 @@ __device__ __forceinline__ void elem_linear_vals(const double4 c, const double (
 
 // a <- M^-1 (-K w + impulse(t));  `w` holds the stage positions on entry, accelerations on exit.
 template <int M, int LV, bool IMP, typename CT>
-__device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], double t) {
+__device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], double t, const double (*uc)[3] = nullptr) {
   constexpr int G = 1 << LV;
   double qh[3];
 #pragma unroll
@@ -122,6 +122,12 @@ __device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], doubl
 #pragma unroll
       for (int d = 0; d < 3; ++d)
         if (C.imp_local == 3 * j + d) b[0][j][d] += C.imp_amp;
+  }
+  if (uc) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) b[0][j][d] += uc[j][d];
   }
   fast_solve_r<M, LV, 1>(b, C);
 #pragma unroll
@@ -452,6 +458,115 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
+      double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          yq[3 * j + d] = q[j][d];
+          yq[n + 3 * j + d] = v[j][d];
+        }
+    }
+  }
+  if (C.active) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        xq[3 * j + d] = q[j][d];
+        xq[n + 3 * j + d] = v[j][d];
+      }
+  }
+}
+
+// ==========================================================================================
+// Implicit midpoint rule (Newmark average acceleration) for the same beams: ONE operator
+// application and ONE solve with the factors of M + h^2/4 K per step (crb_assemble_shifted),
+//     dv = h (M + h^2/4 K)^-1 ( u(t + h/2) - K (q + h/2 v) ),  v+ = v + dv,  q+ = q + h v + h/2 dv
+// Unconditionally stable: the step is chosen for accuracy, not for the highest element frequency
+// (RK4 needs h < 2.8 / omega_max; the reference's examples use LSODA for that reason,
+// examples/example_utilities.py:153-159).  Not a reference code path: parity is against the oracle's
+// restatement of the rule on the reference's M and K.
+// ==========================================================================================
+template <int M, int LV, bool UC, bool IMP, bool PM>
+__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
+crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, double* __restrict__ X, double t0,
+                    double h, int nsteps, double* __restrict__ Y, int save_every) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
+  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mloc = warp * mpw + lane / G;
+  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
+  typedef FastCtx<M, 4, 1, 4> Ctx;  // one solve per step: every constant of the solve stays in registers
+  Ctx C;
+  C.g = lane % G;
+  C.n = P.n_free;
+  C.active = member < S.n_members;
+  C.member = C.active ? member : S.n_members - 1;
+  {
+    const long long off = 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+    if (PM) {
+      const double* src = afac + (long long)C.member * P.mfac_doubles + off;
+      double* dst = smem + mloc * FAST_DOUBLES;
+      for (int k = C.g; k < FAST_DOUBLES; k += G) dst[k] = src[k];
+    } else {
+      const double* src = afac + off;
+      for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+    }
+    __syncthreads();
+  }
+  C.fslot = smem + (PM ? mloc * FAST_DOUBLES : 0);
+  C.fscan = C.fslot + crb_compact_slot_doubles(M, G);
+  fast_pin_load<M, G, Ctx>(C);
+  const int s0 = C.g * M;
+  {
+    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
+      const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
+      C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
+    }
+  }
+  C.imp_amp = (IMP && S.imp_amp) ? S.imp_amp[C.member] : 0.0;
+  C.imp_dur = S.imp_duration;
+  C.imp_local = -1;
+  if (IMP && S.imp_amp) {
+    const int rel = S.imp_dof - 3 * s0;
+    if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
+  }
+  const int n = C.n;
+  double* xq = X + (long long)C.member * 2 * n + 3 * s0;
+  double q[M][3], v[M][3], w[M][3], uc[UC ? M : 1][3];
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      q[j][d] = xq[3 * j + d];
+      v[j][d] = xq[n + 3 * j + d];
+      if (UC) {
+        const long long mo = (long long)C.member * n + 3 * s0 + 3 * j + d;
+        uc[j][d] = (S.u_const ? S.u_const[mo] : 0.0) + (S.f_ext ? S.f_ext[mo] : 0.0);
+      }
+    }
+  const double hh = 0.5 * h;
+  for (int k = 0; k < nsteps; ++k) {
+    const double tm = t0 + (k + 0.5) * h;  // inputs at the midpoint
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) w[j][d] = fma(hh, v[j][d], q[j][d]);
+    fast_accel<M, LV, IMP, Ctx>(C, w, tm, UC ? uc : nullptr);  // w <- (M + h^2/4 K)^-1 (u - K w)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double dv = h * w[j][d];
+        q[j][d] = fma(hh, dv, fma(h, v[j][d], q[j][d]));
+        v[j][d] += dv;
+      }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
       double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
 #pragma unroll

@@ -391,6 +391,29 @@ class BatchedDynamicEulerBernoulliBeam:
         if self.force_params.enable_gravity_effects:
             self.force_registry.register(GravityForce(self, self.force_params.get_gravity_vector(), True))
 
+    def shifted_factors(self, shift: float):
+        """(afac, shared): block-LDL^T factors of M + shift K on the device (crb_assemble_shifted), one set if
+        mass and stiffness are shared by all members, else one per member; cached per shift."""
+        torch = _torch()
+        if not self._all_linear:
+            raise ValueError("M + shift K needs an all-linear beam")
+        cache = self.__dict__.setdefault("_shift_cache", {})
+        key = float(shift)
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.clear()
+            shared = bool(self._mass_shared and self._stiff_shared)
+            Bp = self._params_np.shape[0]
+            n_sets = 1 if shared else Bp
+            afac = torch.empty((n_sets, int(self._plan.mfac_doubles)), dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = _lib.load().crb_assemble_shifted(
+                    C.byref(self._plan), self._d_params.data_ptr(), Bp, self._etype.tobytes(), self._bc.tobytes(),
+                    n_sets, key, afac.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc)
+            cache[key] = (afac, shared)
+        return cache[key]
+
     def with_slots(self, max_slots_per_lane: int) -> "BatchedDynamicEulerBernoulliBeam":
         """Same ensemble assembled for another lane decomposition (e.g. 2 slots per lane for the
         register-hungry adaptive kernel).  Registries and function state are SHARED with ``self``."""

@@ -6,7 +6,9 @@ examples/pyodide_example/pyodide_example.py:69-75) with a batched call whose res
 ``OdeResult`` (``.t``, ``.y``, ``.nfev``, ``.status``, ``.success``, ``.message``), per member.
 
   * ``method="RK4"``  classical fixed-step RK4, ``nsteps`` fused per launch (crb_rk4);
-  * ``method="RK45"`` Dormand-Prince 5(4) with SciPy's controller, per-member dt (crb_rk45).
+  * ``method="RK45"`` Dormand-Prince 5(4) with SciPy's controller, per-member dt (crb_rk45);
+  * ``method="MIDPOINT"`` implicit midpoint rule for all-linear beams (crb_midpoint): not a reference code
+    path, the stiff-capable alternative to the LSODA runs of the reference's examples.
 """
 
 from __future__ import annotations
@@ -83,6 +85,33 @@ def rk4_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, ns
     with torch.cuda.device(beam.device):
         rc = _lib.load().crb_rk4(
             C.byref(beam._plan), C.byref(sysm), X.data_ptr(), float(t0), float(h), int(nsteps),
+            Y_out.data_ptr() if Y_out is not None else None, int(save_every), beam._stream(),
+        )
+    _lib.check(rc)
+    return X
+
+
+def midpoint_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, nsteps: int, *, u=None,
+                   Y_out=None, save_every: int = 0):
+    """Advance X[B,2n] in place by ``nsteps`` implicit-midpoint steps (Newmark average acceleration) in ONE
+    kernel launch (crb_midpoint).  All-linear beams without drag / gravity / feedback; ``u``: constant
+    tensor [B,n] or TipImpulse, evaluated at the step midpoints.  Unconditionally stable: ``h`` is chosen
+    for accuracy (the rule is second order), not for the highest element frequency as with RK4 -- the
+    reason the reference's examples integrate with LSODA (examples/example_utilities.py:153-159)."""
+    import torch
+
+    drag, grav, user = beam._active_forces()
+    if user or beam._forces_func is not None or drag is not None or grav is not None:
+        raise TypeError("the implicit midpoint rule supports force-free all-linear beams (inputs: tensor or TipImpulse)")
+    impulse = u if isinstance(u, TipImpulse) else None
+    uc = None if (u is None or impulse is not None) else u
+    if callable(uc) and not isinstance(uc, torch.Tensor):
+        raise TypeError("implicit midpoint needs a constant tensor or TipImpulse input")
+    sysm, _keep = beam.make_system(X.shape[0], u_const=uc, impulse=impulse)
+    afac, shared = beam.shifted_factors(0.25 * float(h) * float(h))
+    with torch.cuda.device(beam.device):
+        rc = _lib.load().crb_midpoint(
+            C.byref(beam._plan), C.byref(sysm), afac.data_ptr(), int(shared), X.data_ptr(), float(t0), float(h), int(nsteps),
             Y_out.data_ptr() if Y_out is not None else None, int(save_every), beam._stream(),
         )
     _lib.check(rc)
@@ -218,9 +247,9 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
     drag, grav, user = beam._active_forces()
     needs_unfused = bool(user) or beam._forces_func is not None or (callable(u) and not isinstance(u, (TipImpulse, torch.Tensor)))
 
-    if method == "RK4":
+    if method in ("RK4", "MIDPOINT"):
         if h is None or not h > 0:
-            raise ValueError("RK4 needs a positive step h")
+            raise ValueError(f"{method} needs a positive step h")
         nsteps = int(round((tf - t0) / h))
         if t_eval is not None:
             te = np.asarray(t_eval, dtype=np.float64)
@@ -233,7 +262,11 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
         se = int(save_every) if save_every else nsteps
         nframes = nsteps // se
         Y = torch.empty((nframes, B, n2), dtype=torch.float64, device=beam.device) if nframes else None
-        if needs_unfused:
+        if method == "MIDPOINT":
+            if needs_unfused or controller is not None:
+                raise TypeError("MIDPOINT supports force-free all-linear beams with tensor / TipImpulse inputs only")
+            midpoint_steps(beam, X, t0, h, nsteps, u=u, Y_out=Y, save_every=se)
+        elif needs_unfused:
             _rk4_unfused(beam, X, t0, h, nsteps, u, controller, Y, se)
         else:
             rk4_steps(beam, X, t0, h, nsteps, u=u, controller=controller, Y_out=Y, save_every=se)
@@ -245,12 +278,12 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
             frames = frames[torch.as_tensor(sel, device=frames.device)]
             tt = tt[sel]
         y = frames.permute(1, 2, 0).contiguous()
-        nfev = torch.full((B,), 4 * nsteps, dtype=torch.int64, device=beam.device)
+        nfev = torch.full((B,), (4 if method == "RK4" else 1) * nsteps, dtype=torch.int64, device=beam.device)
         status = torch.zeros(B, dtype=torch.int32, device=beam.device)
         return EnsembleResult(tt, y[0] if squeeze else y, nfev, status, True, MESSAGES[0])
 
     if method != "RK45":
-        raise ValueError(f"method must be 'RK4' or 'RK45', got {method!r} (LSODA is out of scope)")
+        raise ValueError(f"method must be 'RK4', 'RK45' or 'MIDPOINT', got {method!r} (LSODA is out of scope)")
     if needs_unfused:
         raise TypeError("RK45 supports built-in forces, tensor/TipImpulse inputs and FullStateLinear feedback only")
     impulse = u if isinstance(u, TipImpulse) else None

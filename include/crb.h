@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 102
+#define CRB_VERSION 103
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 
@@ -179,6 +179,20 @@ int crb_pipeline_wait(crb_pipeline_t* p, void* stream);
 int crb_pipeline_synchronize(crb_pipeline_t* p);
 int crb_rk4_host(crb_pipeline_t* p, const crb_plan_t* plan, const crb_system_t* sys, double* X_host,
                  double* X_dev, int32_t chunk_members, double t0, double h, int32_t nsteps, void* stream);
+
+/* Implicit midpoint rule (= Newmark average acceleration) for all-linear beams, the stiff-capable
+ * companion of crb_rk4: the reference's examples integrate with LSODA because explicit steps are
+ * stability-limited (h < 2.8 / omega_max, examples/example_utilities.py:153-159); this rule is
+ * unconditionally stable, second order and conserves the beam's quadratic energy exactly.
+ *     dv = h (M + h^2/4 K)^-1 ( u(t + h/2) - K (q + h/2 v) ),   v+ = v + dv,   q+ = q + h v + h/2 dv
+ * crb_assemble_shifted factors M + shift K (shift = h^2/4) into afac[n_sets, plan.mfac_doubles]
+ * (n_sets = 1 for one shared design, else n_param_sets); crb_midpoint advances X[B,2n] in place by
+ * nsteps fused steps (inputs: u_const / f_ext / impulse of crb_system_t, evaluated at the midpoint). */
+int crb_assemble_shifted(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
+                         const uint8_t* elem_type_host, const uint8_t* bc_host, int32_t n_sets, double shift,
+                         double* afac, void* stream);
+int crb_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* afac, int32_t afac_shared,
+                 double* X, double t0, double h, int32_t nsteps, double* Y_out, int32_t save_every, void* stream);
 
 /* Adaptive Dormand-Prince 5(4) with SciPy's controller (scipy/integrate/_ivp/rk.py:86-180),
  * one independent (t, h) per member.  Replaces solve_ivp(method="RK45") as called at

@@ -497,6 +497,37 @@ def rk4_solve(f: Callable, x0: np.ndarray, t0: float, h: float, nsteps: int, sav
     return (x, np.array(out)) if save_every else x
 
 
+def dense_stiffness(beam: "BeamOracle") -> np.ndarray:
+    """BC-reduced K of an all-linear beam, column by column from k(e_j) (euler_bernoulli_beam.py:422-511)."""
+    n = beam.n
+    K = np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        K[:, j] = beam.stiffness(e)
+    return K
+
+
+def midpoint_solve(beam: "BeamOracle", u: Callable, x0: np.ndarray, t0: float, h: float, nsteps: int, save_every: int = 0):
+    """Implicit midpoint rule (= Newmark average acceleration) on M q'' = -K q + u(t) for an all-linear,
+    force-free beam.  NOT a reference code path (the reference integrates with SciPy's solve_ivp): this
+    restates the textbook rule on the reference's M and K so that crb_midpoint has a CPU checker.
+        dv = h (M + h^2/4 K)^-1 (u(t + h/2) - K (q + h/2 v)),  v+ = v + dv,  q+ = q + h v + h/2 dv"""
+    n = beam.n
+    K = dense_stiffness(beam)
+    A = beam.M + 0.25 * h * h * K
+    x = np.array(x0, dtype=np.float64)
+    out = []
+    for k in range(nsteps):
+        q, v = x[:n], x[n:]
+        tm = t0 + (k + 0.5) * h
+        dv = h * np.linalg.solve(A, u(tm) - K @ (q + 0.5 * h * v))
+        x = np.concatenate([q + h * v + 0.5 * h * dv, v + dv])
+        if save_every and (k + 1) % save_every == 0:
+            out.append(x.copy())
+    return (x, np.array(out)) if save_every else x
+
+
 # Dormand-Prince 5(4) tableau as used by SciPy (scipy/integrate/_ivp/rk.py:538-565).
 DP_C = np.array([0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1])
 DP_A = np.array(
