@@ -489,8 +489,14 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
 // examples/example_utilities.py:153-159).  Not a reference code path: parity is against the oracle's
 // restatement of the rule on the reference's M and K.
 // ==========================================================================================
+#ifndef CRB_MID_MINBLOCKS
+#define CRB_MID_MINBLOCKS CRB_FAST_MINBLOCKS
+#endif
+#ifndef CRB_MID_PINS
+#define CRB_MID_PINS 4
+#endif
 template <int M, int LV, bool UC, bool IMP, bool PM>
-__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_MID_MINBLOCKS)
 crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, double* __restrict__ X, double t0,
                     double h, int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
@@ -499,7 +505,7 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mloc = warp * mpw + lane / G;
   const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
-  typedef FastCtx<M, 4, 1, 4> Ctx;  // one solve per step: every constant of the solve stays in registers
+  typedef FastCtx<M, CRB_MID_PINS, (CRB_MID_PINS > 0 ? 1 : 0), CRB_MID_PINS> Ctx;  // one solve per step: the constants of the solve stay in registers
   Ctx C;
   C.g = lane % G;
   C.n = P.n_free;
