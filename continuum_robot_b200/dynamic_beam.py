@@ -400,7 +400,7 @@ class BatchedDynamicEulerBernoulliBeam:
         cache = self.__dict__.setdefault("_shift_cache", {})
         key = float(shift)
         if key not in cache:
-            if len(cache) >= 4:
+            if len(cache) >= 2:  # a per-member factor set is as large as 13 KB x members
                 cache.clear()
             shared = bool(self._mass_shared and self._stiff_shared)
             Bp = self._params_np.shape[0]

@@ -171,7 +171,8 @@ int crb_system_slice(const crb_plan_t* plan, const crb_system_t* sys, int32_t lo
  * events only -- X_dev[B,2n] is caller-owned device workspace).  The call returns immediately; its
  * work is ordered after everything enqueued on `stream` so far.  Consecutive calls on the same
  * buffers and chunking overlap chunk by chunk.  crb_pipeline_wait makes `stream` wait for all
- * outstanding copies; crb_pipeline_synchronize blocks the host. */
+ * outstanding copies; crb_pipeline_synchronize blocks the host.  A handle belongs to one device and is
+ * used by one host thread at a time (create one per thread, like a stream). */
 typedef struct crb_pipeline crb_pipeline_t;
 int crb_pipeline_create(crb_pipeline_t** out);
 int crb_pipeline_destroy(crb_pipeline_t* p);

@@ -384,3 +384,33 @@ def test_system_slice_offsets_per_member_pointers():
     assert out.mfac == base + 8 * 7 * plan.mfac_doubles
     assert lib.crb_system_slice(C.byref(plan), C.byref(s), 990, 20, C.byref(out)) < 0
     assert b"outside" in lib.crb_last_error()
+
+
+def test_midpoint_entry_points_validate_before_touching_the_device():
+    """crb_assemble_shifted / crb_midpoint report bad arguments through the return code (no CUDA call yet)."""
+    L = _lib()
+    lib = L.load()
+    rc, plan = _plan(4, [1, 0, 0, 0, 0])
+    assert rc == 0
+    par = np.ones((1, 4, 7))
+    args = (C.byref(plan), par.ctypes.data_as(C.c_void_p), 1, bytes([0, 1, 0, 0]), bytes([1, 0, 0, 0, 0]), 1)
+    assert lib.crb_assemble_shifted(*args, 1e-8, C.c_void_p(16), None) < 0
+    assert b"not linear" in lib.crb_last_error()
+    lin = (C.byref(plan), par.ctypes.data_as(C.c_void_p), 1, bytes([0, 0, 0, 0]), bytes([1, 0, 0, 0, 0]))
+    assert lib.crb_assemble_shifted(*lin, 1, -1.0, C.c_void_p(16), None) < 0 and b"shift" in lib.crb_last_error()
+    assert lib.crb_assemble_shifted(*lin, 3, 1e-8, C.c_void_p(16), None) < 0 and b"n_sets" in lib.crb_last_error()
+    assert lib.crb_assemble_shifted(*lin, 1, 1e-8, None, None) < 0
+    s = L.CrbSystem()
+    s.n_members = 4
+    assert lib.crb_midpoint(C.byref(plan), C.byref(s), C.c_void_p(16), 1, C.c_void_p(16), 0.0, 1e-4, 1, None, 0, None) < 0
+    assert b"not assembled" in lib.crb_last_error()
+    s.mfac = s.kcoef = s.elem_type = s.red_index = 16
+    s.all_linear = 1
+    s.grav_mode = 1
+    s.grav = 16
+    assert lib.crb_midpoint(C.byref(plan), C.byref(s), C.c_void_p(16), 1, C.c_void_p(16), 0.0, 1e-4, 1, None, 0, None) < 0
+    assert b"all-linear beam without drag / gravity" in lib.crb_last_error()
+    s.grav_mode, s.grav = 0, None
+    assert lib.crb_midpoint(C.byref(plan), C.byref(s), C.c_void_p(16), 1, C.c_void_p(16), 0.0, 0.0, 1, None, 0, None) < 0
+    assert b"positive" in lib.crb_last_error()
+    assert lib.crb_midpoint(C.byref(plan), C.byref(s), C.c_void_p(16), 1, C.c_void_p(16), 0.0, 1e-4, 0, None, 0, None) == 0  # nothing to do
