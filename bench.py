@@ -296,7 +296,7 @@ def run_gpu(args):
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": which,
                 "note": "algorithmic 96 B per element-step; launches fuse steps so DRAM traffic is far below it; the "
-                        "kernel is bound by the shared-memory/shuffle (LSU) pipe at 79 % with the FP64 pipe at 60 % "
+                        "kernel is bound on-chip: shared-memory/shuffle (LSU) pipe 65 %, FP64 pipe 63 %, latency-limited at 8 warps/SM "
                         "(see DESIGN.md / profiles/)",
             },
             "e2e": {"value": e2e_val, "unit": "element-steps/s", "h2d_bytes_per_step": X.numel() * 8 / S,
