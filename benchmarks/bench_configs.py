@@ -71,6 +71,21 @@ def main():
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
             print(json.dumps({"config": "cfg2 x%d (nonlinear 20 el + drag), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
                               "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg2m":  # config 2 shape with PER-MEMBER density and stiffness (no shared factor set)
+            B, steps = 32768, 100
+            e = ens.config2()
+            rng = np.random.default_rng(9)
+            par = np.repeat(params(e, 1), B, axis=0)
+            par[:, :, 3] *= np.exp(0.1 * rng.standard_normal((B, 1)))
+            par[:, :, 1] *= np.exp(0.2 * rng.standard_normal((B, 1)))
+            beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["nonlinear"] * 20},
+                                                    ForceParams(fluid_density=1000.0, enable_fluid_effects=True))
+            beam.create_system_func(); beam.create_input_func()
+            X = torch.zeros(B, 120, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.full((B,), 0.1, dtype=torch.float64, device=dev))
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
+            print(json.dumps({"config": "cfg2 x%d with per-member density and stiffness, RK4" % B,
+                              "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg3g":  # config 3 through the GENERAL kernel (comparison)
             B, steps = 65536, 50
             e = ens.config3(B, 32)

@@ -799,6 +799,21 @@ __device__ __forceinline__ void stage_compact(const crb_system_t& S, double* sme
   fm.fscan = smem + crb_compact_slot_doubles(M, G);
 }
 
+// Per-member factor sets: every lane group stages its member's compact copy in its own shared-memory region.
+template <int M, int LV>
+__device__ __forceinline__ void stage_compact_pm(const crb_system_t& S, const KPlan& P, double* smem, FastMass& fm, int g,
+                                                 int mloc, int member) {
+  constexpr int G = 1 << LV, LVE = LV > 0 ? LV : 1;
+  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
+  const double* src = S.mfac + (long long)member * P.mfac_doubles + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+  double* dst = smem + mloc * FAST_DOUBLES;
+  for (int k = g; k < FAST_DOUBLES; k += G) dst[k] = src[k];
+  __syncthreads();
+  fm.g = g;
+  fm.fslot = dst;
+  fm.fscan = dst + crb_compact_slot_doubles(M, G);
+}
+
 template <int M>
 __device__ __forceinline__ void load_state(const LaneCtx<M>& L, const double* __restrict__ X,
                                            double (&q)[M][3], double (&v)[M][3]) {

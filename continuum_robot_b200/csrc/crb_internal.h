@@ -50,6 +50,15 @@ inline SmemLayout smem_layout_compact(const crb_plan_t* plan, const crb_system_t
   *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
   return SL;
 }
+// ... or, with per-member mass, one compact copy per member of the block
+inline SmemLayout smem_layout_compact_pm(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
+  SmemLayout SL = smem_layout(plan, sys, bytes);
+  const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
+  SL.mfac_doubles = crb_compact_doubles(plan->m, plan->g, plan->levels) * mpb;
+  *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
+  return SL;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* who) {
   if (bytes > 48 * 1024) {

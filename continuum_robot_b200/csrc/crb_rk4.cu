@@ -4,7 +4,8 @@
 // Classical RK4, nsteps fused: state, stage state and the running combination stay in registers.
 // LV >= 0: lanes per member = 1 << LV known at compile time (constant shuffle widths and
 // shared-memory offsets); LV = -1: generic.
-template <int M, unsigned FEAT, int LV>
+// PM: per-member mass factors (shape-specialised kernels only): compact solve on per-member shared-memory regions.
+template <int M, unsigned FEAT, int LV, bool PM = false>
 __global__ void __launch_bounds__(CRB_THREADS)
 crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
                int nsteps, double* __restrict__ Y, int save_every) {
@@ -13,7 +14,7 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
   // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
   // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
-  constexpr bool UMS = LV >= 0 && FEAT == CRB_F_PROFILE_A;
+  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || PM);
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Gk = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g;
@@ -26,7 +27,9 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   if (LV >= 0) {  // let the compiler see the constants
     L.G = Gk;
     L.levels = LV;
-    if (UMS) {
+    if (UMS && PM) {
+      stage_compact_pm<M, (LV >= 0 ? LV : 0)>(S, P, smem, L.fm, lane % Gk, mloc, L.member);
+    } else if (UMS) {
       stage_compact<M, (LV >= 0 ? LV : 0)>(S, smem, L.fm, lane % Gk);
     } else {
       L.mc.G = Gk;
@@ -92,20 +95,30 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
   const KPlan P = kplan_of(plan);
   const unsigned need = crb_needed_features(plan, sys);
   const unsigned prof = crb_pick_profile(need);
-#define CRB_RK4_CASE(MM, LL)                                                                                       \
-  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared) {                               \
-    const SmemLayout SL = prof == CRB_F_PROFILE_A ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
-    if (prof == CRB_F_PROFILE_A) {                                                                                  \
-      if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL>, bytes, "crb_rk4")) return rc;                  \
-      crb_rk4_kernel<MM, CRB_F_PROFILE_A, LL><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
-    } else {                                                                                                        \
-      if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_B, LL>, bytes, "crb_rk4")) return rc;                  \
-      crb_rk4_kernel<MM, CRB_F_PROFILE_B, LL><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
-    }                                                                                                               \
+#define CRB_RK4_LAUNCH(MM, PROF, LL, PMV)                                                                          \
+  {                                                                                                                 \
+    if (int rc = set_smem(crb_rk4_kernel<MM, PROF, LL, PMV>, bytes, "crb_rk4")) return rc;                          \
+    crb_rk4_kernel<MM, PROF, LL, PMV><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
     return 0;                                                                                                       \
+  }
+#define CRB_RK4_CASE(MM, LL)                                                                                       \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                                   \
+    if (sys->mass_shared) {                                                                                         \
+      const SmemLayout SL = prof == CRB_F_PROFILE_A ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
+      if (prof == CRB_F_PROFILE_A) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_A, LL, false)                                   \
+      else CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_B, LL, false)                                                           \
+    } else {                                                                                                        \
+      const SmemLayout SL = smem_layout_compact_pm(plan, sys, &bytes);                                              \
+      if (bytes <= 200 * 1024) {                                                                                    \
+        if (prof == CRB_F_PROFILE_A) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_A, LL, true)                                  \
+        else CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_B, LL, true)                                                          \
+      }                                                                                                             \
+      smem_layout(plan, sys, &bytes);                                                                               \
+    }                                                                                                               \
   }
   CRB_SPECIALISED_SHAPES(CRB_RK4_CASE)
 #undef CRB_RK4_CASE
+#undef CRB_RK4_LAUNCH
   CRB_DISPATCH_M(plan->m, {
     if (int rc = set_smem(crb_rk4_kernel<M, CRB_F_ALL, -1>, bytes, "crb_rk4")) return rc;
     crb_rk4_kernel<M, CRB_F_ALL, -1><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every);
