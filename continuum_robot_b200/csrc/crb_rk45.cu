@@ -22,21 +22,33 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   auto total_bytes = [&](const SmemLayout& L, int m) {
     return sizeof(double) * ((size_t)L.mfac_doubles + (size_t)L.scratch_doubles * mpb + (size_t)21 * m * 32 * WPB);
   };
-#define CRB_RK45_CASE(MM, LL)                                                                             \
-  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL && sys->mass_shared) {                      \
-    if (prof == CRB_F_PROFILE_A) SL = smem_layout_compact(plan, sys, &bytes);                              \
+#define CRB_RK45_LAUNCH(MM, PROF, LL, PMV)                                                                 \
+  {                                                                                                        \
     const size_t total = total_bytes(SL, MM);                                                              \
-    if (prof == CRB_F_PROFILE_A) {                                                                         \
-      if (int rc = set_smem(crb_rk45_kernel<MM, CRB_F_PROFILE_A, LL, WPB>, total, "crb_rk45")) return rc;  \
-      crb_rk45_kernel<MM, CRB_F_PROFILE_A, LL, WPB><<<grid, 32 * WPB, total, stream>>>(P, *sys, SL, A, T); \
-    } else {                                                                                               \
-      if (int rc = set_smem(crb_rk45_kernel<MM, CRB_F_PROFILE_B, LL, WPB>, total, "crb_rk45")) return rc;  \
-      crb_rk45_kernel<MM, CRB_F_PROFILE_B, LL, WPB><<<grid, 32 * WPB, total, stream>>>(P, *sys, SL, A, T); \
-    }                                                                                                      \
+    if (int rc = set_smem(crb_rk45_kernel<MM, PROF, LL, WPB, PMV>, total, "crb_rk45")) return rc;          \
+    crb_rk45_kernel<MM, PROF, LL, WPB, PMV><<<grid, 32 * WPB, total, stream>>>(P, *sys, SL, A, T);         \
     return 0;                                                                                              \
+  }
+#define CRB_RK45_CASE(MM, LL)                                                                             \
+  if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                          \
+    if (sys->mass_shared) {                                                                                \
+      if (prof == CRB_F_PROFILE_A) SL = smem_layout_compact(plan, sys, &bytes);                            \
+      if (prof == CRB_F_PROFILE_A) CRB_RK45_LAUNCH(MM, CRB_F_PROFILE_A, LL, false)                         \
+      else CRB_RK45_LAUNCH(MM, CRB_F_PROFILE_B, LL, false)                                                 \
+    } else {                                                                                               \
+      const SmemLayout keep = SL;                                                                          \
+      SL = smem_layout(plan, sys, &bytes);                                                                 \
+      SL.mfac_doubles = crb_compact_doubles(plan->m, plan->g, plan->levels) * mpb;                         \
+      if (total_bytes(SL, MM) <= 200 * 1024) {                                                             \
+        if (prof == CRB_F_PROFILE_A) CRB_RK45_LAUNCH(MM, CRB_F_PROFILE_A, LL, true)                        \
+        else CRB_RK45_LAUNCH(MM, CRB_F_PROFILE_B, LL, true)                                                \
+      }                                                                                                    \
+      SL = keep;                                                                                           \
+    }                                                                                                      \
   }
   CRB_SPECIALISED_SHAPES(CRB_RK45_CASE)
 #undef CRB_RK45_CASE
+#undef CRB_RK45_LAUNCH
   CRB_DISPATCH_M(plan->m, {
     const size_t total = total_bytes(SL, M);
     if (int rc = set_smem(crb_rk45_kernel<M, CRB_F_ALL, -1, WPB>, total, "crb_rk45")) return rc;

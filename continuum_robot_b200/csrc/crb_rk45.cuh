@@ -109,7 +109,8 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 // WPB warps per block: members take different numbers of attempts, and a block lives as long as its
 // slowest member, so the adaptive kernel runs with small blocks (2 warps; the hardware block scheduler
 // then balances the ragged ensemble) where the fixed-step kernels use 4.
-template <int M, unsigned FEAT, int LV, int WPB>
+// PM: per-member mass factors (shape-specialised kernels): compact solve on per-member shared-memory regions.
+template <int M, unsigned FEAT, int LV, int WPB, bool PM = false>
 __global__ void __launch_bounds__(32 * WPB)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   constexpr int THREADS = 32 * WPB;
@@ -118,7 +119,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
   // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
   // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
-  constexpr bool UMS = LV >= 0 && FEAT == CRB_F_PROFILE_A;
+  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || PM);
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g, mpw = 32 / G;
@@ -131,7 +132,9 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   if (LV >= 0) {
     L.G = G;
     L.levels = LV;
-    if (UMS) {
+    if (UMS && PM) {
+      stage_compact_pm<M, (LV >= 0 ? LV : 0)>(S, P, smem, L.fm, lane % G, mloc, L.member);
+    } else if (UMS) {
       stage_compact<M, (LV >= 0 ? LV : 0)>(S, smem, L.fm, lane % G);
     } else {
       L.mc.G = G;

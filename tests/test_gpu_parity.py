@@ -637,3 +637,19 @@ def test_per_member_mass_in_specialised_general_kernels(N, nonlinear):
             return b.rhs(t, x, u)
         want = bo.rk4_solve(f, x0[i], 0.0, h, steps)
         assert block_err(got[i], want, n) < 1e-9, (i, block_err(got[i], want, n))
+    # adaptive integrator on the same per-member ensemble
+    from continuum_robot_b200 import solve_ensemble
+
+    te = np.linspace(0.0, 3e-4, 4)
+    res = solve_ensemble(beam, (0.0, 3e-4), torch.from_numpy(x0).cuda(), method="RK45", t_eval=te, rtol=1e-6, atol=1e-9, u=imp)
+    for i in (0, B - 1):
+        spec = bo.BeamSpec(par[i, :, 0], par[i, :, 1], par[i, :, 2], par[i, :, 3], par[i, :, 4], et, bc[:N], par[i, :, 5], par[i, :, 6])
+        b = bo.BeamOracle(spec, bo.ForceSpec(1000.0, True, (0.5, -9.81, 0.0), True))
+        def f2(t, x, i=i):
+            u = np.zeros(n)
+            u[n - 2] = amp[i]
+            return b.rhs(t, x, u)
+        r = bo.rk45_solve(f2, (0.0, 3e-4), x0[i], t_eval=te, rtol=1e-6, atol=1e-9)
+        gy = res.y[i].cpu().numpy()
+        assert np.all(np.abs(gy - r.y) <= 10 * (1e-9 + 1e-6 * np.abs(r.y))), i
+        assert abs(int(res.nfev[i]) - r.nfev) <= max(12, 0.02 * r.nfev)
