@@ -414,3 +414,26 @@ def test_midpoint_entry_points_validate_before_touching_the_device():
     assert lib.crb_midpoint(C.byref(plan), C.byref(s), C.c_void_p(16), 1, C.c_void_p(16), 0.0, 0.0, 1, None, 0, None) < 0
     assert b"positive" in lib.crb_last_error()
     assert lib.crb_midpoint(C.byref(plan), C.byref(s), C.c_void_p(16), 1, C.c_void_p(16), 0.0, 1e-4, 0, None, 0, None) == 0  # nothing to do
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU port, no GPU needed): one JSON line with the driver-contract keys;
+    under a multi-rank launch only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "12", "--warmup", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and "workload" in d["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
