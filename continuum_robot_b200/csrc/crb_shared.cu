@@ -186,8 +186,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
-// one copy of the double-precision sincos in the instruction stream
-static __device__ __noinline__ void sincos_once(double phi, double& sn, double& cs) { sincos(phi, &sn, &cs); }
 
 struct SharedArgs {
   const double* blob;
@@ -252,7 +250,7 @@ crb_rk4_shared_kernel(SharedArgs A, double* __restrict__ X, double t0, double h,
 #pragma unroll
         for (int p = 0; p < GKP; ++p) {
           double sn, cs;
-          sincos_once(ph[p], sn, cs);
+          crb_sincos(ph[p], sn, cs);
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             dmma884(acc[nt][0], acc[nt][1], cs, Gc[(p * NT + nt) * 32]);
