@@ -461,6 +461,8 @@ struct LaneCtx {
   int ri[M][3];          // reduced index of own DOFs (-1: constrained / phantom)
   int et[M];             // type of the element left of own slot j
   double4 kc[M];         // stiffness coefficients of that element
+  double imp_amp;        // impulse amplitude of this member (0 if none) ...
+  int imp_local;         // ... and the own DOF (3 j + d) it acts on, or -1
   double drag[M];        // drag factor of own slot (0 = none)
   double gl[M], gt[M];   // gravity half masses: two-ended pseudo-segment left of slot, tail
   MassConsts<M> mc;
@@ -525,6 +527,15 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
     L.drag[j] = S.drag ? S.drag[fo + s] : 0.0;
     L.gl[j] = (S.grav && S.grav_mode == 1) ? S.grav[2 * (fo + s)] : 0.0;
     L.gt[j] = (S.grav && S.grav_mode == 1) ? S.grav[2 * (fo + s) + 1] : 0.0;
+  }
+  L.imp_amp = S.imp_amp ? S.imp_amp[L.member] : 0.0;
+  L.imp_local = -1;
+  if (S.imp_amp) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.ri[j][d] == S.imp_dof) L.imp_local = 3 * j + d;
   }
   const double* mf = S.mass_shared ? mfac_smem : S.mfac + (long long)L.member * P.mfac_doubles;
   L.mc.slot = mf;
@@ -752,10 +763,15 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   }
 
   // ---- inputs u(t): constant part, impulse, external force (dynamic_beam_model.py:357-362) ----
-  if (!ONLY_FORCES && (F.uconst || F.fext || F.impulse)) {
+  if (!ONLY_FORCES && F.impulse && L.imp_local >= 0 && t < S.imp_duration) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (L.imp_local == 3 * j + d) acc[j][d] += L.imp_amp;
+  }
+  if (!ONLY_FORCES && (F.uconst || F.fext)) {
     const long long mo = (long long)L.member * L.n;
-    const bool imp_on = F.impulse && (t < S.imp_duration);
-    const double amp = imp_on ? S.imp_amp[L.member] : 0.0;
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -765,7 +781,6 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
           double u = 0.0;
           if (F.uconst) u += S.u_const[mo + r];
           if (F.fext) u += S.f_ext[mo + r];
-          if (imp_on && r == S.imp_dof) u += amp;
           acc[j][d] += u;
         }
       }
