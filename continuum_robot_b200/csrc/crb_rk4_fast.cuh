@@ -136,47 +136,65 @@ __device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], doubl
     for (int d = 0; d < 3; ++d) w[j][d] = b[0][j][d];
 }
 
+// Common prologue of the fast kernels: which member / lane this thread is, the compact factor copy staged in
+// shared memory (one shared set, or with PM one region per member of the block, read from `fac`), the pinned
+// constants and the lane's stiffness coefficients.  Returns the first slot of the lane.
+template <int M, int LV, bool PM, typename CT>
+__device__ __forceinline__ int fast_ctx_init(CT& C, const KPlan& P, const crb_system_t& S, const double* fac, double* smem) {
+  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
+  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mloc = warp * mpw + lane / G;
+  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
+  C.g = lane % G;
+  C.n = P.n_free;
+  C.active = member < S.n_members;
+  C.member = C.active ? member : S.n_members - 1;
+  const long long off = 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
+  if (PM) {
+    const double* src = fac + (long long)C.member * P.mfac_doubles + off;
+    double* dst = smem + mloc * FAST_DOUBLES;
+    for (int k = C.g; k < FAST_DOUBLES; k += G) dst[k] = src[k];
+  } else {
+    const double* src = fac + off;
+    for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+  }
+  __syncthreads();
+  C.fslot = smem + (PM ? mloc * FAST_DOUBLES : 0);
+  C.fscan = C.fslot + crb_compact_slot_doubles(M, G);
+  fast_pin_load<M, G, CT>(C);
+  const int s0 = C.g * M;
+  const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
+    const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
+    C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
+  }
+  C.imp_amp = 0.0;
+  C.imp_dur = S.imp_duration;
+  C.imp_local = -1;
+  return s0;
+}
+
+// impulse target of this lane: contiguous plan, reduced index = 3 slot + dof
+template <int M, typename CT>
+__device__ __forceinline__ void fast_ctx_impulse(CT& C, const crb_system_t& S, int s0) {
+  if (!S.imp_amp) return;
+  C.imp_amp = S.imp_amp[C.member];
+  const int rel = S.imp_dof - 3 * s0;
+  if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
+}
+
 template <int M, int LV, bool IMP>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h,
                     int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
-  // stage the compact copy of the shared mass factors
-  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
-  {
-    const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
-    for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
-    __syncthreads();
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + warp * mpw + lane / G;
   typedef FastCtx<M> Ctx;
   Ctx C;
-  C.g = lane % G;
-  C.n = P.n_free;
-  C.active = member < S.n_members;
-  C.member = C.active ? member : S.n_members - 1;
-  C.fslot = smem;
-  C.fscan = smem + crb_compact_slot_doubles(M, G);
-  fast_pin_load<M, G, Ctx>(C);
-  const int s0 = C.g * M;
-  {
-    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-      const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
-      const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
-      C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
-    }
-  }
-  C.imp_amp = (IMP && S.imp_amp) ? S.imp_amp[C.member] : 0.0;
-  C.imp_dur = S.imp_duration;
-  C.imp_local = -1;
-  if (IMP && S.imp_amp) {
-    const int rel = S.imp_dof - 3 * s0;  // contiguous plan: reduced index = 3 slot + dof
-    if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
-  }
+  const int s0 = fast_ctx_init<M, LV, false>(C, P, S, S.mfac, smem);
+  if (IMP) fast_ctx_impulse<M>(C, S, s0);
 
   // contiguous plan: the lane's 3M position DOFs are consecutive in the reduced vector
   const int n = C.n;
@@ -332,45 +350,9 @@ __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
                     double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
-  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mloc = warp * mpw + lane / G;
-  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
   typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP) ? 0 : 2)> Ctx;  // forcing vectors need the registers
   Ctx C;
-  C.g = lane % G;
-  C.n = P.n_free;
-  C.active = member < S.n_members;
-  C.member = C.active ? member : S.n_members - 1;
-  {
-    const long long off = 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
-    if (PM) {
-      const double* src = S.mfac + (long long)C.member * P.mfac_doubles + off;
-      double* dst = smem + mloc * FAST_DOUBLES;
-      for (int k = C.g; k < FAST_DOUBLES; k += G) dst[k] = src[k];
-    } else {
-      const double* src = S.mfac + off;
-      for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
-    }
-    __syncthreads();
-  }
-  C.fslot = smem + (PM ? mloc * FAST_DOUBLES : 0);
-  C.fscan = C.fslot + crb_compact_slot_doubles(M, G);
-  fast_pin_load<M, G, Ctx>(C);
-  C.imp_amp = 0.0;
-  C.imp_dur = 0.0;
-  C.imp_local = -1;
-  const int s0 = C.g * M;
-  {
-    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-      const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
-      const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
-      C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
-    }
-  }
+  const int s0 = fast_ctx_init<M, LV, PM>(C, P, S, S.mfac, smem);
   const int n = C.n;
   double* xq = X + (long long)C.member * 2 * n + 3 * s0;
   double q[M][3], v[M][3], w[2][M][3];
@@ -500,49 +482,10 @@ __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_MID_MINBLOCKS)
 crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, double* __restrict__ X, double t0,
                     double h, int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
-  constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mloc = warp * mpw + lane / G;
-  const int member = blockIdx.x * (CRB_FAST_WARPS * mpw) + mloc;
   typedef FastCtx<M, CRB_MID_PINS, (CRB_MID_PINS > 0 ? 1 : 0), CRB_MID_PINS> Ctx;  // one solve per step: the constants of the solve stay in registers
   Ctx C;
-  C.g = lane % G;
-  C.n = P.n_free;
-  C.active = member < S.n_members;
-  C.member = C.active ? member : S.n_members - 1;
-  {
-    const long long off = 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * LVE * G;
-    if (PM) {
-      const double* src = afac + (long long)C.member * P.mfac_doubles + off;
-      double* dst = smem + mloc * FAST_DOUBLES;
-      for (int k = C.g; k < FAST_DOUBLES; k += G) dst[k] = src[k];
-    } else {
-      const double* src = afac + off;
-      for (int k = threadIdx.x; k < FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
-    }
-    __syncthreads();
-  }
-  C.fslot = smem + (PM ? mloc * FAST_DOUBLES : 0);
-  C.fscan = C.fslot + crb_compact_slot_doubles(M, G);
-  fast_pin_load<M, G, Ctx>(C);
-  const int s0 = C.g * M;
-  {
-    const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)C.member * (M * G) * 4);
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-      const double2 k0 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j));
-      const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
-      C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
-    }
-  }
-  C.imp_amp = (IMP && S.imp_amp) ? S.imp_amp[C.member] : 0.0;
-  C.imp_dur = S.imp_duration;
-  C.imp_local = -1;
-  if (IMP && S.imp_amp) {
-    const int rel = S.imp_dof - 3 * s0;
-    if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
-  }
+  const int s0 = fast_ctx_init<M, LV, PM>(C, P, S, afac, smem);
+  if (IMP) fast_ctx_impulse<M>(C, S, s0);
   const int n = C.n;
   double* xq = X + (long long)C.member * 2 * n + 3 * s0;
   double q[M][3], v[M][3], w[M][3], uc[UC ? M : 1][3];
