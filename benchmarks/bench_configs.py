@@ -71,6 +71,19 @@ def main():
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
             print(json.dumps({"config": "cfg2 x%d (nonlinear 20 el + drag), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
                               "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg1e":  # config 1 as an ensemble: linear 10-element cantilever, gravity, tip impulse, per-member E
+            B, steps = 131072, 100
+            rng = np.random.default_rng(2)
+            e = ens.config3(8, 10)
+            par = np.repeat(params(e, 1), B, axis=0)
+            par[:, :, 1] = 75e9 * np.exp(0.2 * rng.standard_normal((B, 1)))
+            beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["linear"] * 10}, ForceParams(enable_gravity_effects=True))
+            beam.create_system_func(); beam.create_input_func()
+            X = torch.zeros(B, 60, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.full((B,), 0.1, dtype=torch.float64, device=dev))
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, 2.5e-5, steps, u=imp))
+            print(json.dumps({"config": "cfg1 x%d (linear 10 el + gravity + impulse), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
+                              "element_steps_per_s": B * 10 * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg2m":  # config 2 shape with PER-MEMBER density and stiffness (no shared factor set)
             B, steps = 32768, 100
             e = ens.config2()
