@@ -276,13 +276,20 @@ def run_gpu(args):
         e2e_val = total_units / (e2e_ms * 1e-3)
         peak, which = measured_peak()
         achieved = ALG_BYTES_PER_ELEMENT_STEP * B * N * full_steps / (mean_launch * 1e-3) / 1e9
-        traffic = None
+        traffic, fp64 = None, None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
-                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+                tj = json.load(open(tf))
+                traffic = tj.get("dram_bytes_per_launch")
+                if N == tj.get("elements") and "fp64_flops_per_element_step" in tj:  # counted by ncu for this kernel shape
+                    tfl = tj["fp64_flops_per_element_step"] * B * N * full_steps / (mean_launch * 1e-3) / 1e12
+                    fp64 = {"achieved": tfl, "peak": tj["fp64_peak_tflops_measured"], "unit": "TFLOP/s",
+                            "frac": tfl / tj["fp64_peak_tflops_measured"],
+                            "flops_per_element_step": tj["fp64_flops_per_element_step"],
+                            "note": "FP64 flops counted by ncu for this kernel; peak = measured DFMA rate (benchmarks/micro/pipes.cu)"}
             except Exception:
-                traffic = None
+                traffic, fp64 = None, None
         line = {
             "metric": "beam-element RK4 steps/sec", "value": value, "unit": "element-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -294,7 +301,7 @@ def run_gpu(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": which,
+                "traffic": traffic, "peak_source": which, "fp64": fp64,
                 "note": "algorithmic 96 B per element-step; launches fuse steps so DRAM traffic is far below it; the "
                         "kernel is bound on-chip: shared-memory/shuffle (LSU) pipe 65 %, FP64 pipe 63 %, latency-limited at 8 warps/SM "
                         "(see DESIGN.md / profiles/)",
