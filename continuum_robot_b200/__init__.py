@@ -27,7 +27,7 @@ def __getattr__(name):
         from . import integrate
 
         return getattr(integrate, name)
-    if name in ("FullStateLinear", "LinearQuadraticRegulator"):
+    if name in ("FullStateLinear", "LinearQuadraticRegulator", "BatchedLinearQuadraticRegulator"):
         from . import control
 
         return getattr(control, name)

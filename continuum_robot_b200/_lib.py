@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 103
+CRB_VERSION = 104
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -65,6 +65,7 @@ class CrbSystem(C.Structure):
         ("force_staged", C.c_int32),
         ("shared_op", C.c_void_p),
         ("shared_op_doubles", C.c_int64),
+        ("gain_stride", C.c_int64),
     ]
 
 
@@ -106,6 +107,12 @@ _SIGNATURES = {
                                         C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p]),
     "crb_dense_matrices": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p,
                                      C.c_void_p, C.c_void_p]),
+    "crb_dense_matrices_batched": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crb_lqr_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "crb_lqr_gains": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_size_t, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -7,6 +7,9 @@
     (absent in this image); the CARE solution is unique, so ``scipy.linalg.solve_continuous_are``
     gives the same gain to solver tolerance.  One-off host synthesis is outside the hot path
     (SURVEY section 2 row 7).
+  * ``BatchedLinearQuadraticRegulator`` -- the same contract for an ENSEMBLE of designs, on the device
+    (crb_lqr_gains): per-member A / B build and Riccati solve, one thread block
+    per design; the gains feed the rollout as ``FullStateLinear(K[B,n,2n])``.
 """
 
 from __future__ import annotations
@@ -19,7 +22,9 @@ from .abstractions import AbstractInputHandler
 class FullStateLinear(AbstractInputHandler):
     def __init__(self, gain_matrix, enabled: bool = True, reference=None):
         g = gain_matrix
-        if getattr(g, "ndim", None) != 2:
+        # 2-D: one gain for the ensemble (the reference's contract); 3-D [B,n,2n]: one gain per member
+        # (BatchedLinearQuadraticRegulator)
+        if getattr(g, "ndim", None) not in (2, 3):
             raise ValueError("Gain matrix must be a 2D array.")
         self.gain_matrix = g
         self.enabled = enabled
@@ -36,8 +41,10 @@ class FullStateLinear(AbstractInputHandler):
             K = torch.as_tensor(np.asarray(K, dtype=np.float64), device=x.device)
         if x.shape[-1] != r.shape[-1]:
             raise ValueError("State vector and refrence vector must have the same length.")
-        if K.shape[1] != x.shape[-1]:
+        if K.shape[-1] != x.shape[-1]:
             raise ValueError("Gain matrix column dimension must match state vector length.")
+        if K.ndim == 3:
+            return torch.einsum("bij,bj->bi", K, (r - x).expand(K.shape[0], -1))
         return (r - x) @ K.T
 
     def is_enabled(self) -> bool:
@@ -105,3 +112,83 @@ class LinearQuadraticRegulator:
 
     def get_K(self) -> np.ndarray:
         return self.compute_gain_matrix()
+
+
+class BatchedLinearQuadraticRegulator:
+    """``LinearQuadraticRegulator`` (control/linear_quadratic_regulator.py:5-200) for B designs at once.
+
+    ``K_beam`` / ``M_beam``: CUDA FP64 tensors ``[B,n,n]`` or ``[n,n]`` (shared); ``Q [2n,2n]``, ``R [n,n]`` shared.
+    ``compute_gain_matrix()`` returns ``K[B,n,2n]`` on the device and raises ``ValueError`` with the reference's
+    messages if any member has no stabilising solution (:182-189).  There is no CPU path.
+    """
+
+    STATUS_TEXT = {1: "Mass matrix is singular and cannot be inverted",
+                   2: "Failed to solve LQR problem: no stabilising Riccati solution",
+                   3: "LQR solution results in unstable closed-loop system"}
+
+    def __init__(self, K_beam, M_beam, Q, R, refine_passes: int = 1):
+        import torch
+
+        for name, a in (("K_beam", K_beam), ("M_beam", M_beam), ("Q", Q), ("R", R)):
+            if not isinstance(a, torch.Tensor) or not a.is_cuda:
+                raise TypeError(f"{name} must be a CUDA torch tensor (no CPU path)")
+            if a.ndim < 2 or a.shape[-1] != a.shape[-2]:
+                raise ValueError(f"{name} must be a square matrix")
+        if K_beam.shape[-1] != M_beam.shape[-1]:
+            raise ValueError("K_beam and M_beam must have the same dimensions")
+        n = int(M_beam.shape[-1])
+        if Q.ndim != 2 or Q.shape[0] != 2 * n:
+            raise ValueError(f"Q matrix dimension {Q.shape[0]} must match state dimension {2 * n}")
+        if R.ndim != 2 or R.shape[0] != n:
+            raise ValueError(f"R matrix dimension {R.shape[0]} must match input dimension {n}")
+        f64 = lambda a: a.to(dtype=torch.float64).contiguous()
+        self.K_beam = f64(K_beam if K_beam.ndim == 3 else K_beam[None])
+        self.M_beam = f64(M_beam if M_beam.ndim == 3 else M_beam[None])
+        self.Q, self.R = f64(Q), f64(R)
+        self.n = n
+        self.B = max(self.K_beam.shape[0], self.M_beam.shape[0])
+        for name, a in (("K_beam", self.K_beam), ("M_beam", self.M_beam)):
+            if a.shape[0] not in (1, self.B):
+                raise ValueError(f"{name} has {a.shape[0]} members, expected 1 or {self.B}")
+        self.refine_passes = int(refine_passes)
+        self._K = self._S = self.status = self.residual = None
+
+    def compute_gain_matrix(self):
+        if self._K is not None:
+            return self._K
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        lib = _lib.load()
+        dev, n, B = self.M_beam.device, self.n, self.B
+        need = C.c_size_t(0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.crb_lqr_workspace_bytes(n, B, C.byref(need)), ValueError)
+            ws = torch.empty((need.value + 7) // 8, dtype=torch.float64, device=dev)
+            gain = torch.empty((B, n, 2 * n), dtype=torch.float64, device=dev)
+            S = torch.empty((B, 2 * n, 2 * n), dtype=torch.float64, device=dev)
+            resid = torch.empty(B, dtype=torch.float64, device=dev)
+            status = torch.empty(B, dtype=torch.int32, device=dev)
+            rc = lib.crb_lqr_gains(
+                n, B, self.M_beam.data_ptr(), int(self.M_beam.shape[0] == 1), self.K_beam.data_ptr(),
+                int(self.K_beam.shape[0] == 1), self.Q.data_ptr(), self.R.data_ptr(), self.refine_passes,
+                gain.data_ptr(), S.data_ptr(), resid.data_ptr(), status.data_ptr(), ws.data_ptr(), need.value,
+                torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, ValueError)
+            bad = torch.nonzero(status).flatten()
+        self.status, self.residual = status, resid
+        if bad.numel():
+            i = int(bad[0])
+            raise ValueError(f"{self.STATUS_TEXT[int(status[i])]} (member {i}; {bad.numel()} of {B} members failed)")
+        self._K, self._S = gain, S
+        return gain
+
+    def get_K(self):
+        return self.compute_gain_matrix()
+
+    def get_S(self):
+        self.compute_gain_matrix()
+        return self._S

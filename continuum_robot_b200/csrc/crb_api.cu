@@ -201,6 +201,11 @@ static int check_system(const char* who, const crb_plan_t* plan, const crb_syste
     return fail(CRB_E_ARG, "%s: slot-space gravity needs grav[] and a contiguous plan", who);
   if (sys->grav_mode == 2 && !sys->seg_half_mass)
     return fail(CRB_E_ARG, "%s: generic gravity needs seg_half_mass[]", who);
+  if (sys->gain_stride != 0 && sys->gain_stride != 2ll * plan->n_free * plan->n_free)
+    return fail(CRB_E_ARG, "%s: gain_stride must be 0 (shared gain) or n*2n = %lld, got %lld", who,
+                2ll * plan->n_free * plan->n_free, (long long)sys->gain_stride);
+  if (sys->gain_stride != 0 && (sys->gain_frag || sys->shared_op))
+    return fail(CRB_E_ARG, "%s: per-member gains (gain_stride != 0) exclude gain_frag / shared_op", who);
   if (sys->imp_amp && (sys->imp_dof < 0 || sys->imp_dof >= plan->n_free))
     return fail(CRB_E_ARG, "%s: imp_dof %d outside [0,%d)", who, sys->imp_dof, plan->n_free);
   return 0;

@@ -35,7 +35,7 @@ inline KPlan kplan_of(const crb_plan_t* p) {
 inline SmemLayout smem_layout(const crb_plan_t* plan, const crb_system_t* sys, size_t* bytes) {
   SmemLayout SL;
   SL.mfac_doubles = sys->mass_shared ? 2 * CRB_SLOT_PAIRS * plan->p + 2 * CRB_SCAN_PAIRS * (plan->levels > 0 ? plan->levels : 1) * plan->g : 0;
-  SL.scratch_doubles = ((sys->gain && !(sys->gain_frag && plan->g == 4)) || sys->grav_mode == 2)
+  SL.scratch_doubles = ((sys->gain && !(sys->gain_frag && plan->g == 4 && sys->gain_stride == 0)) || sys->grav_mode == 2)
                            ? 2 * plan->n_free + 2 * plan->n_elements : 0;  // reduced state + per-segment gravity
   const int mpb = CRB_WARPS_PER_BLOCK * (32 / plan->g);
   *bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpb);
@@ -88,7 +88,7 @@ inline unsigned crb_needed_features(const crb_plan_t* plan, const crb_system_t* 
   if (s->grav_mode == 2) f |= CRB_F_GRAVG;
   if (plan->has_mask) f |= CRB_F_MASK;
   if (s->u_const || s->imp_amp || s->f_ext) f |= CRB_F_INPUT;
-  if (s->gain) f |= (s->gain_frag && plan->g == 4) ? CRB_F_GAINM : CRB_F_GAINS;
+  if (s->gain) f |= (s->gain_frag && plan->g == 4 && s->gain_stride == 0) ? CRB_F_GAINM : CRB_F_GAINS;
   return f;
 }
 inline unsigned crb_pick_profile(unsigned need) {

@@ -1,0 +1,471 @@
+// crb_lqr.cu -- batched LQR synthesis on the device: per-member A / B build and the
+// continuous-time algebraic Riccati equation, one thread block per design.
+//
+// Reference behaviour (control/linear_quadratic_regulator.py:84-191, examples/lqr_control.py:46-84):
+//   A = [[0, I], [-M^-1 K, 0]],  B = [[0], [M^-1]],  K_gain, S, E = control.lqr(A, B, Q, R),
+//   ValueError when the closed loop A - B K_gain has an eigenvalue with Re >= 0.
+// control.lqr (python-control / slycot) is a third-party dependency that is absent from this image; its result is
+// the unique stabilising solution S of  A^T S + S A - S B R^-1 B^T S + Q = 0  and  K_gain = R^-1 B^T S.
+//
+// Method (chosen for the GPU: only inversions and products of small dense matrices in shared memory):
+//   * sign(H) of the Hamiltonian H = [[A, -G], [-Q, -A^T]], G = B R^-1 B^T, by the Newton iteration
+//     Z <- (c Z + (c Z)^-1) / 2 with determinant scaling c = |det Z|^(-1/D) (Roberts 1980; Byers 1987);
+//   * the stable invariant subspace is the range of (I - sign H) / 2, whose first block column gives
+//     S = W21 (W11 - I)^-1;
+//   * iterative refinement: with the residual Res = A^T S + S A - S G S + Q, the correction dS solves the
+//     Riccati equation of (A - G S, G, Res) EXACTLY, so the same solver is applied to it (`refine_passes`
+//     times).  One pass brings the gain from ~1e-6 to ~2e-10 of the Newton-Kleinman-refined solution
+//     (SciPy's own solve_continuous_are is at ~1.5e-8 on these beams);
+//   * closed-loop check: sign(A - G S) = -I  <=>  every closed-loop eigenvalue has Re < 0.
+// All inversions are Gauss-Jordan with partial pivoting, in place in shared memory.
+#include "crb_internal.h"
+
+#define CRB_LQR_THREADS 256
+#define CRB_LQR_MAX_ITERS 80
+
+namespace {
+
+struct LqrArgs {
+  int n, n_members;
+  const double* Mb;
+  const double* Kb;
+  int m_shared, k_shared;
+  const double* Q;
+  const double* R;
+  int passes;
+  double* gain;
+  double* S_out;
+  double* residual;
+  int* status;
+  double* ws;
+  long long ws_stride;  // doubles per block
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // red may still be read from a previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < CRB_LQR_THREADS / 32; ++w) s += red[w];
+  return s;
+}
+
+// In-place inverse of the m x m row-major matrix `a` (shared memory) by Gauss-Jordan elimination with partial
+// pivoting.  Returns sum log|pivot| = log|det a|; a zero pivot column sets *singular (block-uniform).
+__device__ double gj_inverse(double* a, int m, double* col, double* prow, int* piv, double* red, bool* singular) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double logdet = 0.0;
+  *singular = false;
+  for (int p = 0; p < m; ++p) {
+    if (warp == 0) {  // pivot search in column p
+      double best = -1.0;
+      int bi = p;
+      for (int i = p + lane; i < m; i += 32) {
+        const double v = fabs(a[i * m + p]);
+        if (v > best) { best = v; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { piv[p] = bi; red[16] = best; }
+    }
+    __syncthreads();
+    const int r = piv[p];
+    const double best = red[16];
+    if (!(best > 0.0) || !isfinite(best)) { *singular = true; return logdet; }
+    if (r != p)
+      for (int j = tid; j < m; j += CRB_LQR_THREADS) {
+        const double x = a[p * m + j];
+        a[p * m + j] = a[r * m + j];
+        a[r * m + j] = x;
+      }
+    __syncthreads();
+    const double pv = a[p * m + p];
+    for (int i = tid; i < m; i += CRB_LQR_THREADS) {
+      col[i] = a[i * m + p];
+      prow[i] = (i == p) ? 1.0 : a[p * m + i];
+    }
+    __syncthreads();
+    const double ipv = 1.0 / pv;
+    for (int i = warp; i < m; i += CRB_LQR_THREADS / 32) {
+      const double f = -col[i] * ipv;
+      for (int j = lane; j < m; j += 32) {
+        double nv;
+        if (i == p) nv = prow[j] * ipv;
+        else nv = fma(f, prow[j], (j == p) ? 0.0 : a[i * m + j]);
+        a[i * m + j] = nv;
+      }
+    }
+    logdet += log(fabs(pv));
+    // the next pivot search reads column p + 1 of the updated matrix
+    __syncthreads();
+  }
+  for (int p = m - 1; p >= 0; --p) {  // undo the row exchanges as column exchanges, in reverse
+    const int r = piv[p];
+    if (r != p) {
+      for (int i = tid; i < m; i += CRB_LQR_THREADS) {
+        const double x = a[i * m + p];
+        a[i * m + p] = a[i * m + r];
+        a[i * m + r] = x;
+      }
+      __syncthreads();
+    }
+  }
+  return logdet;
+}
+
+// Z (global, m x m) <- sign(Z).  Returns the number of iterations, or -1 (singular iterate / no convergence).
+__device__ int sign_iteration(double* Z, int m, double* sm, double* col, double* prow, int* piv, double* red) {
+  const int tid = threadIdx.x;
+  double dprev = 1e300;
+  bool scaling = true;
+  for (int it = 1; it <= CRB_LQR_MAX_ITERS; ++it) {
+    for (int k = tid; k < m * m; k += CRB_LQR_THREADS) sm[k] = Z[k];
+    __syncthreads();
+    bool singular;
+    const double logdet = gj_inverse(sm, m, col, prow, piv, red, &singular);
+    if (singular) return -1;
+    const double c = scaling ? exp(-logdet / m) : 1.0, ic = 1.0 / c;
+    double dd = 0.0, nn = 0.0;
+    for (int k = tid; k < m * m; k += CRB_LQR_THREADS) {
+      const double z = Z[k];
+      const double zn = 0.5 * fma(c, z, ic * sm[k]);
+      const double e = zn - z;
+      dd = fma(e, e, dd);
+      nn = fma(zn, zn, nn);
+      Z[k] = zn;
+    }
+    dd = block_sum(dd, red);
+    nn = block_sum(nn, red);
+    if (!isfinite(nn) || !(nn > 0.0)) return -1;
+    const double d = sqrt(dd / nn);
+    if (d < 1e-14) return it;
+    if (dprev < 1e-6 && d >= dprev) return it;  // quadratic phase over: rounding level reached
+    if (d < 1e-2) scaling = false;
+    dprev = d;
+  }
+  return -1;
+}
+
+// C(i,j) = sum_k A(i,k) B(k,j), i < m, j < n (accessors are lambdas; C is written through `store`)
+template <typename FA, typename FB, typename FS>
+__device__ __forceinline__ void mat_mul(int m, int n, int kk, FA a, FB b, FS store) {
+  for (int idx = threadIdx.x; idx < m * n; idx += CRB_LQR_THREADS) {
+    const int i = idx / n, j = idx - i * n;
+    double acc = 0.0;
+    for (int k = 0; k < kk; ++k) acc = fma(a(i, k), b(k, j), acc);
+    store(i, j, acc);
+  }
+}
+
+// Res = A^T X + X A - X G X + Q (n2 x n2, all dense); T, T2 scratch
+__device__ void riccati_residual(int n2, const double* A, const double* G, const double* Q, const double* X, double* T,
+                                 double* T2, double* Res) {
+  mat_mul(n2, n2, n2, [&](int i, int k) { return X[i * n2 + k]; }, [&](int k, int j) { return A[k * n2 + j]; },
+          [&](int i, int j, double v) { T[i * n2 + j] = v; });
+  mat_mul(n2, n2, n2, [&](int i, int k) { return G[i * n2 + k]; }, [&](int k, int j) { return X[k * n2 + j]; },
+          [&](int i, int j, double v) { T2[i * n2 + j] = v; });
+  __syncthreads();
+  mat_mul(n2, n2, n2, [&](int i, int k) { return X[i * n2 + k]; }, [&](int k, int j) { return T2[k * n2 + j]; },
+          [&](int i, int j, double v) { Res[i * n2 + j] = T[i * n2 + j] + T[j * n2 + i] - v + Q[i * n2 + j]; });
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(CRB_LQR_THREADS) crb_lqr_kernel(LqrArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = a.n, n2 = 2 * n, D = 4 * n, tid = threadIdx.x;
+  double* sm = smem;           // D x D
+  double* col = sm + D * D;    // D
+  double* prow = col + D;      // D
+  double* red = prow + D;      // 32
+  int* piv = reinterpret_cast<int*>(red + 32);  // D
+  double* ws = a.ws + (long long)blockIdx.x * a.ws_stride;
+  double* Z = ws;                 // D^2
+  double* A = Z + D * D;          // n2^2 each
+  double* G = A + n2 * n2;
+  double* X = G + n2 * n2;
+  double* Ac = X + n2 * n2;
+  double* Qc = Ac + n2 * n2;
+  double* T = Qc + n2 * n2;
+  double* T2 = T + n2 * n2;
+  double* Minv = T2 + n2 * n2;    // n^2 each
+  double* Rinv = Minv + n * n;
+  double* tmp = Rinv + n * n;
+  bool singular;
+
+  // R^-1 once per block
+  for (int k = tid; k < n * n; k += CRB_LQR_THREADS) sm[k] = a.R[k];
+  __syncthreads();
+  gj_inverse(sm, n, col, prow, piv, red, &singular);
+  const bool r_singular = singular;
+  for (int k = tid; k < n * n; k += CRB_LQR_THREADS) Rinv[k] = sm[k];
+  __syncthreads();
+
+  for (int member = blockIdx.x; member < a.n_members; member += gridDim.x) {
+    const double* Mb = a.Mb + (a.m_shared ? 0ll : (long long)member * n * n);
+    const double* Kb = a.Kb + (a.k_shared ? 0ll : (long long)member * n * n);
+    int status = 0;
+    double resid = 0.0;
+    // M^-1 (linear_quadratic_regulator.py:100-104)
+    __syncthreads();
+    for (int k = tid; k < n * n; k += CRB_LQR_THREADS) sm[k] = Mb[k];
+    __syncthreads();
+    gj_inverse(sm, n, col, prow, piv, red, &singular);
+    if (singular || r_singular) status = 1;
+    for (int k = tid; k < n * n; k += CRB_LQR_THREADS) Minv[k] = sm[k];
+    __syncthreads();
+    if (status == 0) {
+      // A = [[0, I], [-M^-1 K, 0]]   (:84-118);   G = B R^-1 B^T = [[0, 0], [0, M^-1 R^-1 M^-T]]   (:120-146)
+      for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
+        const int i = k / n2, j = k - i * n2;
+        A[k] = (i < n && j == i + n) ? 1.0 : 0.0;
+        G[k] = 0.0;
+        X[k] = 0.0;
+        Qc[k] = a.Q[k];
+      }
+      __syncthreads();
+      mat_mul(n, n, n, [&](int i, int k) { return Minv[i * n + k]; }, [&](int k, int j) { return Kb[k * n + j]; },
+              [&](int i, int j, double v) { A[(n + i) * n2 + j] = -v; });
+      mat_mul(n, n, n, [&](int i, int k) { return Minv[i * n + k]; }, [&](int k, int j) { return Rinv[k * n + j]; },
+              [&](int i, int j, double v) { tmp[i * n + j] = v; });
+      __syncthreads();
+      mat_mul(n, n, n, [&](int i, int k) { return tmp[i * n + k]; }, [&](int k, int j) { return Minv[j * n + k]; },
+              [&](int i, int j, double v) { G[(n + i) * n2 + n + j] = v; });
+      __syncthreads();
+      for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) Ac[k] = A[k];
+      __syncthreads();
+
+      for (int pass = 0; pass <= a.passes && status == 0; ++pass) {
+        // H = [[Ac, -G], [-Qc, -Ac^T]]
+        for (int k = tid; k < D * D; k += CRB_LQR_THREADS) {
+          const int i = k / D, j = k - i * D;
+          double v;
+          if (i < n2) v = (j < n2) ? Ac[i * n2 + j] : -G[i * n2 + (j - n2)];
+          else v = (j < n2) ? -Qc[(i - n2) * n2 + j] : -Ac[(j - n2) * n2 + (i - n2)];
+          Z[k] = v;
+        }
+        __syncthreads();
+        if (sign_iteration(Z, D, sm, col, prow, piv, red) < 0) { status = 2; break; }
+        __syncthreads();
+        // dS = W21 (W11 - I)^-1
+        for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
+          const int i = k / n2, j = k - i * n2;
+          sm[k] = Z[i * D + j] - (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        gj_inverse(sm, n2, col, prow, piv, red, &singular);
+        if (singular) { status = 2; break; }
+        mat_mul(n2, n2, n2, [&](int i, int k) { return Z[(n2 + i) * D + k]; }, [&](int k, int j) { return sm[k * n2 + j]; },
+                [&](int i, int j, double v) { T[i * n2 + j] = v; });
+        __syncthreads();
+        for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
+          const int i = k / n2, j = k - i * n2;
+          X[k] += 0.5 * (T[k] + T[j * n2 + i]);
+        }
+        __syncthreads();
+        // closed loop and residual of the updated solution: next pass solves for the correction
+        mat_mul(n2, n2, n2, [&](int i, int k) { return G[i * n2 + k]; }, [&](int k, int j) { return X[k * n2 + j]; },
+                [&](int i, int j, double v) { Ac[i * n2 + j] = A[i * n2 + j] - v; });
+        __syncthreads();
+        riccati_residual(n2, A, G, a.Q, X, T, T2, Qc);
+      }
+    }
+    if (status == 0) {
+      // relative residual ||Res||_F / ||Q||_F of the returned solution
+      double rr = 0.0, qq = 0.0;
+      for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
+        rr = fma(Qc[k], Qc[k], rr);
+        qq = fma(a.Q[k], a.Q[k], qq);
+      }
+      rr = block_sum(rr, red);
+      qq = block_sum(qq, red);
+      resid = sqrt(rr / qq);
+      // closed-loop eigenvalues (:185-189): sign(A - B K) must be -I
+      for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) Z[k] = Ac[k];
+      __syncthreads();
+      if (sign_iteration(Z, n2, sm, col, prow, piv, red) < 0) {
+        status = 3;
+      } else {
+        double tr = 0.0;
+        for (int i = tid; i < n2; i += CRB_LQR_THREADS) tr += Z[i * n2 + i];
+        tr = block_sum(tr, red);
+        if (fabs(tr + n2) > 0.5) status = 3;
+      }
+      // K_gain = R^-1 B^T S = R^-1 M^-T S[n:, :]
+      mat_mul(n, n2, n, [&](int i, int k) { return Minv[k * n + i]; }, [&](int k, int j) { return X[(n + k) * n2 + j]; },
+              [&](int i, int j, double v) { T[i * n2 + j] = v; });
+      __syncthreads();
+      double* gout = a.gain + (long long)member * n * n2;
+      mat_mul(n, n2, n, [&](int i, int k) { return Rinv[i * n + k]; }, [&](int k, int j) { return T[k * n2 + j]; },
+              [&](int i, int j, double v) { gout[i * n2 + j] = v; });
+      if (a.S_out)
+        for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) a.S_out[(long long)member * n2 * n2 + k] = X[k];
+    } else {
+      const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+      for (int k = tid; k < n * n2; k += CRB_LQR_THREADS) a.gain[(long long)member * n * n2 + k] = qnan;
+      if (a.S_out)
+        for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) a.S_out[(long long)member * n2 * n2 + k] = qnan;
+      resid = qnan;
+    }
+    if (tid == 0) {
+      a.status[member] = status;
+      if (a.residual) a.residual[member] = resid;
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t lqr_smem_bytes(int n) {
+  const size_t D = 4 * (size_t)n;
+  return sizeof(double) * (D * D + 2 * D + 32) + sizeof(int) * D;
+}
+inline long long lqr_ws_doubles(int n) { return 16ll * n * n + 7 * 4ll * n * n + 3ll * n * n; }
+
+int lqr_grid(int n, int n_members, int* out) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_lqr: %s", cudaGetErrorString(e));
+  if (int rc = set_smem(crb_lqr_kernel, lqr_smem_bytes(n), "crb_lqr_gains")) return rc;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crb_lqr_kernel, CRB_LQR_THREADS, lqr_smem_bytes(n));
+  if (e != cudaSuccess || per_sm < 1) return crb_fail(CRB_E_CUDA, "crb_lqr: occupancy query failed (%s)", cudaGetErrorString(e));
+  const long long cap = (long long)sms * per_sm;
+  *out = (int)(n_members < cap ? n_members : cap);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched dense M, K (device): one thread per (set, element)
+// ------------------------------------------------------------------------------------------
+struct RedMap { int r[3 * (CRB_LQR_MAX_ELEMENTS + 1)]; };
+
+__global__ void crb_dense_batched_kernel(int N, int n, int n_sets, const double* __restrict__ params, RedMap map,
+                                         double* __restrict__ Mo, double* __restrict__ Ko) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n_sets * N) return;
+  const int set = (int)(gid / N), e = (int)(gid - (long long)set * N);
+  const double* q = params + gid * CRB_NPARAM;
+  const double L = q[CRB_P_LENGTH], mu = q[CRB_P_RHO] * q[CRB_P_AREA] * L / 420;
+  const double EI = q[CRB_P_E] * q[CRB_P_I], EA = q[CRB_P_E] * q[CRB_P_AREA];
+  const double ax = EA / L, c1 = EI / L, c2 = EI / (L * L), c3 = EI / (L * L * L);
+  const double L2 = L * L;
+  // models/segments.py:32-78 (DOF order u1, w1, phi1, u2, w2, phi2)
+  const double me[6][6] = {{140, 0, 0, 70, 0, 0},
+                           {0, 156, -22 * L, 0, 54, 13 * L},
+                           {0, -22 * L, 4 * L2, 0, -13 * L, -3 * L2},
+                           {70, 0, 0, 140, 0, 0},
+                           {0, 54, -13 * L, 0, 156, 22 * L},
+                           {0, 13 * L, -3 * L2, 0, 22 * L, 4 * L2}};
+  const double ke[6][6] = {{ax, 0, 0, -ax, 0, 0},
+                           {0, 12 * c3, -6 * c2, 0, -12 * c3, -6 * c2},
+                           {0, -6 * c2, 4 * c1, 0, 6 * c2, 2 * c1},
+                           {-ax, 0, 0, ax, 0, 0},
+                           {0, -12 * c3, 6 * c2, 0, 12 * c3, 6 * c2},
+                           {0, -6 * c2, 2 * c1, 0, 6 * c2, 4 * c1}};
+  double* Ms = Mo + (long long)set * n * n;
+  double* Ks = Ko ? Ko + (long long)set * n * n : nullptr;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      const int ri = map.r[3 * e + i], rj = map.r[3 * e + j];
+      if (ri < 0 || rj < 0) continue;
+      // neighbouring elements add into the shared node block: two addends per entry at most, so the
+      // sum does not depend on the order of the atomics
+      atomicAdd(Ms + (long long)ri * n + rj, me[i][j] * mu);
+      if (Ks) atomicAdd(Ks + (long long)ri * n + rj, ke[i][j]);
+    }
+}
+
+}  // namespace
+
+extern "C" int crb_dense_matrices_batched(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
+                                          const uint8_t* elem_type_host, const uint8_t* bc_host, double* M_out,
+                                          double* K_out, void* stream) {
+  if (!plan || !params || !elem_type_host || !bc_host || !M_out)
+    return crb_fail(CRB_E_ARG, "crb_dense_matrices_batched: null argument");
+  if (n_param_sets < 1) return crb_fail(CRB_E_ARG, "crb_dense_matrices_batched: n_param_sets must be positive");
+  const int N = plan->n_elements, n = plan->n_free;
+  if (N > CRB_LQR_MAX_ELEMENTS)
+    return crb_fail(CRB_E_LIMIT, "crb_dense_matrices_batched: at most %d elements (got %d)", CRB_LQR_MAX_ELEMENTS, N);
+  if (K_out)
+    for (int e = 0; e < N; ++e)
+      if (elem_type_host[e] != CRB_ELEM_LINEAR)
+        return crb_fail(CRB_E_ARG, "Cannot extract stiffness matrix from beam with nonlinear segments. Segment %d is nonlinear.", e);
+  RedMap map;
+  int r = 0;
+  for (int node = 0; node <= N; ++node)
+    for (int d = 0; d < 3; ++d) {
+      const bool c = bc_host[node] == CRB_BC_FIXED || (bc_host[node] == CRB_BC_PINNED && d < 2);
+      map.r[3 * node + d] = c ? -1 : r++;
+    }
+  if (r != n) return crb_fail(CRB_E_ARG, "crb_dense_matrices_batched: plan / bc mismatch (%d vs %d free DOFs)", r, n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = sizeof(double) * (size_t)n_param_sets * n * n;
+  cudaError_t e = cudaMemsetAsync(M_out, 0, bytes, st);
+  if (e == cudaSuccess && K_out) e = cudaMemsetAsync(K_out, 0, bytes, st);
+  if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_dense_matrices_batched: %s", cudaGetErrorString(e));
+  const long long work = (long long)n_param_sets * N;
+  crb_dense_batched_kernel<<<(unsigned)((work + 127) / 128), 128, 0, st>>>(N, n, n_param_sets, params, map, M_out, K_out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_dense_matrices_batched: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int lqr_check_n(int32_t n, const char* who) {
+  if (n < 1) return crb_fail(CRB_E_ARG, "%s: n must be positive", who);
+  if (lqr_smem_bytes(n) > 227 * 1024)
+    return crb_fail(CRB_E_LIMIT, "%s: n = %d free DOFs need %zu bytes of shared memory for the %d x %d Hamiltonian (> 227 KB; n <= 42)",
+                    who, n, lqr_smem_bytes(n), 4 * n, 4 * n);
+  return 0;
+}
+
+extern "C" int crb_lqr_workspace_bytes(int32_t n, int32_t n_members, size_t* out) {
+  if (!out) return crb_fail(CRB_E_ARG, "crb_lqr_workspace_bytes: null out");
+  if (int rc = lqr_check_n(n, "crb_lqr_workspace_bytes")) return rc;
+  if (n_members < 1) return crb_fail(CRB_E_ARG, "crb_lqr_workspace_bytes: n_members must be positive");
+  int grid = 0;
+  if (int rc = lqr_grid(n, n_members, &grid)) return rc;
+  *out = sizeof(double) * (size_t)lqr_ws_doubles(n) * (size_t)grid;
+  return 0;
+}
+
+extern "C" int crb_lqr_gains(int32_t n, int32_t n_members, const double* M_beam, int32_t m_shared, const double* K_beam,
+                             int32_t k_shared, const double* Q, const double* R, int32_t refine_passes, double* gain_out,
+                             double* S_out, double* residual_out, int32_t* status_out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!M_beam || !K_beam || !Q || !R || !gain_out || !status_out || !workspace)
+    return crb_fail(CRB_E_ARG, "crb_lqr_gains: null argument");
+  if (int rc = lqr_check_n(n, "crb_lqr_gains")) return rc;
+  if (n_members < 1) return crb_fail(CRB_E_ARG, "crb_lqr_gains: n_members must be positive");
+  if (refine_passes < 0 || refine_passes > 8) return crb_fail(CRB_E_ARG, "crb_lqr_gains: refine_passes must be in [0, 8]");
+  int grid = 0;
+  if (int rc = lqr_grid(n, n_members, &grid)) return rc;
+  const size_t need = sizeof(double) * (size_t)lqr_ws_doubles(n) * (size_t)grid;
+  if (workspace_bytes < need)
+    return crb_fail(CRB_E_ARG, "crb_lqr_gains: workspace of %zu bytes, %zu needed (crb_lqr_workspace_bytes)", workspace_bytes, need);
+  LqrArgs a;
+  a.n = n;
+  a.n_members = n_members;
+  a.Mb = M_beam;
+  a.Kb = K_beam;
+  a.m_shared = m_shared;
+  a.k_shared = k_shared;
+  a.Q = Q;
+  a.R = R;
+  a.passes = refine_passes;
+  a.gain = gain_out;
+  a.S_out = S_out;
+  a.residual = residual_out;
+  a.status = status_out;
+  a.ws = static_cast<double*>(workspace);
+  a.ws_stride = lqr_ws_doubles(n);
+  crb_lqr_kernel<<<grid, CRB_LQR_THREADS, lqr_smem_bytes(n), static_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_lqr_gains: %s", cudaGetErrorString(e));
+  return 0;
+}

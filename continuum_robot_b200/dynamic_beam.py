@@ -391,6 +391,23 @@ class BatchedDynamicEulerBernoulliBeam:
         if self.force_params.enable_gravity_effects:
             self.force_registry.register(GravityForce(self, self.force_params.get_gravity_vector(), True))
 
+    def dense_matrices(self, want_stiffness: bool = True):
+        """BC-reduced dense ``M[Bp,n,n]`` and ``K[Bp,n,n]`` of every parameter set, built on the device
+        (crb_dense_matrices_batched): the per-member A / B build of an LQR design ensemble
+        (``beam.beam_model.get_mass_matrix()`` / ``get_stiffness_matrix()`` of the reference, for all members
+        at once; euler_bernoulli_beam.py:357-361, 422-511).  ``Bp`` = 1 for one shared design."""
+        torch = _torch()
+        n, Bp = self.n_free, int(self._params_np.shape[0])
+        par = torch.from_numpy(np.ascontiguousarray(self._params_np)).to(self.device)
+        M = torch.empty((Bp, n, n), dtype=torch.float64, device=self.device)
+        K = torch.empty((Bp, n, n), dtype=torch.float64, device=self.device) if want_stiffness else None
+        with torch.cuda.device(self.device):
+            rc = _lib.load().crb_dense_matrices_batched(
+                C.byref(self._plan), par.data_ptr(), Bp, self._etype.tobytes(), self._bc.tobytes(),
+                M.data_ptr(), K.data_ptr() if want_stiffness else None, self._stream())
+        _lib.check(rc, ValueError)
+        return M, K
+
     def shifted_factors(self, shift: float):
         """(afac, shared): block-LDL^T factors of M + shift K on the device (crb_assemble_shifted), one set if
         mass and stiffness are shared by all members, else one per member; cached per shift."""
@@ -521,6 +538,18 @@ class BatchedDynamicEulerBernoulliBeam:
         if gain is not None:
             if not isinstance(gain, torch.Tensor):
                 gain = torch.as_tensor(np.asarray(gain, dtype=np.float64))
+            per_member = gain.ndim == 3
+            if per_member:  # one design-specific gain per member (BatchedLinearQuadraticRegulator / crb_lqr_gains)
+                if tuple(gain.shape) != (B, n, 2 * n):
+                    raise ValueError(f"Per-member gains must have shape ({B}, {n}, {2 * n}), got {tuple(gain.shape)}")
+                gdev = dev64(gain, (B, n, 2 * n), "gain")
+                s.gain = gdev.data_ptr() + 8 * lo * n * 2 * n
+                s.gain_stride = n * 2 * n
+                if ref is not None:
+                    if not isinstance(ref, torch.Tensor):
+                        ref = torch.as_tensor(np.asarray(ref, dtype=np.float64))
+                    s.ref = dev64(ref.reshape(-1), (2 * n,), "reference").data_ptr()
+                return s, keep
             if gain.ndim != 2 or tuple(gain.shape) != (n, 2 * n):
                 raise ValueError(f"Gain matrix must have shape ({n}, {2 * n}), got {tuple(gain.shape)}")
             gdev = dev64(gain, (n, 2 * n), "gain")

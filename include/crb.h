@@ -33,9 +33,10 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 103
+#define CRB_VERSION 104
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
+#define CRB_LQR_MAX_ELEMENTS 128 /* crb_dense_matrices_batched: elements per beam */
 
 /* element types: models/abstractions.py:9-13 (ElementType) */
 #define CRB_ELEM_LINEAR 0
@@ -96,7 +97,7 @@ typedef struct crb_system_t {
   int32_t imp_dof;          /* reduced position index (examples use n-2: tip w) */
   double imp_duration;
   /* FullStateLinear (control/full_state_linear.py:58): u_c = gain @ (ref - x) */
-  const double* gain;       /* [n, 2n] shared gain, or NULL */
+  const double* gain;       /* [n, 2n] shared gain (or [B, n, 2n], see gain_stride), or NULL */
   const double* ref;        /* [2n] shared reference, NULL = 0 */
   const double* gain_frag;  /* [6m][(3m+1)/2][32] gain re-tiled as FP64 mma B-fragments (crb_gain_fragments),
                                used when plan.g == 4 (8 members per warp = the 8 rows of mma.m8n8k4); else NULL */
@@ -112,6 +113,10 @@ typedef struct crb_system_t {
    * gravity vector / imp_dof are the ones the blob was built with. */
   const double* shared_op;
   int64_t shared_op_doubles;
+  /* doubles between the gains of consecutive members: 0 = `gain` is ONE [n,2n] matrix shared by the ensemble,
+   * n*2n = `gain` is [B,n,2n], one design-specific gain per member (crb_lqr_gains); gain_frag / shared_op
+   * must be NULL then */
+  int64_t gain_stride;
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */
@@ -233,6 +238,32 @@ int64_t crb_shared_operator(const crb_plan_t* plan, const double* params_host, c
 int crb_dense_matrices(const crb_plan_t* plan, const double* params_host,
                        const uint8_t* elem_type_host, const uint8_t* bc_host,
                        double* M_out, double* K_out);
+
+/* Device.  crb_dense_matrices for every parameter set at once: the per-member A / B build of an LQR design
+ * ensemble (euler_bernoulli_beam.py:139-161, 265, 422-511; segments.py:32-78).  params device
+ * [n_param_sets, N, 7]; elem_type_host [N], bc_host [N+1] host; M_out, K_out device [n_param_sets, n, n]
+ * row-major (K_out may be NULL).  N <= CRB_LQR_MAX_ELEMENTS. */
+int crb_dense_matrices_batched(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
+                               const uint8_t* elem_type_host, const uint8_t* bc_host, double* M_out,
+                               double* K_out, void* stream);
+
+/* Device.  Batched LQR synthesis: replaces LinearQuadraticRegulator.compute_gain_matrix
+ * (control/linear_quadratic_regulator.py:84-191; `ct.lqr(A, B, Q, R)` at :180) for an ENSEMBLE of designs.
+ * Per member: A = [[0, I], [-M^-1 K, 0]], B = [[0], [M^-1]] (:84-146), the stabilising solution S of
+ * A^T S + S A - S B R^-1 B^T S + Q = 0 (matrix sign function of the Hamiltonian + `refine_passes` exact
+ * correction solves, 1 recommended), gain = R^-1 B^T S.
+ *   M_beam, K_beam  device [B or 1, n, n] (m_shared / k_shared = 1: one matrix for all members)
+ *   Q device [2n,2n], R device [n,n] (shared);  gain_out device [B, n, 2n];  S_out device [B, 2n, 2n] or NULL
+ *   residual_out device [B] or NULL: ||A^T S + S A - S G S + Q||_F / ||Q||_F of the returned S
+ *   status_out device int32 [B]: 0 ok, 1 M or R singular, 2 no stabilising solution found (sign iteration
+ *       failed), 3 closed loop A - B gain not stable (:185-189); gain/S are NaN unless status is 0 or 3
+ *   workspace device, crb_lqr_workspace_bytes(n, B) bytes.  n <= 42 (the 4n x 4n Hamiltonian lives in
+ *   shared memory). */
+int crb_lqr_workspace_bytes(int32_t n, int32_t n_members, size_t* out);
+int crb_lqr_gains(int32_t n, int32_t n_members, const double* M_beam, int32_t m_shared, const double* K_beam,
+                  int32_t k_shared, const double* Q, const double* R, int32_t refine_passes, double* gain_out,
+                  double* S_out, double* residual_out, int32_t* status_out, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
