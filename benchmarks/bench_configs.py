@@ -71,6 +71,44 @@ def main():
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
             print(json.dumps({"config": "cfg2 x%d (nonlinear 20 el + drag), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
                               "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "cfg3p":  # config 3 shape with a PINNED root (constrained DOFs inside an active slot: NC variant of the paired kernel)
+            B, steps = 65536, 50
+            e = ens.config3(B, 32)
+            beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, B), "type": ["linear"] * 32,
+                                                     "boundary_condition": [2] + [0] * 31})
+            beam.create_system_func(); beam.create_input_func()
+            n = beam.n_free
+            rng = np.random.default_rng(4)
+            X = torch.from_numpy(np.concatenate([1e-3 * rng.standard_normal((B, n)), 1e-1 * rng.standard_normal((B, n))], axis=1)).to(dev)
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
+            print(json.dumps({"config": "cfg3 shape with a pinned root (NC variant of the paired kernel)", "m": beam._plan.m, "g": beam._plan.g, "n_free": n,
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+        if name == "lqr":  # batched LQR synthesis + rollout with one gain per member
+            from continuum_robot_b200 import BatchedLinearQuadraticRegulator
+            B, steps, N = 8192, 200, 6
+            rng = np.random.default_rng(6)
+            e = ens.config3(8, N)
+            par = np.repeat(params(e, 1), B, axis=0)
+            par[:, :, 1] = 75e9 * np.exp(0.3 * rng.standard_normal((B, 1)))
+            par[:, :, 3] *= np.exp(0.2 * rng.standard_normal((B, 1)))
+            beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["linear"] * N}, ForceParams(enable_gravity_effects=True))
+            beam.create_system_func(); beam.create_input_func()
+            n = beam.n_free
+            Q = torch.diag(torch.cat([torch.full((n,), 100.0), torch.full((n,), 10.0)])).to(dev, torch.float64)
+            R = torch.eye(n, dtype=torch.float64, device=dev)
+            Md, Kd = beam.dense_matrices()
+            out = {}
+            def synth():
+                out["K"] = BatchedLinearQuadraticRegulator(Kd, Md, Q, R).compute_gain_matrix()
+            ms = timed(synth)
+            print(json.dumps({"config": "LQR synthesis, %d designs x %d elements (n = %d, Hamiltonian %d^2), 1 correction pass" % (B, N, n, 4 * n),
+                              "designs_per_s": B / (ms * 1e-3), "ms": ms}))
+            ctrl = FullStateLinear(out["K"])
+            X = torch.zeros(B, 2 * n, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.from_numpy(rng.uniform(1, 20, B)).to(dev))
+            ms = timed(lambda: rk4_steps(beam, X, 0.0, 5e-6, steps, u=imp, controller=ctrl))
+            print(json.dumps({"config": "LQR rollout with one gain per member, %d x %d el" % (B, N),
+                              "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg1e":  # config 1 as an ensemble: linear 10-element cantilever, gravity, tip impulse, per-member E
             B, steps = 131072, 100
             rng = np.random.default_rng(2)

@@ -666,7 +666,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   // dense [8 x 2n] x [2n x n] product: mma.sync.m8n8k4.f64 with rows = members (4 lanes each,
   // plan.g == 4), k-tiles = the lanes' own state values (no shuffle needed to build A) and n-tiles
   // = the lanes' own position DOFs (the C fragment lands where the force is consumed).
-  const bool gain_mma = (FEAT & CRB_F_GAINM) && F.gain && S.gain_frag != nullptr && G == 4;
+  const bool gain_mma = (FEAT & CRB_F_GAINM) && F.gain && S.gain_frag != nullptr && G == 4 && S.gain_stride == 0;
   if (gain_mma) {
     constexpr int KT = 6 * M, NT = (3 * M + 1) / 2;
     double ev[KT];
@@ -711,21 +711,30 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
     __syncwarp();
     const int n = L.n;
     if ((FEAT & CRB_F_GAINS) && F.gain && !gain_mma) {
+      // the lane's 3M gain rows advance together along the state (3M independent FMA chains, one read of
+      // e[c] for all of them); gain_stride != 0: one gain per member (crb_lqr_gains)
+      const double* gbase = S.gain + (long long)L.member * S.gain_stride;
+      int roff[M][3];
+      double sacc[M][3];
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const int r = L.ri[j][d];
-          if (r >= 0) {
-            const double* row = S.gain + (long long)r * 2 * n;
-            double sacc = 0.0;
-            for (int c = 0; c < 2 * n; ++c) {
-              const double ref = S.ref ? __ldg(S.ref + c) : 0.0;
-              sacc = fma(__ldg(row + c), ref - e[c], sacc);
-            }
-            acc[j][d] += sacc;
-          }
+          roff[j][d] = (L.ri[j][d] >= 0 ? L.ri[j][d] : 0) * 2 * n;
+          sacc[j][d] = 0.0;
         }
+      for (int c = 0; c < 2 * n; ++c) {
+        const double ec = (S.ref ? __ldg(S.ref + c) : 0.0) - e[c];
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) sacc[j][d] = fma(__ldg(gbase + roff[j][d] + c), ec, sacc[j][d]);
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          if (L.ri[j][d] >= 0) acc[j][d] += sacc[j][d];
     }
     if (F.grav_generic) {
       // gravity_forces.py:97-146 evaluated in REDUCED indices.  Pass 1: the lanes of the

@@ -11,11 +11,24 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
-#define CRB_LIN2(UCV, IMPV)                                                                              \
-  {                                                                                                      \
-    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM>, bytes, "crb_rk4")) return rc;       \
-    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
-                                                                                        Y_out, save_every); \
+#define CRB_LIN2N(UCV, IMPV, NCV)                                                                             \
+  {                                                                                                            \
+    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_rk4")) return rc;        \
+    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
+                                                                                             Y_out, save_every); \
+  }
+#define CRB_LIN2(UCV, IMPV) CRB_LIN2N(UCV, IMPV, false)
+  // constrained DOFs inside active slots (PINNED root, interior supports ...) or phantom slots: the NC variants
+  // (reduced-index table for state I/O, masked right-hand sides); shared mass factors only
+  if (!(plan->contiguous && plan->p_act == plan->p)) {
+    if (PM || sys->force_staged) return 1;
+    if constexpr (!PM) {
+      if (uc && imp) CRB_LIN2N(true, true, true)
+      else if (uc) CRB_LIN2N(true, false, true)
+      else if (imp) CRB_LIN2N(false, true, true)
+      else CRB_LIN2N(false, false, true)
+    }
+    return 0;
   }
   if (!sys->force_staged || PM) {  // paired operator applications (forcing piecewise constant in time)
     if (uc && imp) CRB_LIN2(true, true)
@@ -32,6 +45,7 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
     crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
   }
 #undef CRB_LIN2
+#undef CRB_LIN2N
   return 0;
 }
 
@@ -51,6 +65,7 @@ int crb_launch_rk4_fast(const crb_plan_t* plan, const crb_system_t* sys, double*
   if (plan->m == MM && plan->levels == LL) return launch<MM, LL, false>(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
   CRB_CASE(4, 3) CRB_CASE(4, 4) CRB_CASE(4, 5) CRB_CASE(4, 2)
   CRB_CASE(3, 1) CRB_CASE(3, 2) CRB_CASE(3, 3) CRB_CASE(2, 0) CRB_CASE(2, 1) CRB_CASE(4, 0) CRB_CASE(3, 0) CRB_CASE(1, 0) CRB_CASE(4, 1)
+  CRB_CASE(3, 4) CRB_CASE(3, 5)
 #undef CRB_CASE
   return 1;  // shape not instantiated: the caller falls back to the general kernel
 }

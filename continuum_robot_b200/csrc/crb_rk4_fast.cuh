@@ -30,8 +30,13 @@
 // by every solve): 2x2 T blocks of the first PT slots, the tu values, Sinv of the first PS slots.
 // Measured on B200, cfg 3 (ms per 50-step launch): none 1.886, T 1.832, T + tu 1.841, T + tu + 2 Sinv 1.805,
 // everything 1.838.  Kernels that carry forcing vectors pin less (they would spill).
-template <int M, int PT = 0, int PU = 0, int PS = 0>
+// NC: plan with constrained DOFs inside active slots, an untrimmed root or phantom slots (any boundary
+// condition pattern): state I/O goes through the reduced-index table and constrained / phantom DOFs are
+// masked before the solve (their factor rows are identity rows).
+template <int M, int PT = 0, int PU = 0, int PS = 0, bool NC = false>
 struct FastCtx {
+  static constexpr bool kNC = NC;
+  int ri[NC ? M : 1][3];  // reduced index of own DOFs (-1: constrained / phantom)
   int g;
   int member;
   bool active;
@@ -171,6 +176,12 @@ __device__ __forceinline__ int fast_ctx_init(CT& C, const KPlan& P, const crb_sy
     const double2 k1 = *reinterpret_cast<const double2*>(kc + 4 * (s0 + j) + 2);
     C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
   }
+  if (CT::kNC) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) C.ri[CT::kNC ? j : 0][d] = S.red_index[3 * (s0 + j) + d];
+  }
   C.imp_amp = 0.0;
   C.imp_dur = S.imp_duration;
   C.imp_local = -1;
@@ -182,6 +193,14 @@ template <int M, typename CT>
 __device__ __forceinline__ void fast_ctx_impulse(CT& C, const crb_system_t& S, int s0) {
   if (!S.imp_amp) return;
   C.imp_amp = S.imp_amp[C.member];
+  if (CT::kNC) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (C.ri[CT::kNC ? j : 0][d] == S.imp_dof) C.imp_local = 3 * j + d;
+    return;
+  }
   const int rel = S.imp_dof - 3 * s0;
   if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
 }
@@ -325,6 +344,13 @@ __device__ __forceinline__ void fast_apply2(const CT& C, double (&w)[2][M][3]) {
       b[r][j][1] = V[j] - V[j + 1];
       b[r][j][2] = -(m2[j] + m1[j + 1]);
     }
+    if (CT::kNC) {
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          if (C.ri[CT::kNC ? j : 0][d] < 0) b[r][j][d] = 0.0;
+    }
   }
   fast_solve_r<M, LV, 2>(b, C);
 #pragma unroll
@@ -345,39 +371,45 @@ __device__ __forceinline__ void fast_apply2(const CT& C, double (&w)[2][M][3]) {
 // launch by one paired solve.
 // PM: every member has its OWN mass factors (density / area / lengths differ per member): each lane group stages its member's compact factor copy in its own shared-memory
 // region.
-template <int M, int LV, bool UC, bool IMP, bool PM>
+template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
                     double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP) ? 0 : 2)> Ctx;  // forcing vectors need the registers
+  typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP || NC) ? 0 : 2), NC> Ctx;  // forcing vectors / index tables need the registers
   Ctx C;
   const int s0 = fast_ctx_init<M, LV, PM>(C, P, S, S.mfac, smem);
   const int n = C.n;
-  double* xq = X + (long long)C.member * 2 * n + 3 * s0;
+  // reduced index of own DOF (j, d): 3 (s0 + j) + d on contiguous plans without phantom slots, else the
+  // plan's table (-1: constrained or phantom, held at zero)
+  auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  double* xm = X + (long long)C.member * 2 * n;
   double q[M][3], v[M][3], w[2][M][3];
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      q[j][d] = xq[3 * j + d];
-      v[j][d] = xq[n + 3 * j + d];
+      const int r = rix(j, d);
+      q[j][d] = (!NC || r >= 0) ? xm[r] : 0.0;
+      v[j][d] = (!NC || r >= 0) ? xm[n + r] : 0.0;
     }
   // forcing in acceleration space: cu = M^-1 (u_const + f_ext), ci = amp * M^-1 e_k
   double cu[UC ? M : 1][3], ci[IMP ? M : 1][3];
   if (UC || IMP) {
-    const long long mo = (long long)C.member * n + 3 * s0;
-    const int rel = IMP ? S.imp_dof - 3 * s0 : -1;
+    const long long mo = (long long)C.member * n;
     const double amp = IMP ? S.imp_amp[C.member] : 0.0;
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
+        const int r = rix(j, d);
         double u = 0.0;
-        if (UC && S.u_const) u += S.u_const[mo + 3 * j + d];
-        if (UC && S.f_ext) u += S.f_ext[mo + 3 * j + d];
+        if (!NC || r >= 0) {
+          if (UC && S.u_const) u += S.u_const[mo + r];
+          if (UC && S.f_ext) u += S.f_ext[mo + r];
+        }
         w[0][j][d] = u;
-        w[1][j][d] = (rel == 3 * j + d) ? amp : 0.0;
+        w[1][j][d] = (IMP && r == S.imp_dof) ? amp : 0.0;
       }
     fast_solve_r<M, LV, 2>(w, C);
 #pragma unroll
@@ -441,13 +473,16 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
       }
     }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          yq[3 * j + d] = q[j][d];
-          yq[n + 3 * j + d] = v[j][d];
+          const int r = rix(j, d);
+          if (!NC || r >= 0) {
+            ym[r] = q[j][d];
+            ym[n + r] = v[j][d];
+          }
         }
     }
   }
@@ -456,8 +491,11 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        xq[3 * j + d] = q[j][d];
-        xq[n + 3 * j + d] = v[j][d];
+        const int r = rix(j, d);
+        if (!NC || r >= 0) {
+          xm[r] = q[j][d];
+          xm[n + r] = v[j][d];
+        }
       }
   }
 }
