@@ -53,10 +53,36 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
-// In-place inverse of the m x m row-major matrix `a` (shared memory) by Gauss-Jordan elimination with partial
-// pivoting.  Returns sum log|pivot| = log|det a|; a zero pivot column sets *singular (block-uniform).
+// Elimination step of gj_inverse for pivot p: warp w owns rows w, w + 8, ..., lane l owns columns l + 32 c
+// (c < CH): the pivot-row values of the lane's columns stay in registers for all of its rows, so that the inner
+// loop is LDS / DFMA / STS.  Column p was zeroed when it was saved, which makes the update of column p
+// (a[i][p] <- -col[i] / pivot) the same FMA as every other column (prow[p] = 1).
+template <int CH>
+__device__ __forceinline__ void gj_eliminate(double* a, int m, int p, const double* col, const double* prow, double ipv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double pr[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) pr[c] = (lane + 32 * c < m) ? prow[lane + 32 * c] : 0.0;
+  for (int i = warp; i < m; i += CRB_LQR_THREADS / 32) {
+    double* row = a + i * m + lane;
+    if (i == p) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (lane + 32 * c < m) row[32 * c] = pr[c] * ipv;
+    } else {
+      const double f = -col[i] * ipv;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (lane + 32 * c < m) row[32 * c] = fma(f, pr[c], row[32 * c]);
+    }
+  }
+}
+
+// In-place inverse of the m x m row-major matrix `a` (shared memory, m <= 192) by Gauss-Jordan elimination with
+// partial pivoting.  Returns sum log|pivot| = log|det a|; a zero pivot column sets *singular (block-uniform).
 __device__ double gj_inverse(double* a, int m, double* col, double* prow, int* piv, double* red, bool* singular) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunks = (m + 31) >> 5;
   double logdet = 0.0;
   *singular = false;
   for (int p = 0; p < m; ++p) {
@@ -79,28 +105,30 @@ __device__ double gj_inverse(double* a, int m, double* col, double* prow, int* p
     const int r = piv[p];
     const double best = red[16];
     if (!(best > 0.0) || !isfinite(best)) { *singular = true; return logdet; }
-    if (r != p)
+    if (r != p) {  // block-uniform
       for (int j = tid; j < m; j += CRB_LQR_THREADS) {
         const double x = a[p * m + j];
         a[p * m + j] = a[r * m + j];
         a[r * m + j] = x;
       }
-    __syncthreads();
+      __syncthreads();
+    }
     const double pv = a[p * m + p];
+    __syncthreads();  // every thread has read the pivot before column p is zeroed
     for (int i = tid; i < m; i += CRB_LQR_THREADS) {
       col[i] = a[i * m + p];
       prow[i] = (i == p) ? 1.0 : a[p * m + i];
+      a[i * m + p] = 0.0;
     }
     __syncthreads();
     const double ipv = 1.0 / pv;
-    for (int i = warp; i < m; i += CRB_LQR_THREADS / 32) {
-      const double f = -col[i] * ipv;
-      for (int j = lane; j < m; j += 32) {
-        double nv;
-        if (i == p) nv = prow[j] * ipv;
-        else nv = fma(f, prow[j], (j == p) ? 0.0 : a[i * m + j]);
-        a[i * m + j] = nv;
-      }
+    switch (chunks) {
+      case 1: gj_eliminate<1>(a, m, p, col, prow, ipv); break;
+      case 2: gj_eliminate<2>(a, m, p, col, prow, ipv); break;
+      case 3: gj_eliminate<3>(a, m, p, col, prow, ipv); break;
+      case 4: gj_eliminate<4>(a, m, p, col, prow, ipv); break;
+      case 5: gj_eliminate<5>(a, m, p, col, prow, ipv); break;
+      default: gj_eliminate<6>(a, m, p, col, prow, ipv); break;
     }
     logdet += log(fabs(pv));
     // the next pivot search reads column p + 1 of the updated matrix
@@ -177,7 +205,7 @@ __device__ void riccati_residual(int n2, const double* A, const double* G, const
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(CRB_LQR_THREADS) crb_lqr_kernel(LqrArgs a) {
+__global__ void __launch_bounds__(CRB_LQR_THREADS, 4) crb_lqr_kernel(LqrArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int n = a.n, n2 = 2 * n, D = 4 * n, tid = threadIdx.x;
   double* sm = smem;           // D x D
