@@ -327,9 +327,9 @@ extern "C" int crb_midpoint(const crb_plan_t* plan, const crb_system_t* sys, con
   if (nsteps < 0) return fail(CRB_E_ARG, "crb_midpoint: nsteps must be >= 0");
   if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_midpoint: step h must be positive and finite");
   if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_midpoint: save_every must be >= 1 when Y_out is given");
-  if (!(sys->all_linear && plan->contiguous && plan->p_act == plan->p && !sys->drag && sys->grav_mode == 0 && !sys->gain))
-    return fail(CRB_E_ARG, "crb_midpoint: needs an all-linear beam without drag / gravity / feedback on a contiguous "
-                           "plan without phantom slots (the implicit step solves with M + h^2/4 K)");
+  if (!(sys->all_linear && !sys->drag && sys->grav_mode == 0 && !sys->gain))
+    return fail(CRB_E_ARG, "crb_midpoint: needs an all-linear beam without drag / gravity / feedback "
+                           "(the implicit step solves with M + h^2/4 K)");
   if (nsteps == 0) return 0;
   if (int rc = crb_launch_midpoint(plan, sys, afac, afac_shared, X, t0, h, nsteps, Y_out, save_every, (cudaStream_t)stream))
     return rc;

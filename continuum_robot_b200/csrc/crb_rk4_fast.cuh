@@ -134,6 +134,13 @@ __device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], doubl
 #pragma unroll
       for (int d = 0; d < 3; ++d) b[0][j][d] += uc[j][d];
   }
+  if (CT::kNC) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (C.ri[CT::kNC ? j : 0][d] < 0) b[0][j][d] = 0.0;
+  }
   fast_solve_r<M, LV, 1>(b, C);
 #pragma unroll
   for (int j = 0; j < M; ++j)
@@ -515,27 +522,31 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
 #ifndef CRB_MID_PINS
 #define CRB_MID_PINS 4
 #endif
-template <int M, int LV, bool UC, bool IMP, bool PM>
+template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_MID_MINBLOCKS)
 crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, double* __restrict__ X, double t0,
                     double h, int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  typedef FastCtx<M, CRB_MID_PINS, (CRB_MID_PINS > 0 ? 1 : 0), CRB_MID_PINS> Ctx;  // one solve per step: the constants of the solve stay in registers
+  typedef FastCtx<M, CRB_MID_PINS, (CRB_MID_PINS > 0 ? 1 : 0), (NC ? 0 : CRB_MID_PINS), NC> Ctx;  // one solve per step: the constants of the solve stay in registers
   Ctx C;
   const int s0 = fast_ctx_init<M, LV, PM>(C, P, S, afac, smem);
   if (IMP) fast_ctx_impulse<M>(C, S, s0);
   const int n = C.n;
-  double* xq = X + (long long)C.member * 2 * n + 3 * s0;
+  // reduced index of own DOF (j, d); NC: the plan's table (-1: constrained or phantom, held at zero)
+  auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  double* xm = X + (long long)C.member * 2 * n;
   double q[M][3], v[M][3], w[M][3], uc[UC ? M : 1][3];
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      q[j][d] = xq[3 * j + d];
-      v[j][d] = xq[n + 3 * j + d];
+      const int r = rix(j, d);
+      const bool ok = !NC || r >= 0;
+      q[j][d] = ok ? xm[r] : 0.0;
+      v[j][d] = ok ? xm[n + r] : 0.0;
       if (UC) {
-        const long long mo = (long long)C.member * n + 3 * s0 + 3 * j + d;
-        uc[j][d] = (S.u_const ? S.u_const[mo] : 0.0) + (S.f_ext ? S.f_ext[mo] : 0.0);
+        const long long mo = (long long)C.member * n + r;
+        uc[j][d] = ok ? (S.u_const ? S.u_const[mo] : 0.0) + (S.f_ext ? S.f_ext[mo] : 0.0) : 0.0;
       }
     }
   const double hh = 0.5 * h;
@@ -555,13 +566,16 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         v[j][d] += dv;
       }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          yq[3 * j + d] = q[j][d];
-          yq[n + 3 * j + d] = v[j][d];
+          const int r = rix(j, d);
+          if (!NC || r >= 0) {
+            ym[r] = q[j][d];
+            ym[n + r] = v[j][d];
+          }
         }
     }
   }
@@ -570,8 +584,11 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        xq[3 * j + d] = q[j][d];
-        xq[n + 3 * j + d] = v[j][d];
+        const int r = rix(j, d);
+        if (!NC || r >= 0) {
+          xm[r] = q[j][d];
+          xm[n + r] = v[j][d];
+        }
       }
   }
 }

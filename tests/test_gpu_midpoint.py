@@ -128,3 +128,64 @@ def test_midpoint_argument_errors():
     lin = make_gpu_beam(par, np.zeros(N, dtype=int), np.array([1] + [0] * N))
     with pytest.raises(ValueError, match="positive"):
         midpoint_steps(lin, X, 0.0, -1.0, 1)
+
+
+@pytest.mark.parametrize("N,bcs,variant", [
+    (10, {0: 1}, "impulse"),          # cantilever with phantom slots (10 active nodes on 4 lanes x 3 slots)
+    (32, {0: 2}, "plain"),            # pinned root: constrained DOFs inside the root slot
+    (9, {0: 2, 5: 2}, "force"),       # pinned root + interior pin
+    (7, {3: 1}, "impulse"),           # free ends, clamped in the middle
+    (33, {0: 1, 20: 2}, "force"),
+])
+def test_midpoint_any_boundary_conditions(N, bcs, variant):
+    """Implicit midpoint on plans with constrained DOFs inside active slots / phantom slots (NC kernel variants,
+    factors of M + h^2/4 K with identity rows) vs the oracle (<= 1e-9), per-member stiffness."""
+    from continuum_robot_b200 import TipImpulse, midpoint_steps
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.dynamic_beam import BatchedDynamicEulerBernoulliBeam
+    from oracle import beam_oracle as bo
+
+    rng = np.random.default_rng(40 + N)
+    B, h, steps = 19, 1e-4, 40
+    m = ens.material()
+    par = np.zeros((B, N, 7))
+    par[:, :, 0] = m["length"] * (1 + 0.2 * rng.random(N))[None]
+    par[:, :, 1] = m["E"] * np.exp(0.2 * rng.standard_normal((B, N)))
+    par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["I"], m["rho"], m["A"]
+    par[:, :, 5:] = 1.0
+    bc = np.zeros(N, dtype=int)
+    for k, v in bcs.items():
+        bc[k] = v
+    et = np.zeros(N, dtype=int)
+    beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": [0] * N, "boundary_condition": [int(b) for b in bc]})
+    beam.create_system_func()
+    beam.create_input_func()
+    n = beam.n_free
+    amp = rng.uniform(0.05, 0.5, B)
+    dof = int(rng.integers(0, n))
+    uconst = 1e-2 * rng.standard_normal((B, n))
+    u = None
+    if variant == "impulse":
+        u = TipImpulse(torch.from_numpy(amp).cuda(), dof=dof, duration=20.3 * h)
+    if variant == "force":
+        u = torch.from_numpy(uconst).cuda()
+    x0 = np.concatenate([1e-4 * rng.standard_normal((B, n)), 1e-2 * rng.standard_normal((B, n))], axis=1)
+    X = torch.from_numpy(x0).cuda()
+    Y = torch.zeros(steps // 20, B, 2 * n, dtype=torch.float64, device="cuda")
+    midpoint_steps(beam, X, 0.0, h, steps, u=u, Y_out=Y, save_every=20)
+    got, frames = X.cpu().numpy(), Y.cpu().numpy()
+    for i in (0, B // 2, B - 1):
+        p = par[i]
+        orc = bo.BeamOracle(bo.BeamSpec(p[:, 0], p[:, 1], p[:, 2], p[:, 3], p[:, 4], et, bc, p[:, 5], p[:, 6]))
+
+        def uf(t, i=i):
+            f = np.zeros(n)
+            if variant == "impulse" and t < 20.3 * h:
+                f[dof] = amp[i]
+            if variant == "force":
+                f = uconst[i].copy()
+            return f
+
+        want, wf = bo.midpoint_solve(orc, uf, x0[i], 0.0, h, steps, save_every=20)
+        assert block_err(got[i], want, n) < 1e-9, (i, block_err(got[i], want, n))
+        assert max(block_err(frames[k, i], wf[k], n) for k in range(len(wf))) < 1e-9
