@@ -103,12 +103,18 @@ def main():
             ms = timed(synth)
             print(json.dumps({"config": "LQR synthesis, %d designs x %d elements (n = %d, Hamiltonian %d^2), 1 correction pass" % (B, N, n, 4 * n),
                               "designs_per_s": B / (ms * 1e-3), "ms": ms}))
-            ctrl = FullStateLinear(out["K"])
-            X = torch.zeros(B, 2 * n, dtype=torch.float64, device=dev)
-            imp = TipImpulse(torch.from_numpy(rng.uniform(1, 20, B)).to(dev))
-            ms = timed(lambda: rk4_steps(beam, X, 0.0, 5e-6, steps, u=imp, controller=ctrl))
-            print(json.dumps({"config": "LQR rollout with one gain per member, %d x %d el" % (B, N),
-                              "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}))
+            # rollout: 8 disturbance realisations per design so that the ensemble fills the GPU (65536 members)
+            rep = 8
+            Bb = B * rep
+            big = BatchedDynamicEulerBernoulliBeam({"params": np.tile(par, (rep, 1, 1)), "type": ["linear"] * N},
+                                                   ForceParams(enable_gravity_effects=True))
+            big.create_system_func(); big.create_input_func()
+            ctrl = FullStateLinear(out["K"].repeat(rep, 1, 1))
+            X = torch.zeros(Bb, 2 * n, dtype=torch.float64, device=dev)
+            imp = TipImpulse(torch.from_numpy(rng.uniform(1, 20, Bb)).to(dev))
+            ms = timed(lambda: rk4_steps(big, X, 0.0, 5e-6, steps, u=imp, controller=ctrl))
+            print(json.dumps({"config": "LQR rollout with one gain per member, %d x %d el" % (Bb, N), "m": big._plan.m, "g": big._plan.g,
+                              "member_steps_per_s": Bb * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg1e":  # config 1 as an ensemble: linear 10-element cantilever, gravity, tip impulse, per-member E
             B, steps = 131072, 100
             rng = np.random.default_rng(2)

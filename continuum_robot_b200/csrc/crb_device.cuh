@@ -484,6 +484,9 @@ enum : unsigned {
   CRB_F_PROFILE_A = CRB_F_LINEAR | CRB_F_GRAVS | CRB_F_INPUT | CRB_F_GAINM,
   // profile B: nonlinear elements, drag, slot gravity, inputs (configs 2, 4)
   CRB_F_PROFILE_B = CRB_F_NONLIN | CRB_F_DRAG | CRB_F_GRAVS | CRB_F_INPUT,
+  // profile C: profile A with the feedback product on the reduced-vector path (one gain PER MEMBER, or lane
+  // layouts other than 4 lanes per member): LQR rollout of a design ensemble
+  CRB_F_PROFILE_C = CRB_F_LINEAR | CRB_F_GRAVS | CRB_F_INPUT | CRB_F_GAINS,
 };
 
 __device__ __forceinline__ RhsFlags make_flags(const crb_system_t& s, const KPlan& p) {

@@ -93,6 +93,7 @@ inline unsigned crb_needed_features(const crb_plan_t* plan, const crb_system_t* 
 }
 inline unsigned crb_pick_profile(unsigned need) {
   if ((need & ~CRB_F_PROFILE_A) == 0) return CRB_F_PROFILE_A;
+  if ((need & ~CRB_F_PROFILE_C) == 0) return CRB_F_PROFILE_C;
   if ((need & ~CRB_F_PROFILE_B) == 0) return CRB_F_PROFILE_B;
   return CRB_F_ALL;
 }

@@ -14,7 +14,7 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
   // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
   // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
-  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || PM);
+  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || FEAT == CRB_F_PROFILE_C || PM);
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Gk = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g;
@@ -104,13 +104,15 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
 #define CRB_RK4_CASE(MM, LL)                                                                                       \
   if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                                   \
     if (sys->mass_shared) {                                                                                         \
-      const SmemLayout SL = prof == CRB_F_PROFILE_A ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
+      const SmemLayout SL = prof != CRB_F_PROFILE_B ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
       if (prof == CRB_F_PROFILE_A) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_A, LL, false)                                   \
+      else if (prof == CRB_F_PROFILE_C) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_C, LL, false)                              \
       else CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_B, LL, false)                                                           \
     } else {                                                                                                        \
       const SmemLayout SL = smem_layout_compact_pm(plan, sys, &bytes);                                              \
       if (bytes <= 200 * 1024) {                                                                                    \
         if (prof == CRB_F_PROFILE_A) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_A, LL, true)                                  \
+        else if (prof == CRB_F_PROFILE_C) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_C, LL, true)                             \
         else CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_B, LL, true)                                                          \
       }                                                                                                             \
       smem_layout(plan, sys, &bytes);                                                                               \

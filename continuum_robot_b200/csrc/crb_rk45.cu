@@ -17,7 +17,8 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   A.max_attempts = max_attempts;
   const DpTab T = make_dp_tab();
   const unsigned need = crb_needed_features(plan, sys);
-  const unsigned prof = crb_pick_profile(need);
+  unsigned prof = crb_pick_profile(need);
+  if (prof == CRB_F_PROFILE_C) prof = CRB_F_ALL;  // the reduced-vector feedback path is compiled into the generic RK45 kernel only
   // shared memory: [mass factors][per-member scratch][stage accelerations 21 m doubles per thread]
   auto total_bytes = [&](const SmemLayout& L, int m) {
     return sizeof(double) * ((size_t)L.mfac_doubles + (size_t)L.scratch_doubles * mpb + (size_t)21 * m * 32 * WPB);
