@@ -112,9 +112,10 @@ def main():
             ctrl = FullStateLinear(out["K"].repeat(rep, 1, 1))
             X = torch.zeros(Bb, 2 * n, dtype=torch.float64, device=dev)
             imp = TipImpulse(torch.from_numpy(rng.uniform(1, 20, Bb)).to(dev))
-            ms = timed(lambda: rk4_steps(big, X, 0.0, 5e-6, steps, u=imp, controller=ctrl))
-            print(json.dumps({"config": "LQR rollout with one gain per member, %d x %d el" % (Bb, N), "m": big._plan.m, "g": big._plan.g,
-                              "member_steps_per_s": Bb * steps / (ms * 1e-3), "ms": ms}))
+            for bm in (big, big.with_slots(2)):
+                ms = timed(lambda: rk4_steps(bm, X, 0.0, 5e-6, steps, u=imp, controller=ctrl))
+                print(json.dumps({"config": "LQR rollout with one gain per member, %d x %d el" % (Bb, N), "m": bm._plan.m, "g": bm._plan.g,
+                                  "member_steps_per_s": Bb * steps / (ms * 1e-3), "ms": ms}))
         if name == "cfg1e":  # config 1 as an ensemble: linear 10-element cantilever, gravity, tip impulse, per-member E
             B, steps = 131072, 100
             rng = np.random.default_rng(2)

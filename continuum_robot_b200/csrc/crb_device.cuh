@@ -468,6 +468,7 @@ struct LaneCtx {
   MassConsts<M> mc;
   FastMass fm;           // uniform-mass solve constants (shape-specialised kernels)
   double* scratch;       // shared-memory scratch of this member (2n doubles) or nullptr
+  const double* gain_sm; // this warp's per-member gains staged in shared memory as [c][3 j + d][lane], or nullptr
 };
 
 struct RhsFlags {
@@ -515,6 +516,7 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
   L.active = member < S.n_members;
   L.member = L.active ? member : S.n_members - 1;
   L.scratch = scratch;
+  L.gain_sm = nullptr;
   const int s0 = g * M;
   const double* kc = S.kcoef + (S.stiff_shared ? 0ll : (long long)L.member * P.p * 4);
 #pragma unroll
@@ -726,12 +728,24 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
           roff[j][d] = (L.ri[j][d] >= 0 ? L.ri[j][d] : 0) * 2 * n;
           sacc[j][d] = 0.0;
         }
-      for (int c = 0; c < 2 * n; ++c) {
-        const double ec = (S.ref ? __ldg(S.ref + c) : 0.0) - e[c];
+      if (L.gain_sm) {  // staged per-member gains: conflict-free LDS, 3M independent FMA chains
+        const double* gs = L.gain_sm + L.lane;
+#pragma unroll 4
+        for (int c = 0; c < 2 * n; ++c) {
+          const double ec = (S.ref ? __ldg(S.ref + c) : 0.0) - e[c];
 #pragma unroll
-        for (int j = 0; j < M; ++j)
+          for (int j = 0; j < M; ++j)
 #pragma unroll
-          for (int d = 0; d < 3; ++d) sacc[j][d] = fma(__ldg(gbase + roff[j][d] + c), ec, sacc[j][d]);
+            for (int d = 0; d < 3; ++d) sacc[j][d] = fma(gs[(c * 3 * M + 3 * j + d) * 32], ec, sacc[j][d]);
+        }
+      } else {
+        for (int c = 0; c < 2 * n; ++c) {
+          const double ec = (S.ref ? __ldg(S.ref + c) : 0.0) - e[c];
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) sacc[j][d] = fma(__ldg(gbase + roff[j][d] + c), ec, sacc[j][d]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < M; ++j)

@@ -5,8 +5,11 @@
 // LV >= 0: lanes per member = 1 << LV known at compile time (constant shuffle widths and
 // shared-memory offsets); LV = -1: generic.
 // PM: per-member mass factors (shape-specialised kernels only): compact solve on per-member shared-memory regions.
-template <int M, unsigned FEAT, int LV, bool PM = false>
-__global__ void __launch_bounds__(CRB_THREADS)
+// GST: one gain PER MEMBER (crb_system_t.gain_stride != 0) staged in shared memory, one warp per block (a member's
+// n x 2n gain is 5 KB for the 6-element LQR example: 16 members per warp fill 83 KB); without it the gains are
+// re-read from L2 at every RHS evaluation.
+template <int M, unsigned FEAT, int LV, bool PM = false, bool GST = false>
+__global__ void __launch_bounds__(GST ? 32 : CRB_THREADS)
 crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
                int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
@@ -20,7 +23,7 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   const int Gk = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g;
   const int mpw = 32 / Gk;
   const int mloc = warp * mpw + lane / Gk;
-  const int member = blockIdx.x * (CRB_WARPS_PER_BLOCK * mpw) + mloc;
+  const int member = blockIdx.x * ((GST ? 1 : CRB_WARPS_PER_BLOCK) * mpw) + mloc;
   LaneCtx<M> L;
   load_lane_ctx<M>(L, P, S, member, lane % Gk, mf,
                    SL.scratch_doubles ? smem + SL.mfac_doubles + mloc * SL.scratch_doubles : nullptr);
@@ -36,6 +39,20 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
       L.mc.slot = smem;  // specialised kernels require a shared mass set: plain LDS instead of generic loads
       L.mc.scan = smem + 2 * CRB_SLOT_PAIRS * (M * Gk);
     }
+  }
+  if (GST) {  // stage the own rows of this member's gain: [c][3 j + d][lane]
+    double* gsm = smem + SL.mfac_doubles + mpw * SL.scratch_doubles;
+    const double* gm = S.gain + (long long)L.member * S.gain_stride;
+    const int n2 = 2 * L.n;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int r = L.ri[j][d];
+        for (int c = 0; c < n2; ++c) gsm[(c * 3 * M + 3 * j + d) * 32 + lane] = r >= 0 ? gm[(long long)r * n2 + c] : 0.0;
+      }
+    L.gain_sm = gsm;
+    __syncwarp();
   }
   const RhsFlags F = make_flags(S, P);
   double q[M][3], v[M][3];
@@ -101,6 +118,28 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
     crb_rk4_kernel<MM, PROF, LL, PMV><<<grid, CRB_THREADS, bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
     return 0;                                                                                                       \
   }
+  // one gain per member: one-warp blocks with the gains of the warp's members staged in shared memory
+#define CRB_RK4_CASE_GST(MM, LL)                                                                                   \
+  if (plan->m == MM && plan->levels == LL && prof == CRB_F_PROFILE_C && sys->gain_stride != 0) {                    \
+    const int mpw = 32 >> LL;                                                                                       \
+    SmemLayout SL = smem_layout(plan, sys, &bytes);                                                                 \
+    SL.mfac_doubles = crb_compact_doubles(plan->m, plan->g, plan->levels) * (sys->mass_shared ? 1 : mpw);           \
+    const size_t gst_bytes = sizeof(double) * ((size_t)SL.mfac_doubles + (size_t)SL.scratch_doubles * mpw +         \
+                                               (size_t)2 * plan->n_free * 3 * MM * 32);                             \
+    if (gst_bytes <= 113 * 1024) { /* two blocks per SM at least */                                                 \
+      const int gst_grid = (sys->n_members + mpw - 1) / mpw;                                                        \
+      if (sys->mass_shared) {                                                                                       \
+        if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_C, LL, false, true>, gst_bytes, "crb_rk4")) return rc; \
+        crb_rk4_kernel<MM, CRB_F_PROFILE_C, LL, false, true><<<gst_grid, 32, gst_bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
+      } else {                                                                                                      \
+        if (int rc = set_smem(crb_rk4_kernel<MM, CRB_F_PROFILE_C, LL, true, true>, gst_bytes, "crb_rk4")) return rc; \
+        crb_rk4_kernel<MM, CRB_F_PROFILE_C, LL, true, true><<<gst_grid, 32, gst_bytes, stream>>>(P, *sys, SL, X, t0, h, nsteps, Y_out, save_every); \
+      }                                                                                                             \
+      return 0;                                                                                                     \
+    }                                                                                                               \
+  }
+  if (!sys->force_staged) { CRB_RK4_CASE_GST(3, 1) CRB_RK4_CASE_GST(2, 2) CRB_RK4_CASE_GST(3, 2) }
+#undef CRB_RK4_CASE_GST
 #define CRB_RK4_CASE(MM, LL)                                                                                       \
   if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                                   \
     if (sys->mass_shared) {                                                                                         \

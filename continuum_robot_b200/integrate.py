@@ -57,6 +57,8 @@ def _feedback_layout(beam, controller):
     """State feedback runs on the FP64 tensor cores when a member spans 4 lanes (8 members = the 8
     rows of mma.m8n8k4): short beams are re-assembled with 2 slots per lane to get that layout."""
     if controller is not None and controller.is_enabled() and int(beam._plan.g) != 4 and beam._plan.p_act <= 8:
+        if getattr(getattr(controller, "gain_matrix", None), "ndim", 2) == 3:
+            return beam  # one gain per member: no shared operand for the tensor cores, keep the default layout
         return beam.with_slots(2)
     return beam
 

@@ -107,7 +107,8 @@ typedef struct crb_system_t {
   int32_t all_linear;       /* 1: every element is CRB_ELEM_LINEAR */
   int32_t all_nonlinear;    /* 1: every element is CRB_ELEM_NONLINEAR */
   int32_t force_general;    /* 1: always use the general kernels (testing / comparison) */
-  int32_t force_staged;     /* 1: fast path keeps the stage-by-stage kernel (no paired operator form) */
+  int32_t force_staged;     /* 1: fast path keeps the stage-by-stage kernel (no paired operator form); per-member
+                               gains stay in global memory (no shared-memory staging) -- testing / comparison */
   /* shared-operator form (crb_shared_operator): device copy of the operator blob, or NULL.  When set,
    * crb_rk4 evaluates the whole closed-loop RHS as a dense FP64 tensor-core contraction; gain / ref /
    * gravity vector / imp_dof are the ones the blob was built with. */
