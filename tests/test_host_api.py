@@ -437,3 +437,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_lqr_entry_points_validate_arguments_on_the_host():
+    """crb_lqr_* / crb_dense_matrices_batched reject bad arguments before touching the device (no compute calls)."""
+    L = _lib()
+    lib = L.load()
+    err = lambda: lib.crb_last_error().decode()
+    need = C.c_size_t(0)
+    assert lib.crb_lqr_workspace_bytes(43, 8, C.byref(need)) == -3 and "shared memory" in err()  # 4n x 4n Hamiltonian > 227 KB
+    assert lib.crb_lqr_workspace_bytes(0, 8, C.byref(need)) == -1
+    assert lib.crb_lqr_workspace_bytes(18, 8, None) == -1
+    assert lib.crb_lqr_gains(18, 4, None, 0, None, 0, None, None, 1, None, None, None, None, None, 0, None) == -1
+    assert "null argument" in err()
+    one = C.c_void_p(8)  # never dereferenced: the size checks come first
+    assert lib.crb_lqr_gains(60, 4, one, 0, one, 0, one, one, 1, one, None, None, one, one, 0, None) == -3
+    rc, p = _plan(4, [1, 0, 0, 0, 0])
+    assert rc == 0
+    et_nl, bc = bytes([0, 1, 0, 0]), bytes([1, 0, 0, 0, 0])
+    assert lib.crb_dense_matrices_batched(C.byref(p), None, 1, et_nl, bc, None, None, None) == -1
+    assert lib.crb_dense_matrices_batched(C.byref(p), one, 1, et_nl, bc, one, one, None) == -1
+    assert "nonlinear segments" in err()  # euler_bernoulli_beam.py:422-456
+    assert lib.crb_dense_matrices_batched(C.byref(p), one, 0, bytes(4), bc, one, None, None) == -1
+    assert lib.crb_dense_matrices_batched(C.byref(p), one, 1, bytes(4), bytes([2, 0, 0, 0, 0]), one, None, None) == -1
+    assert "mismatch" in err()
+    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.gain_stride.offset == C.sizeof(L.CrbSystem) - 8
