@@ -249,11 +249,12 @@ extern "C" int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const
   return 0;
 }
 
-// fast path: all-linear, no forces and no input other than a constant force / tip impulse (BASELINE config 3
-// shape); any mass distribution, shared or per member; any boundary conditions (plans with constrained DOFs in
-// active slots or phantom slots take the NC variants of the paired kernel)
+// fast path: all-linear, no drag, no feedback and no input other than a constant force / tip impulse (BASELINE
+// config 3 shape); any mass distribution, shared or per member; any boundary conditions (plans with constrained
+// DOFs in active slots or phantom slots take the NC variants of the paired kernel); slot-space gravity (config 1
+// as an ensemble) on the stage-by-stage kernel
 static bool rk4_fast_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
-  return sys->all_linear && !sys->drag && sys->grav_mode == 0 && !sys->gain && !sys->force_general;
+  return sys->all_linear && !sys->drag && sys->grav_mode != 2 && !sys->gain && !sys->force_general;
 }
 
 extern "C" int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* sys, int32_t* out) {

@@ -18,9 +18,27 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
                                                                                              Y_out, save_every); \
   }
 #define CRB_LIN2(UCV, IMPV) CRB_LIN2N(UCV, IMPV, false)
+  const bool nc = !(plan->contiguous && plan->p_act == plan->p);
+  if (sys->grav_mode == 1) {  // slot-space gravity: stage-by-stage kernel (the force is nonlinear in the rotations)
+    if (PM || uc) return 1;
+    if constexpr (!PM) {
+#define CRB_FASTG(IMPV, NCV)                                                                                  \
+  {                                                                                                           \
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, IMPV, true, NCV>, bytes, "crb_rk4")) return rc;          \
+    crb_rk4_fast_kernel<M, LV, IMPV, true, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
+                                                                                          Y_out, save_every); \
+  }
+      if (imp && nc) CRB_FASTG(true, true)
+      else if (imp) CRB_FASTG(true, false)
+      else if (nc) CRB_FASTG(false, true)
+      else CRB_FASTG(false, false)
+#undef CRB_FASTG
+    }
+    return 0;
+  }
   // constrained DOFs inside active slots (PINNED root, interior supports ...) or phantom slots: the NC variants
   // (reduced-index table for state I/O, masked right-hand sides); shared mass factors only
-  if (!(plan->contiguous && plan->p_act == plan->p)) {
+  if (nc) {
     if (PM || sys->force_staged) return 1;
     if constexpr (!PM) {
       if (uc && imp) CRB_LIN2N(true, true, true)

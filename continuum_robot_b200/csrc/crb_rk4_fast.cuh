@@ -93,9 +93,30 @@ __device__ __forceinline__ void elem_linear_vals(const double4 c, const double (
   m2 = fma(c.w, qb[2], R);
 }
 
-// a <- M^-1 (-K w + impulse(t));  `w` holds the stage positions on entry, accelerations on exit.
+// Slot-space gravity constants of a lane (gravity_forces.py:97-146 in REDUCED indices; contiguous plans):
+// half mass of the pseudo-segment between slot s - 1 and s, and of the tail pseudo-segment whose end node falls
+// off the reduced vector.
+template <int M>
+struct FastGrav {
+  double gl[M], gt[M];
+  double gx, gy;
+};
+template <int M>
+__device__ __forceinline__ void fast_grav_load(FastGrav<M>& Gv, const KPlan& P, const crb_system_t& S, int member, int s0) {
+  const long long fo = S.force_shared ? 0ll : (long long)member * P.p;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    Gv.gl[j] = S.grav[2 * (fo + s0 + j)];
+    Gv.gt[j] = S.grav[2 * (fo + s0 + j) + 1];
+  }
+  Gv.gx = S.gx;
+  Gv.gy = S.gy;
+}
+
+// a <- M^-1 (-K w + gravity(w) + impulse(t));  `w` holds the stage positions on entry, accelerations on exit.
 template <int M, int LV, bool IMP, typename CT>
-__device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], double t, const double (*uc)[3] = nullptr) {
+__device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], double t, const double (*uc)[3] = nullptr,
+                                           const FastGrav<M>* gv = nullptr) {
   constexpr int G = 1 << LV;
   double qh[3];
 #pragma unroll
@@ -120,6 +141,28 @@ __device__ __forceinline__ void fast_accel(const CT& C, double (&w)[M][3], doubl
     b[0][j][0] = fu[j] - fu[j + 1];
     b[0][j][1] = V[j] - V[j + 1];
     b[0][j][2] = -(m2[j] + m1[j + 1]);
+  }
+  if (gv) {  // pseudo-segment j joins slot j - 1 (left neighbour's last slot for j = 0) and slot j
+    double fa[M + 1], ft[M + 1];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double pl = (j == 0) ? qh[2] : w[j == 0 ? 0 : j - 1][2];
+      grav_pair(0.5 * (pl + w[j][2]), gv->gl[j], gv->gx, gv->gy, fa[j], ft[j]);  // zero half mass: no segment
+    }
+    fa[M] = shfl_down_d(fa[0], 1, G);
+    ft[M] = shfl_down_d(ft[0], 1, G);
+    if (C.g == G - 1) { fa[M] = 0.0; ft[M] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      b[0][j][0] += fa[j] + fa[j + 1];
+      b[0][j][1] += ft[j] + ft[j + 1];
+      if (gv->gt[j] != 0.0) {
+        double ta, tt;
+        grav_pair(w[j][2], gv->gt[j], gv->gx, gv->gy, ta, tt);
+        b[0][j][0] += ta;
+        b[0][j][1] += tt;
+      }
+    }
   }
   if (IMP && C.imp_local >= 0 && t < C.imp_dur) {
 #pragma unroll
@@ -212,26 +255,32 @@ __device__ __forceinline__ void fast_ctx_impulse(CT& C, const crb_system_t& S, i
   if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
 }
 
-template <int M, int LV, bool IMP>
+// GRAV: slot-space gravity (config 1 as an ensemble: linear beams under gravity; the force depends on the stage
+// positions only, so the Nystrom form still applies).  NC: see FastCtx.
+template <int M, int LV, bool IMP, bool GRAV = false, bool NC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h,
                     int nsteps, double* __restrict__ Y, int save_every) {
   extern __shared__ __align__(16) double smem[];
-  typedef FastCtx<M> Ctx;
+  typedef FastCtx<M, 0, 0, 0, NC> Ctx;
   Ctx C;
   const int s0 = fast_ctx_init<M, LV, false>(C, P, S, S.mfac, smem);
   if (IMP) fast_ctx_impulse<M>(C, S, s0);
+  FastGrav<M> Gv;
+  if (GRAV) fast_grav_load<M>(Gv, P, S, C.member, s0);
 
-  // contiguous plan: the lane's 3M position DOFs are consecutive in the reduced vector
+  // reduced index of own DOF (j, d): consecutive on contiguous plans without phantom slots, else the plan's table
   const int n = C.n;
-  double* xq = X + (long long)C.member * 2 * n + 3 * s0;
+  auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  double* xm = X + (long long)C.member * 2 * n;
   double Q0[M][3], v[M][3], Sa[M][3], Aa[M][3], w[M][3];
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      w[j][d] = xq[3 * j + d];
-      v[j][d] = xq[n + 3 * j + d];
+      const int r = rix(j, d);
+      w[j][d] = (!NC || r >= 0) ? xm[r] : 0.0;
+      v[j][d] = (!NC || r >= 0) ? xm[n + r] : 0.0;
       Q0[j][d] = fma(0.5 * h, v[j][d], w[j][d]);
     }
   const double hh = 0.5 * h, h6 = h / 6.0, hq = 0.25 * h * h, hs = 0.5 * h * h, hx = h * h / 6.0;
@@ -242,7 +291,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
       const double ts = t + (st == 0 ? 0.0 : (st == 3 ? h : hh));
-      fast_accel<M, LV, IMP>(C, w, ts);
+      fast_accel<M, LV, IMP>(C, w, ts, nullptr, GRAV ? &Gv : nullptr);
       if (st == 0) {  // a1: next input q + h/2 v
 #pragma unroll
         for (int j = 0; j < M; ++j)
@@ -289,13 +338,16 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
       }
     }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* yq = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n + 3 * s0;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          yq[3 * j + d] = w[j][d];
-          yq[n + 3 * j + d] = v[j][d];
+          const int r = rix(j, d);
+          if (!NC || r >= 0) {
+            ym[r] = w[j][d];
+            ym[n + r] = v[j][d];
+          }
         }
     }
   }
@@ -304,8 +356,11 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        xq[3 * j + d] = w[j][d];
-        xq[n + 3 * j + d] = v[j][d];
+        const int r = rix(j, d);
+        if (!NC || r >= 0) {
+          xm[r] = w[j][d];
+          xm[n + r] = v[j][d];
+        }
       }
   }
 }

@@ -224,3 +224,47 @@ def test_paired_linear_kernel_any_boundary_conditions(N, bcs):
 
             want = bo.rk4_solve(f, x0[i], 0.0, h, steps)
             assert block_err(fast[i], want, n) < 1e-9, (uc, imp, i)
+
+
+@pytest.mark.parametrize("N,B,with_imp", [(10, 33, True), (32, 19, False), (6, 40, True), (13, 5, True), (64, 3, False)])
+def test_fast_kernel_with_gravity_matches_general_kernel_and_oracle(N, B, with_imp):
+    """Linear cantilevers under (tilted) gravity with per-member stiffness -- config 1 as an ensemble -- run on the
+    stage-by-stage fast kernel with the slot-space gravity term; vs the general kernel (<= 1e-11) and the oracle
+    (<= 1e-9), with and without the tip impulse, element counts with and without phantom slots."""
+    import torch
+
+    from continuum_robot_b200 import TipImpulse
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    par = _uniform_par(N, B, seed=70 + N)
+    et, bc = np.zeros(N, dtype=int), np.array([1] + [0] * N)
+    gvec = (1.3, -9.81, 0.0)
+    beam = make_gpu_beam(par, et, bc, 0.0, True, gvec)
+    n = beam.n_free
+    rng = np.random.default_rng(N)
+    x0 = np.concatenate([1e-4 * rng.standard_normal((B, n)), 1e-2 * rng.standard_normal((B, n))], axis=1)
+    amp = rng.uniform(0.05, 0.5, B)
+    h, steps = 2e-6, 150
+    imp = TipImpulse(torch.from_numpy(amp).cuda(), duration=60.5 * h) if with_imp else None
+    out = []
+    for general in (False, True):
+        beam.force_general_kernels = general
+        X = torch.from_numpy(x0).cuda()
+        rk4_steps(beam, X, 0.0, h, steps, u=imp)
+        out.append(X.cpu().numpy())
+    beam.force_general_kernels = False
+    assert max(block_err(out[0][i], out[1][i], n) for i in range(B)) < 1e-11
+    for i in (0, B - 1):
+        p = par[i]
+        orc = bo.BeamOracle(bo.BeamSpec(p[:, 0], p[:, 1], p[:, 2], p[:, 3], p[:, 4], et, bc[:N], p[:, 5], p[:, 6]),
+                            bo.ForceSpec(0.0, False, gvec, True))
+
+        def f(t, x, i=i):
+            u = np.zeros(n)
+            if with_imp and t < 60.5 * h:
+                u[n - 2] = amp[i]
+            return orc.rhs(t, x, u)
+
+        want = bo.rk4_solve(f, x0[i], 0.0, h, steps)
+        assert block_err(out[0][i], want, n) < 1e-9
