@@ -38,6 +38,9 @@ ALG_BYTES_PER_ELEMENT_STEP = 96.0  # q,v (2) x 3 DOF x 8 B x (read + write), SUR
 WORKLOAD = "cfg3: 65536-member linear beam ensemble (random per-element E, random IC), 32 elements, fixed-step RK4 FP64"
 
 
+_OUT = sys.stdout
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -106,7 +109,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -321,7 +324,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_port_throughput(args.cpu_steps, members_per_core=1, n_elements=N)
             line["cpu_baseline"] = {"value": v, "unit": "element-steps/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -341,6 +344,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there under torchrun) are sent to stderr, the JSON line goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
