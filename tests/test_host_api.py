@@ -462,3 +462,34 @@ def test_lqr_entry_points_validate_arguments_on_the_host():
     assert lib.crb_dense_matrices_batched(C.byref(p), one, 1, bytes(4), bytes([2, 0, 0, 0, 0]), one, None, None) == -1
     assert "mismatch" in err()
     assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.gain_stride.offset == C.sizeof(L.CrbSystem) - 8
+
+
+def test_header_is_plain_c_and_the_library_serves_a_c_client(tmp_path):
+    """include/crb.h compiles as C99 (no C++ / torch types in the boundary) and a plain-C program linked against
+    libcrb.so gets the same answers from the host-only entry points as the ctypes binding."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    L = _lib()
+    lib = L.load()
+    libdir = os.path.dirname(L.LIB_PATH)
+    exe = str(tmp_path / "host_smoke")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "host_smoke.c"), "-o", exe,
+                           "-L" + libdir, "-l:libcrb.so", "-Wl,-rpath," + libdir, "-Wl,--allow-shlib-undefined"])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    vals = dict(line.split(" ", 1) for line in out.strip().splitlines())
+    assert int(vals["version"]) == L.CRB_VERSION
+    rc, p = _plan(4, [1, 0, 0, 0, 0])
+    assert vals["plan"] == f"n_free {p.n_free} m {p.m} g {p.g} p {p.p} contiguous {p.contiguous}"
+    par = np.tile(np.array([0.25, 75e9, 4.908738521234052e-10, 6450.0, 7.853981633974483e-05, 0.007853981633974483, 0.82]), (4, 1))
+    M, K = np.zeros((12, 12)), np.zeros((12, 12))
+    assert lib.crb_dense_matrices(C.byref(p), par.ctypes.data_as(C.c_void_p), bytes(4), bytes([1, 0, 0, 0, 0]),
+                                  M.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p)) == 0
+    serial = lambda A: float(sum(float(A[i, i]) for i in range(12)))  # same left-to-right order as the C loop
+    assert float(vals["trace_M"]) == serial(M) and float(vals["trace_K"]) == serial(K)
+    assert float(vals["asym_K"]) == 0.0
+    assert vals["bad_bc"].startswith("rc -1") and int(vals["bad_bc"].split()[-1]) > 10
