@@ -210,3 +210,27 @@ def test_staged_per_member_gains_equal_the_global_memory_path(slots):
     beam.force_staged_kernels = False
     assert np.isfinite(out[0]).all()
     assert np.array_equal(out[0], out[1])
+
+
+def test_host_pipeline_with_per_member_gains():
+    """Host-resident state through crb_rk4_host: the chunked pipeline slices the per-member gains together with the
+    per-member factor sets (crb_system_slice); bitwise equal to the device-resident rollout."""
+    from continuum_robot_b200 import FullStateLinear, HostPipeline, TipImpulse
+    from continuum_robot_b200.integrate import rk4_steps
+
+    B, N, h, steps = 83, 6, 5e-6, 60
+    par, et, bc = design_ensemble(B, N, seed=9)
+    beam = make_gpu_beam(par, et, bc, 0.0, True)
+    n = beam.n_free
+    rng = np.random.default_rng(2)
+    gain = torch.from_numpy(np.concatenate([50.0 * rng.standard_normal((B, n, n)), 0.05 * rng.standard_normal((B, n, n))], axis=2)).cuda()
+    amp = torch.from_numpy(rng.uniform(1.0, 5.0, B)).cuda()
+    x0 = np.concatenate([1e-4 * rng.standard_normal((B, n)), 1e-2 * rng.standard_normal((B, n))], axis=1)
+    ctrl, imp = FullStateLinear(gain), TipImpulse(amp, duration=1e-4)
+    X = torch.from_numpy(x0).cuda()
+    rk4_steps(beam, X, 0.0, h, steps, u=imp, controller=ctrl)
+    xh = torch.from_numpy(x0.copy()).pin_memory()
+    pipe = HostPipeline(beam, B, chunk_members=24, u=imp, controller=ctrl)
+    pipe.run(xh, 0.0, h, steps)
+    pipe.synchronize()
+    assert np.array_equal(xh.numpy(), X.cpu().numpy())
