@@ -139,3 +139,48 @@ def test_config4_full_size_member_independence():
     assert torch.equal(part.nfev, full.nfev[idx]) and torch.equal(part.naccept, full.naccept[idx])
     assert torch.equal(part.h_last, full.h_last[idx])
     assert len(set(full.nfev.tolist())) > 10  # the ensemble really is ragged
+
+
+def test_config5_full_shard_of_a_design_ensemble():
+    """One GPU's shard of config 5 (131,072 members) as a DESIGN ensemble: 2,048 designs synthesised on the device
+    (crb_dense_matrices_batched + crb_lqr_gains), each rolled out 64 times with its own gain (staged-gain kernel).
+    Size-independent properties: every synthesis succeeds with a small Riccati residual, replicas of a design are
+    bitwise identical wherever they sit in the ensemble, and the closed loop damps the disturbance."""
+    from continuum_robot_b200 import BatchedLinearQuadraticRegulator, FullStateLinear, TipImpulse
+    from continuum_robot_b200 import ensembles as ens
+    from continuum_robot_b200.dynamic_beam import BatchedDynamicEulerBernoulliBeam
+    from continuum_robot_b200.force_params import ForceParams
+    from continuum_robot_b200.integrate import rk4_steps
+
+    # h: the fastest closed loop of the 2,048 designs (stiff, light tail of the distribution) needs h < 4.7e-6
+    D, rep, N, h = 2048, 64, 6, 2e-6
+    B = D * rep
+    rng = np.random.default_rng(555)
+    m = ens.material()
+    par = np.zeros((D, N, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 4] = m["length"], m["I"], m["A"]
+    par[:, :, 1] = m["E"] * np.exp(0.3 * rng.standard_normal((D, 1)))
+    par[:, :, 3] = m["rho"] * np.exp(0.2 * rng.standard_normal((D, 1)))
+    par[:, :, 5], par[:, :, 6] = m["wetted_area"], m["drag_coef"]
+    designs = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["linear"] * N}, ForceParams(enable_gravity_effects=True))
+    n = designs.n_free
+    Q = torch.diag(torch.cat([torch.full((n,), 100.0), torch.full((n,), 10.0)])).to("cuda", torch.float64)
+    R = torch.eye(n, dtype=torch.float64, device="cuda")
+    Md, Kd = designs.dense_matrices()
+    lqr = BatchedLinearQuadraticRegulator(Kd, Md, Q, R)
+    gain = lqr.compute_gain_matrix()
+    assert int(lqr.status.abs().sum()) == 0 and float(lqr.residual.max()) < 1e-5
+    beam = BatchedDynamicEulerBernoulliBeam({"params": np.tile(par, (rep, 1, 1)), "type": ["linear"] * N},
+                                            ForceParams(enable_gravity_effects=True))
+    beam.create_system_func()
+    beam.create_input_func()
+    amp = torch.from_numpy(np.tile(rng.uniform(1.0, 20.0, D), rep)).cuda()
+    ctrl = FullStateLinear(gain.repeat(rep, 1, 1))
+    X = torch.zeros(B, 2 * n, dtype=torch.float64, device="cuda")
+    rk4_steps(beam, X, 0.0, h, 5200, u=TipImpulse(amp, duration=0.01), controller=ctrl)
+    assert bool(torch.isfinite(X).all())
+    Xr = X.view(rep, D, 2 * n)
+    assert bool((Xr == Xr[0:1]).all())
+    peak = float(X[:, :n].abs().max())
+    rk4_steps(beam, X, 5200 * h, h, 4000, controller=ctrl)  # impulse over: the regulator pulls the state back
+    assert float(X[:, n:].abs().max()) < 10.0 and float(X[:, :n].abs().max()) <= 1.5 * peak
