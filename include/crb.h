@@ -251,8 +251,8 @@ int crb_dense_matrices_batched(const crb_plan_t* plan, const double* params, int
 /* Device.  Batched LQR synthesis: replaces LinearQuadraticRegulator.compute_gain_matrix
  * (control/linear_quadratic_regulator.py:84-191; `ct.lqr(A, B, Q, R)` at :180) for an ENSEMBLE of designs.
  * Per member: A = [[0, I], [-M^-1 K, 0]], B = [[0], [M^-1]] (:84-146), the stabilising solution S of
- * A^T S + S A - S B R^-1 B^T S + Q = 0 (matrix sign function of the Hamiltonian + `refine_passes` exact
- * correction solves, 1 recommended), gain = R^-1 B^T S.
+ * A^T S + S A - S B R^-1 B^T S + Q = 0 (matrix sign function of the Hamiltonian + `refine_passes` Newton-Kleinman
+ * correction steps, 1 recommended), gain = R^-1 B^T S.
  *   M_beam, K_beam  device [B or 1, n, n] (m_shared / k_shared = 1: one matrix for all members)
  *   Q device [2n,2n], R device [n,n] (shared);  gain_out device [B, n, 2n];  S_out device [B, 2n, 2n] or NULL
  *   residual_out device [B] or NULL: ||A^T S + S A - S G S + Q||_F / ||Q||_F of the returned S
