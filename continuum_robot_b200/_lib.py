@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 104
+CRB_VERSION = 105
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -66,6 +66,7 @@ class CrbSystem(C.Structure):
         ("shared_op", C.c_void_p),
         ("shared_op_doubles", C.c_int64),
         ("gain_stride", C.c_int64),
+        ("member_op", C.c_void_p),
     ]
 
 
@@ -110,6 +111,8 @@ _SIGNATURES = {
     "crb_dense_matrices_batched": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "crb_lqr_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "crb_member_operators": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crb_lqr_gains": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),

@@ -204,6 +204,8 @@ static int check_system(const char* who, const crb_plan_t* plan, const crb_syste
   if (sys->gain_stride != 0 && sys->gain_stride != 2ll * plan->n_free * plan->n_free)
     return fail(CRB_E_ARG, "%s: gain_stride must be 0 (shared gain) or n*2n = %lld, got %lld", who,
                 2ll * plan->n_free * plan->n_free, (long long)sys->gain_stride);
+  if (sys->member_op && (!sys->gain || sys->gain_stride == 0))
+    return fail(CRB_E_ARG, "%s: member_op needs the per-member gains it was built from (gain, gain_stride)", who);
   if (sys->gain_stride != 0 && (sys->gain_frag || sys->shared_op))
     return fail(CRB_E_ARG, "%s: per-member gains (gain_stride != 0) exclude gain_frag / shared_op", who);
   if (sys->imp_amp && (sys->imp_dof < 0 || sys->imp_dof >= plan->n_free))
@@ -274,6 +276,8 @@ static int rk4_dispatch(const crb_plan_t* plan, const crb_system_t* sys, double*
   int rc;
   if (crb_shared_eligible(plan, sys)) {  // one design + gain shared by all members: dense tensor-core contraction
     rc = crb_launch_rk4_shared(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
+  } else if (crb_dense_eligible(plan, sys)) {  // linear designs with one gain per member: dense operator per member
+    rc = crb_launch_rk4_dense(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream);
   } else {
     rc = rk4_fast_eligible(plan, sys) ? crb_launch_rk4_fast(plan, sys, X, t0, h, nsteps, Y_out, save_every, stream) : 1;
     if (rc == 1)  // not eligible, or shape not instantiated in the fast family

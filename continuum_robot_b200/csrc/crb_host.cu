@@ -109,6 +109,7 @@ extern "C" int crb_system_slice(const crb_plan_t* plan, const crb_system_t* sys,
   if (sys->f_ext) out->f_ext = sys->f_ext + lo * n;
   if (sys->imp_amp) out->imp_amp = sys->imp_amp + lo;
   if (sys->gain && sys->gain_stride) out->gain = sys->gain + lo * sys->gain_stride;
+  if (sys->member_op) out->member_op = sys->member_op + lo * n * (3 * n + 1);
   return 0;
 }
 

@@ -110,6 +110,9 @@ inline unsigned crb_pick_profile(unsigned need) {
 
 int crb_fast_members_per_sm(int members_per_warp);  // resident members per SM of the fast RK4 family (crb_rk4_fast.cu)
 bool crb_shared_eligible(const crb_plan_t* plan, const crb_system_t* sys);  // crb_shared.cu
+bool crb_dense_eligible(const crb_plan_t* plan, const crb_system_t* sys);   // crb_rk4_dense.cu
+int crb_launch_rk4_dense(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
+                         double* Y_out, int save_every, cudaStream_t stream);
 int crb_launch_rk4_shared(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
                           double* Y_out, int save_every, cudaStream_t stream);
 // launchers implemented in their own translation units (parallel nvcc builds)

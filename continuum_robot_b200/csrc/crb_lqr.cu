@@ -622,6 +622,65 @@ __global__ void crb_dense_batched_kernel(int N, int n, int n_sets, const double*
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// per-member closed-loop operators (one block per member, grid-stride)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CRB_LQR_THREADS, 3)
+crb_member_operator_kernel(int n, int n_members, const double* __restrict__ Mb, int m_shared, const double* __restrict__ Kb,
+                           int k_shared, const double* __restrict__ gain, const double* __restrict__ ref,
+                           double* __restrict__ op, int* __restrict__ status) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, n2 = 2 * n, RL = 3 * n + 1;
+  double* sm = smem;                    // n x n: M^-1
+  double* col = sm + n * n;             // 2 (n + 16)
+  double* prow = col + 2 * (n + 16);    // 2 (n + 16)
+  double* red = prow + 2 * (n + 16);    // 32
+  double* gr = red + 32;                // n: gain . ref
+  int* piv = reinterpret_cast<int*>(gr + n);
+  int* rinv = piv + n;
+  int* pinfo = rinv + n;
+  for (int member = blockIdx.x; member < n_members; member += gridDim.x) {
+    const double* M = Mb + (m_shared ? 0ll : (long long)member * n * n);
+    const double* K = Kb + (k_shared ? 0ll : (long long)member * n * n);
+    const double* G = gain + (long long)member * n * n2;
+    double* out = op + (long long)member * n * RL;
+    __syncthreads();
+    for (int k = tid; k < n * n; k += CRB_LQR_THREADS) sm[k] = M[k];
+    for (int i = tid; i < n; i += CRB_LQR_THREADS) {
+      double acc = 0.0;
+      if (ref)
+        for (int c = 0; c < n2; ++c) acc = fma(G[i * n2 + c], ref[c], acc);
+      gr[i] = acc;
+    }
+    __syncthreads();
+    bool singular;
+    gj_inverse_any(sm, n, col, prow, piv, rinv, pinfo, red, &singular);
+    if (tid == 0) status[member] = singular ? 1 : 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int idx = tid; idx < n * RL; idx += CRB_LQR_THREADS) {
+      const int l = idx / RL, j = idx - l * RL;
+      double v;
+      if (singular) {
+        v = qnan;
+      } else if (j < n2) {  // -M^-1 (K + G_q) | -M^-1 G_v
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double g = G[k * n2 + j] + (j < n ? K[k * n + j] : 0.0);
+          acc = fma(sm[l * n + k], g, acc);
+        }
+        v = -acc;
+      } else if (j < 3 * n) {  // M^-1
+        v = sm[l * n + (j - n2)];
+      } else {  // M^-1 G ref
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc = fma(sm[l * n + k], gr[k], acc);
+        v = acc;
+      }
+      out[idx] = v;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int crb_dense_matrices_batched(const crb_plan_t* plan, const double* params, int32_t n_param_sets,
@@ -708,5 +767,20 @@ extern "C" int crb_lqr_gains(int32_t n, int32_t n_members, const double* M_beam,
   crb_lqr_kernel<<<grid, CRB_LQR_THREADS, lqr_smem_bytes(n), static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_lqr_gains: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int crb_member_operators(int32_t n, int32_t n_members, const double* M_beam, int32_t m_shared, const double* K_beam,
+                                    int32_t k_shared, const double* gain, const double* ref, double* op_out,
+                                    int32_t* status_out, void* stream) {
+  if (!M_beam || !K_beam || !gain || !op_out || !status_out) return crb_fail(CRB_E_ARG, "crb_member_operators: null argument");
+  if (n < 1 || n > 32) return crb_fail(CRB_E_LIMIT, "crb_member_operators: n = %d free DOFs outside [1, 32] (one lane per DOF)", n);
+  if (n_members < 1) return crb_fail(CRB_E_ARG, "crb_member_operators: n_members must be positive");
+  const size_t bytes = sizeof(double) * ((size_t)n * n + 4 * (n + 16) + 32 + n) + sizeof(int) * (2 * n + 8);
+  const int grid = n_members < 148 * 6 ? n_members : 148 * 6;
+  crb_member_operator_kernel<<<grid, CRB_LQR_THREADS, bytes, static_cast<cudaStream_t>(stream)>>>(
+      n, n_members, M_beam, m_shared, K_beam, k_shared, gain, ref, op_out, status_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_member_operators: %s", cudaGetErrorString(e));
   return 0;
 }

@@ -446,6 +446,7 @@ class BatchedDynamicEulerBernoulliBeam:
         sib.force_registry, sib.input_registry = self.force_registry, self.input_registry
         sib._forces_func, sib.system_func, sib.input_func = self._forces_func, self.system_func, self.input_func
         sib.force_general_kernels, sib.force_staged_kernels = self.force_general_kernels, self.force_staged_kernels
+        sib.use_member_operators = getattr(self, "use_member_operators", True)
         return sib
 
     # -- state maps -----------------------------------------------------------------------------
@@ -545,10 +546,18 @@ class BatchedDynamicEulerBernoulliBeam:
                 gdev = dev64(gain, (B, n, 2 * n), "gain")
                 s.gain = gdev.data_ptr() + 8 * lo * n * 2 * n
                 s.gain_stride = n * 2 * n
+                rdev = None
                 if ref is not None:
                     if not isinstance(ref, torch.Tensor):
                         ref = torch.as_tensor(np.asarray(ref, dtype=np.float64))
-                    s.ref = dev64(ref.reshape(-1), (2 * n,), "reference").data_ptr()
+                    rdev = dev64(ref.reshape(-1), (2 * n,), "reference")
+                    s.ref = rdev.data_ptr()
+                # all-linear designs: the closed loop of every member as one dense operator (crb_member_operators)
+                if (getattr(self, "use_member_operators", True) and self._all_linear and drag is None and u_const is None and f_ext is None and n <= 32
+                        and self.n_elements <= 16 and not self.force_general_kernels and not self.force_staged_kernels):
+                    op = self._member_operators(gdev, rdev)
+                    keep.append(op)
+                    s.member_op = op.data_ptr() + 8 * lo * n * (3 * n + 1)
                 return s, keep
             if gain.ndim != 2 or tuple(gain.shape) != (n, 2 * n):
                 raise ValueError(f"Gain matrix must have shape ({n}, {2 * n}), got {tuple(gain.shape)}")
@@ -588,6 +597,28 @@ class BatchedDynamicEulerBernoulliBeam:
                 s.shared_op = blob.data_ptr()
                 s.shared_op_doubles = blob.numel()
         return s, keep
+
+    def _member_operators(self, gdev, rdev):
+        """[B, n, 3n+1] closed-loop operators of the members for the per-member gains ``gdev`` (crb_member_operators);
+        cached on the identity and version of the gain / reference tensors."""
+        torch = _torch()
+        key = (gdev.data_ptr(), gdev._version, None if rdev is None else (rdev.data_ptr(), rdev._version))
+        cached = getattr(self, "_member_op_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        B, n = int(gdev.shape[0]), self.n_free
+        M, K = self.dense_matrices()
+        op = torch.empty((B, n, 3 * n + 1), dtype=torch.float64, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().crb_member_operators(
+                n, B, M.data_ptr(), int(M.shape[0] == 1), K.data_ptr(), int(K.shape[0] == 1), gdev.data_ptr(),
+                rdev.data_ptr() if rdev is not None else None, op.data_ptr(), status.data_ptr(), self._stream())
+        _lib.check(rc, ValueError)
+        if bool(status.any().item()):
+            raise ValueError("Mass matrix is singular and cannot be inverted")
+        self._member_op_cache = (key, op, gdev, rdev)  # tensors kept alive so that their addresses stay unique
+        return op
 
     def _shared_operator(self, gdev, rdev, grav_xy, imp_dof: int):
         """Device copy of the shared-operator blob for (gain, ref, gravity vector, impulse DOF); cached on

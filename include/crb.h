@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 104
+#define CRB_VERSION 105
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 #define CRB_LQR_MAX_ELEMENTS 128 /* crb_dense_matrices_batched: elements per beam */
@@ -118,6 +118,11 @@ typedef struct crb_system_t {
    * n*2n = `gain` is [B,n,2n], one design-specific gain per member (crb_lqr_gains); gain_frag / shared_op
    * must be NULL then */
   int64_t gain_stride;
+  /* per-member closed-loop operators (crb_member_operators) for ensembles of linear designs with one gain per
+   * member: [B, n, 3n+1] rows [ -M^-1 (K + G_q) | -M^-1 G_v | M^-1 | M^-1 G ref ], or NULL.  When set (with
+   * gain / gain_stride / ref describing the same feedback), crb_rk4 evaluates the closed-loop RHS as ONE dense
+   * product per member (one lane per free DOF, the operator row in registers). */
+  const double* member_op;
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */
@@ -261,6 +266,15 @@ int crb_dense_matrices_batched(const crb_plan_t* plan, const double* params, int
  *   workspace device, crb_lqr_workspace_bytes(n, B) bytes.  n <= 42 (the 4n x 4n Hamiltonian lives in
  *   shared memory). */
 int crb_lqr_workspace_bytes(int32_t n, int32_t n_members, size_t* out);
+/* Device.  Dense closed-loop operator of every member of a linear design ensemble under state feedback
+ * u_c = gain (ref - x) (control/full_state_linear.py:58 inside examples/lqr_control.py:95-111):
+ *   a = -M^-1 K q + M^-1 (f_gravity(q) + impulse(t) + gain (ref - x))
+ *     = [ -M^-1 (K + G_q) | -M^-1 G_v ] [q; v] + M^-1 f_gravity(q) + impulse(t) M^-1 e_k + M^-1 G ref.
+ * M_beam, K_beam device [B or 1, n, n]; gain device [B, n, 2n]; ref device [2n] or NULL;
+ * op_out device [B, n, 3n+1]; n <= 32.  status_out device int32 [B]: 1 where M is singular. */
+int crb_member_operators(int32_t n, int32_t n_members, const double* M_beam, int32_t m_shared, const double* K_beam,
+                         int32_t k_shared, const double* gain, const double* ref, double* op_out,
+                         int32_t* status_out, void* stream);
 int crb_lqr_gains(int32_t n, int32_t n_members, const double* M_beam, int32_t m_shared, const double* K_beam,
                   int32_t k_shared, const double* Q, const double* R, int32_t refine_passes, double* gain_out,
                   double* S_out, double* residual_out, int32_t* status_out, void* workspace,

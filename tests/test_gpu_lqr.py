@@ -202,6 +202,7 @@ def test_staged_per_member_gains_equal_the_global_memory_path(slots):
     x0 = np.concatenate([1e-4 * rng.standard_normal((B, n)), 1e-2 * rng.standard_normal((B, n))], axis=1)
     amp = torch.from_numpy(rng.uniform(1.0, 5.0, B)).cuda()
     out = []
+    beam.use_member_operators = False  # banded kernels only (the dense per-member operator path is tested below)
     for staged_off in (False, True):
         beam.force_staged_kernels = staged_off
         X = torch.from_numpy(x0).cuda()
@@ -210,6 +211,16 @@ def test_staged_per_member_gains_equal_the_global_memory_path(slots):
     beam.force_staged_kernels = False
     assert np.isfinite(out[0]).all()
     assert np.array_equal(out[0], out[1])
+    # dense per-member closed-loop operators (crb_member_operators + crb_rk4_dense_kernel): same physics, different
+    # arithmetic (dense M^-1 instead of the banded factorisation)
+    beam.use_member_operators = True
+    X = torch.from_numpy(x0).cuda()
+    Y = torch.zeros(steps // 40, B, 2 * n, dtype=torch.float64, device="cuda")
+    rk4_steps(beam, X, 0.0, h, steps, u=TipImpulse(amp, duration=3e-4), controller=FullStateLinear(gain, reference=ref),
+              Y_out=Y, save_every=40)
+    dense = X.cpu().numpy()
+    assert max(block_err(dense[i], out[0][i], n) for i in range(B)) < 1e-10
+    assert np.array_equal(Y[-1].cpu().numpy(), dense)
 
 
 def test_host_pipeline_with_per_member_gains():
