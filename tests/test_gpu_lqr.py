@@ -245,3 +245,51 @@ def test_host_pipeline_with_per_member_gains():
     pipe.run(xh, 0.0, h, steps)
     pipe.synchronize()
     assert np.array_equal(xh.numpy(), X.cpu().numpy())
+
+
+@pytest.mark.parametrize("N,bc0,gravity,with_ref", [(1, 1, True, False), (3, 1, False, True), (4, 2, True, True), (8, 1, True, False),
+                                                    (10, 1, False, False), (10, 2, True, True)])
+def test_dense_member_operator_path_matches_oracle(N, bc0, gravity, with_ref):
+    """crb_member_operators + crb_rk4_dense_kernel (one dense closed-loop operator per member) for n = 3 ... 31 free
+    DOFs, FIXED and PINNED roots, gravity on / off, non-zero reference, per-member mass and stiffness: vs the oracle
+    stepping the same closed loops (<= 1e-9), saved frames included."""
+    from continuum_robot_b200 import FullStateLinear, TipImpulse
+    from continuum_robot_b200.integrate import rk4_steps
+    from oracle import beam_oracle as bo
+
+    B, h, steps = 11, 2e-6, 150
+    par, et, bc = design_ensemble(B, N, seed=300 + N, bc0=bc0)
+    gvec = (0.7, -9.81, 0.0)
+    beam = make_gpu_beam(par, et, bc, 0.0, gravity, gvec)
+    n = beam.n_free
+    rng = np.random.default_rng(N)
+    gain = np.concatenate([50.0 * rng.standard_normal((B, n, n)), 0.05 * rng.standard_normal((B, n, n))], axis=2)
+    ref = 1e-3 * rng.standard_normal(2 * n) if with_ref else None
+    amp = rng.uniform(1.0, 5.0, B)
+    x0 = np.concatenate([1e-4 * rng.standard_normal((B, n)), 1e-2 * rng.standard_normal((B, n))], axis=1)
+    ctrl = FullStateLinear(torch.from_numpy(gain).cuda(), reference=torch.from_numpy(ref).cuda() if with_ref else None)
+    X = torch.from_numpy(x0).cuda()
+    Y = torch.zeros(steps // 50, B, 2 * n, dtype=torch.float64, device="cuda")
+    rk4_steps(beam, X, 0.0, h, steps, u=TipImpulse(torch.from_numpy(amp).cuda(), duration=80.5 * h), controller=ctrl,
+              Y_out=Y, save_every=50)
+    got, frames = X.cpu().numpy(), Y.cpu().numpy()
+    for i in (0, B // 2, B - 1):
+        p = par[i]
+        ob = bo.BeamOracle(bo.BeamSpec(p[:, 0], p[:, 1], p[:, 2], p[:, 3], p[:, 4], et, bc[:N], p[:, 5], p[:, 6]),
+                           bo.ForceSpec(0.0, False, gvec, gravity))
+
+        def f(t, x, i=i, ob=ob):
+            u = bo.full_state_feedback(gain[i], x, ref if with_ref else np.zeros(2 * n)).copy()
+            if t < 80.5 * h:
+                u[n - 2] += amp[i]
+            return ob.rhs(t, x, u)
+
+        want, wf = bo.rk4_solve(f, x0[i], 0.0, h, steps, save_every=50)
+        assert block_err(got[i], want, n) < 1e-9, (i, block_err(got[i], want, n))
+        assert max(block_err(frames[k, i], wf[k], n) for k in range(len(wf))) < 1e-9
+    # the dense path was the one that ran: switching it off changes the rounding, not the physics
+    beam.use_member_operators = False
+    X2 = torch.from_numpy(x0).cuda()
+    rk4_steps(beam, X2, 0.0, h, steps, u=TipImpulse(torch.from_numpy(amp).cuda(), duration=80.5 * h), controller=ctrl)
+    b2 = X2.cpu().numpy()
+    assert not np.array_equal(b2, got) and max(block_err(got[i], b2[i], n) for i in range(B)) < 1e-10

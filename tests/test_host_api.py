@@ -461,7 +461,10 @@ def test_lqr_entry_points_validate_arguments_on_the_host():
     assert lib.crb_dense_matrices_batched(C.byref(p), one, 0, bytes(4), bc, one, None, None) == -1
     assert lib.crb_dense_matrices_batched(C.byref(p), one, 1, bytes(4), bytes([2, 0, 0, 0, 0]), one, None, None) == -1
     assert "mismatch" in err()
-    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.gain_stride.offset == C.sizeof(L.CrbSystem) - 8
+    assert lib.crb_member_operators(18, 4, None, 0, None, 0, None, None, None, None, None) == -1
+    assert lib.crb_member_operators(33, 4, one, 0, one, 0, one, None, one, one, None) == -3 and "one lane per DOF" in err()
+    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.member_op.offset == C.sizeof(L.CrbSystem) - 8
+    assert L.CrbSystem.gain_stride.offset == C.sizeof(L.CrbSystem) - 16
 
 
 def test_header_is_plain_c_and_the_library_serves_a_c_client(tmp_path):
