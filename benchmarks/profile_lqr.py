@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from continuum_robot_b200 import BatchedDynamicEulerBernoulliBeam, BatchedLinearQuadraticRegulator
 from continuum_robot_b200 import ensembles as ens
 
-B, N = int(os.environ.get("LQR_B", 1480)), 6
+B, N = int(os.environ.get("LQR_B", 1480)), int(os.environ.get("LQR_N", 6))
 rng = np.random.default_rng(6)
 m = ens.material()
 par = np.zeros((B, N, 7))

@@ -45,6 +45,7 @@ struct LqrArgs {
   int* status;
   double* ws;
   long long ws_stride;  // doubles per block
+  int big;              // 1: the 4n x 4n work matrix lives in the block's global workspace (it does not fit shared memory)
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -134,7 +135,18 @@ __device__ double gj_inverse(double* a, int m, double* col, double* prow, int* p
       case 3: gj_eliminate<3>(a, m, p, col, prow, ipv); break;
       case 4: gj_eliminate<4>(a, m, p, col, prow, ipv); break;
       case 5: gj_eliminate<5>(a, m, p, col, prow, ipv); break;
-      default: gj_eliminate<6>(a, m, p, col, prow, ipv); break;
+      case 6: gj_eliminate<6>(a, m, p, col, prow, ipv); break;
+      default:  // wider than 192 columns (matrix in global memory): pivot row read from shared memory
+        for (int i = warp; i < m; i += CRB_LQR_THREADS / 32) {
+          double* row = a + (long long)i * m;
+          if (i == p) {
+            for (int j = lane; j < m; j += 32) row[j] = prow[j] * ipv;
+          } else {
+            const double f = -col[i] * ipv;
+            for (int j = lane; j < m; j += 32) row[j] = fma(f, prow[j], row[j]);
+          }
+        }
+        break;
     }
     logdet += log(fabs(pv));
     // the next pivot search reads column p + 1 of the updated matrix
@@ -402,14 +414,16 @@ __device__ void riccati_residual(int n2, const double* A, const double* G, const
 __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int n = a.n, n2 = 2 * n, D = 4 * n, tid = threadIdx.x;
-  double* sm = smem;           // D x D
-  double* col = sm + D * D;        // 2 (D + 16): double-buffered pivot column (register-resident elimination)
+  double* ws = a.ws + (long long)blockIdx.x * a.ws_stride;
+  // D x D work matrix: shared memory up to n = 42, else the tail of the block's global workspace (L2-resident;
+  // the elimination then streams it once per pivot -- a functional path for long beams, not a fast one)
+  double* sm = a.big ? ws + (a.ws_stride - (long long)D * D) : smem;
+  double* col = a.big ? smem : smem + D * D;  // 2 (D + 16): double-buffered pivot column (register-resident elimination)
   double* prow = col + 2 * (D + 16);  // 2 (D + 16): pivot row
   double* red = prow + 2 * (D + 16);  // 32
   int* piv = reinterpret_cast<int*>(red + 32);  // D
   int* rinv = piv + D;             // D
   int* pinfo = rinv + D;           // 4
-  double* ws = a.ws + (long long)blockIdx.x * a.ws_stride;
   double* Z = ws;                 // D^2
   double* A = Z + D * D;          // n2^2 each
   double* G = A + n2 * n2;
@@ -562,11 +576,13 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
   }
 }
 
-inline size_t lqr_smem_bytes(int n) {
+inline size_t lqr_smem_small(int n) {  // everything but the D x D work matrix
   const size_t D = 4 * (size_t)n;
-  return sizeof(double) * (D * D + 4 * (D + 16) + 32) + sizeof(int) * (2 * D + 8);
+  return sizeof(double) * (4 * (D + 16) + 32) + sizeof(int) * (2 * D + 8);
 }
-inline long long lqr_ws_doubles(int n) { return 16ll * n * n + 7 * 4ll * n * n + 3ll * n * n; }
+inline bool lqr_big(int n) { return lqr_smem_small(n) + sizeof(double) * 16 * (size_t)n * n > 227 * 1024; }
+inline size_t lqr_smem_bytes(int n) { return lqr_smem_small(n) + (lqr_big(n) ? 0 : sizeof(double) * 16 * (size_t)n * n); }
+inline long long lqr_ws_doubles(int n) { return 16ll * n * n + 7 * 4ll * n * n + 3ll * n * n + (lqr_big(n) ? 16ll * n * n : 0); }
 
 int lqr_grid(int n, int n_members, int* out) {
   int dev = 0, sms = 0, per_sm = 0;
@@ -718,9 +734,8 @@ extern "C" int crb_dense_matrices_batched(const crb_plan_t* plan, const double* 
 
 static int lqr_check_n(int32_t n, const char* who) {
   if (n < 1) return crb_fail(CRB_E_ARG, "%s: n must be positive", who);
-  if (lqr_smem_bytes(n) > 227 * 1024)
-    return crb_fail(CRB_E_LIMIT, "%s: n = %d free DOFs need %zu bytes of shared memory for the %d x %d Hamiltonian (> 227 KB; n <= 42)",
-                    who, n, lqr_smem_bytes(n), 4 * n, 4 * n);
+  if (n > CRB_LQR_MAX_N)
+    return crb_fail(CRB_E_LIMIT, "%s: n = %d free DOFs exceed the limit of %d (%d x %d Hamiltonian)", who, n, CRB_LQR_MAX_N, 4 * n, 4 * n);
   return 0;
 }
 
@@ -764,6 +779,7 @@ extern "C" int crb_lqr_gains(int32_t n, int32_t n_members, const double* M_beam,
   a.status = status_out;
   a.ws = static_cast<double*>(workspace);
   a.ws_stride = lqr_ws_doubles(n);
+  a.big = lqr_big(n) ? 1 : 0;
   crb_lqr_kernel<<<grid, CRB_LQR_THREADS, lqr_smem_bytes(n), static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_lqr_gains: %s", cudaGetErrorString(e));

@@ -37,6 +37,7 @@ extern "C" {
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 #define CRB_LQR_MAX_ELEMENTS 128 /* crb_dense_matrices_batched: elements per beam */
+#define CRB_LQR_MAX_N 96         /* crb_lqr_gains: free position DOFs per design (32-element cantilever) */
 
 /* element types: models/abstractions.py:9-13 (ElementType) */
 #define CRB_ELEM_LINEAR 0
@@ -263,8 +264,8 @@ int crb_dense_matrices_batched(const crb_plan_t* plan, const double* params, int
  *   residual_out device [B] or NULL: ||A^T S + S A - S G S + Q||_F / ||Q||_F of the returned S
  *   status_out device int32 [B]: 0 ok, 1 M or R singular, 2 no stabilising solution found (sign iteration
  *       failed), 3 closed loop A - B gain not stable (:185-189); gain/S are NaN unless status is 0 or 3
- *   workspace device, crb_lqr_workspace_bytes(n, B) bytes.  n <= 42 (the 4n x 4n Hamiltonian lives in
- *   shared memory). */
+ *   workspace device, crb_lqr_workspace_bytes(n, B) bytes.  n <= CRB_LQR_MAX_N; up to n = 42 the 4n x 4n
+ *   Hamiltonian lives in shared memory, beyond it in the workspace (slower: one pass over it per pivot). */
 int crb_lqr_workspace_bytes(int32_t n, int32_t n_members, size_t* out);
 /* Device.  Dense closed-loop operator of every member of a linear design ensemble under state feedback
  * u_c = gain (ref - x) (control/full_state_linear.py:58 inside examples/lqr_control.py:95-111):

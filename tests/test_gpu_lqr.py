@@ -134,9 +134,9 @@ def test_lqr_failures_raise_like_the_reference():
         BatchedLinearQuadraticRegulator(Kd, Md, Qd, Qd)
     with pytest.raises(TypeError):
         BatchedLinearQuadraticRegulator(Kd.cpu(), Md, Qd, Rd)
-    big = torch.eye(43, dtype=torch.float64, device="cuda")
-    with pytest.raises(ValueError, match="shared memory"):
-        BatchedLinearQuadraticRegulator(big, big, torch.eye(86, dtype=torch.float64, device="cuda"), big).compute_gain_matrix()
+    big = torch.eye(97, dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError, match="exceed the limit"):
+        BatchedLinearQuadraticRegulator(big, big, torch.eye(194, dtype=torch.float64, device="cuda"), big).compute_gain_matrix()
 
 
 @pytest.mark.parametrize("N,gravity", [(6, True), (4, False)])
@@ -293,3 +293,27 @@ def test_dense_member_operator_path_matches_oracle(N, bc0, gravity, with_ref):
     rk4_steps(beam, X2, 0.0, h, steps, u=TipImpulse(torch.from_numpy(amp).cuda(), duration=80.5 * h), controller=ctrl)
     b2 = X2.cpu().numpy()
     assert not np.array_equal(b2, got) and max(block_err(got[i], b2[i], n) for i in range(B)) < 1e-10
+
+
+@pytest.mark.parametrize("N,B", [(15, 3), (16, 2), (32, 2)])
+def test_lqr_gains_of_long_beams(N, B):
+    """Designs whose 4n x 4n Hamiltonian does not fit shared memory (n > 42: up to the 32-element cantilever of
+    config 3, n = 96, a 384 x 384 Hamiltonian): the work matrix lives in the kernel's global workspace.  Same
+    parity bar as the short beams."""
+    from continuum_robot_b200 import BatchedLinearQuadraticRegulator
+    from oracle import beam_oracle as bo
+
+    par, et, bc = design_ensemble(B, N, seed=900 + N)
+    beam = make_gpu_beam(par, et, bc)
+    n = beam.n_free
+    Q, R, Qd, Rd = weights(n)
+    Md, Kd = beam.dense_matrices()
+    lqr = BatchedLinearQuadraticRegulator(Kd, Md, Qd, Rd)
+    G = lqr.compute_gain_matrix().cpu().numpy()
+    assert int(lqr.status.abs().sum()) == 0
+    Mh, Kh = Md.cpu().numpy(), Kd.cpu().numpy()
+    for i in range(B):
+        ks = bo.lqr_gain(Kh[i], Mh[i], Q, R)
+        kr = bo.lqr_gain_refined(Kh[i], Mh[i], Q, R)
+        assert np.abs(G[i] - ks).max() / np.abs(ks).max() < TOL_VS_SCIPY
+        assert np.abs(G[i] - kr).max() / np.abs(kr).max() < TOL_VS_REFINED

@@ -445,13 +445,13 @@ def test_lqr_entry_points_validate_arguments_on_the_host():
     lib = L.load()
     err = lambda: lib.crb_last_error().decode()
     need = C.c_size_t(0)
-    assert lib.crb_lqr_workspace_bytes(43, 8, C.byref(need)) == -3 and "shared memory" in err()  # 4n x 4n Hamiltonian > 227 KB
+    assert lib.crb_lqr_workspace_bytes(97, 8, C.byref(need)) == -3 and "exceed the limit" in err()  # CRB_LQR_MAX_N
     assert lib.crb_lqr_workspace_bytes(0, 8, C.byref(need)) == -1
     assert lib.crb_lqr_workspace_bytes(18, 8, None) == -1
     assert lib.crb_lqr_gains(18, 4, None, 0, None, 0, None, None, 1, None, None, None, None, None, 0, None) == -1
     assert "null argument" in err()
     one = C.c_void_p(8)  # never dereferenced: the size checks come first
-    assert lib.crb_lqr_gains(60, 4, one, 0, one, 0, one, one, 1, one, None, None, one, one, 0, None) == -3
+    assert lib.crb_lqr_gains(100, 4, one, 0, one, 0, one, one, 1, one, None, None, one, one, 0, None) == -3
     rc, p = _plan(4, [1, 0, 0, 0, 0])
     assert rc == 0
     et_nl, bc = bytes([0, 1, 0, 0]), bytes([1, 0, 0, 0, 0])
