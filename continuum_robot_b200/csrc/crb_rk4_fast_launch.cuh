@@ -1,0 +1,71 @@
+// crb_rk4_fast_launch.cuh -- launcher template of the fast RK4 family, shared by crb_rk4_fast.cu (one shared mass
+// factor set) and crb_rk4_fast_pm.cu (per-member factor sets): the two sets of instantiations compile in parallel.
+#pragma once
+#include "crb_internal.h"
+#include "crb_rk4_fast.cuh"
+
+template <int M, int LV, bool PM>
+static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
+                  double* Y_out, int save_every, cudaStream_t stream) {
+  const int mpb = CRB_FAST_WARPS * (32 >> LV);
+  // compact factor copy: ONE shared set, or (PM) one region per member of the block
+  const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
+  const int grid = (sys->n_members + mpb - 1) / mpb;
+  const KPlan P = kplan_of(plan);
+  const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
+#define CRB_LIN2N(UCV, IMPV, NCV)                                                                             \
+  {                                                                                                            \
+    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_rk4")) return rc;        \
+    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
+                                                                                             Y_out, save_every); \
+  }
+#define CRB_LIN2(UCV, IMPV) CRB_LIN2N(UCV, IMPV, false)
+  const bool nc = !(plan->contiguous && plan->p_act == plan->p);
+  if (sys->grav_mode == 1) {  // slot-space gravity: stage-by-stage kernel (the force is nonlinear in the rotations)
+    if (PM || uc) return 1;
+    if constexpr (!PM) {
+#define CRB_FASTG(IMPV, NCV)                                                                                  \
+  {                                                                                                           \
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, IMPV, true, NCV>, bytes, "crb_rk4")) return rc;          \
+    crb_rk4_fast_kernel<M, LV, IMPV, true, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
+                                                                                          Y_out, save_every); \
+  }
+      if (imp && nc) CRB_FASTG(true, true)
+      else if (imp) CRB_FASTG(true, false)
+      else if (nc) CRB_FASTG(false, true)
+      else CRB_FASTG(false, false)
+#undef CRB_FASTG
+    }
+    return 0;
+  }
+  // constrained DOFs inside active slots (PINNED root, interior supports ...) or phantom slots: the NC variants
+  // (reduced-index table for state I/O, masked right-hand sides); shared mass factors only
+  if (nc) {
+    if (PM || sys->force_staged) return 1;
+    if constexpr (!PM) {
+      if (uc && imp) CRB_LIN2N(true, true, true)
+      else if (uc) CRB_LIN2N(true, false, true)
+      else if (imp) CRB_LIN2N(false, true, true)
+      else CRB_LIN2N(false, false, true)
+    }
+    return 0;
+  }
+  if (!sys->force_staged || PM) {  // paired operator applications (forcing piecewise constant in time)
+    if (uc && imp) CRB_LIN2(true, true)
+    else if (uc) CRB_LIN2(true, false)
+    else if (imp) CRB_LIN2(false, true)
+    else CRB_LIN2(false, false)
+  } else if (uc) {
+    return 1;  // the stage-by-stage fast kernel has no constant-force path: use the general kernel
+  } else if (imp) {
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
+    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
+  } else {
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
+    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
+  }
+#undef CRB_LIN2
+#undef CRB_LIN2N
+  return 0;
+}
+
