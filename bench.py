@@ -138,9 +138,10 @@ class ClockSampler:
     def stop(self, t_begin, t_end):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        rows = [r for (ts, r) in self.rows if t_begin <= ts <= t_end + 0.2] or [r for (_, r) in self.rows[-3:]]
+        # the device is under the same load from 0.35 s before the timed region (spin-up + warm-up) to its end
+        rows = [r for (ts, r) in self.rows if t_begin - 0.35 <= ts <= t_end + 0.02] or [r for (_, r) in self.rows[-3:]]
         sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -200,15 +201,23 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- warm-up ----
+    # ---- clocks: the sampler needs ~0.3 s to start; the GPU is kept under load meanwhile (same kernel on a scratch
+    # copy of the state) so that the timed region does not begin on an idle, down-clocked device ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    scratch = X.clone()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.4:
+        for _ in range(20):
+            rk4_steps(beam, scratch, 0.0, h, S, system=system)
+        torch.cuda.synchronize(dev)
+    del scratch
+    # ---- warm-up: W steps on the ensemble itself ----
     tk = 0
     for c in chunks(args.warmup):
         rk4_steps(beam, X, tk * h, h, c, system=system)
         tk += c
     # ---- timed region: EXACTLY K steps, state resident in HBM ----
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in chunks(args.steps)]
     t_begin = time.perf_counter()

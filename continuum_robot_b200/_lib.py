@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 105
+CRB_VERSION = 106
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -67,11 +67,19 @@ class CrbSystem(C.Structure):
         ("shared_op_doubles", C.c_int64),
         ("gain_stride", C.c_int64),
         ("member_op", C.c_void_p),
+        ("u_sin_amp", C.c_void_p),
+        ("u_sin_omega", C.c_double),
+        ("u_sin_phase", C.c_double),
+        ("u_tab_t", C.c_void_p),
+        ("u_tab_v", C.c_void_p),
+        ("u_tab_k", C.c_int32),
+        ("u_time_shared", C.c_int32),
     ]
 
 
 _SIGNATURES = {
     "crb_version": (C.c_int, []),
+    "crb_abi_sizes": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "crb_last_error": (C.c_char_p, []),
     "crb_plan": (C.c_int, [C.c_int32, C.c_char_p, C.c_int32, C.POINTER(CrbPlan)]),
     "crb_assemble": (
@@ -141,6 +149,11 @@ def load() -> C.CDLL:
     v = lib.crb_version()
     if v != CRB_VERSION:
         raise RuntimeError(f"libcrb.so reports ABI version {v}, expected {CRB_VERSION}: rebuild it")
+    pb, sb = C.c_int32(), C.c_int32()
+    lib.crb_abi_sizes(C.byref(pb), C.byref(sb))
+    if (pb.value, sb.value) != (C.sizeof(CrbPlan), C.sizeof(CrbSystem)):
+        raise RuntimeError(f"struct layout mismatch: libcrb.so has crb_plan_t {pb.value} B / crb_system_t {sb.value} B, "
+                           f"the ctypes mirror {C.sizeof(CrbPlan)} / {C.sizeof(CrbSystem)}")
     _lib = lib
     return lib
 

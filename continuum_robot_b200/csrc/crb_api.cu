@@ -19,6 +19,12 @@ int crb_fail(int code, const char* fmt, ...) {
 #define fail crb_fail
 
 extern "C" int crb_version(void) { return CRB_VERSION; }
+extern "C" int crb_abi_sizes(int32_t* plan_bytes, int32_t* system_bytes) {
+  if (!plan_bytes || !system_bytes) return fail(CRB_E_ARG, "crb_abi_sizes: null argument");
+  *plan_bytes = (int32_t)sizeof(crb_plan_t);
+  *system_bytes = (int32_t)sizeof(crb_system_t);
+  return 0;
+}
 extern "C" const char* crb_last_error(void) { return g_err; }
 
 // ------------------------------------------------------------------------------------------
@@ -210,6 +216,8 @@ static int check_system(const char* who, const crb_plan_t* plan, const crb_syste
     return fail(CRB_E_ARG, "%s: per-member gains (gain_stride != 0) exclude gain_frag / shared_op", who);
   if (sys->imp_amp && (sys->imp_dof < 0 || sys->imp_dof >= plan->n_free))
     return fail(CRB_E_ARG, "%s: imp_dof %d outside [0,%d)", who, sys->imp_dof, plan->n_free);
+  if (sys->u_tab_v && (!sys->u_tab_t || sys->u_tab_k < 2))
+    return fail(CRB_E_ARG, "%s: the input table needs its knots u_tab_t and u_tab_k >= 2 (got %d)", who, sys->u_tab_k);
   return 0;
 }
 
@@ -256,7 +264,8 @@ extern "C" int crb_forces(const crb_plan_t* plan, const crb_system_t* sys, const
 // DOFs in active slots or phantom slots take the NC variants of the paired kernel); slot-space gravity (config 1
 // as an ensemble) on the stage-by-stage kernel
 static bool rk4_fast_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
-  return sys->all_linear && !sys->drag && sys->grav_mode != 2 && !sys->gain && !sys->force_general;
+  return sys->all_linear && !sys->drag && sys->grav_mode != 2 && !sys->gain && !sys->force_general &&
+         !crb_time_varying_input(sys);
 }
 
 extern "C" int crb_rk4_wave_members(const crb_plan_t* plan, const crb_system_t* sys, int32_t* out) {
@@ -332,7 +341,7 @@ extern "C" int crb_midpoint(const crb_plan_t* plan, const crb_system_t* sys, con
   if (nsteps < 0) return fail(CRB_E_ARG, "crb_midpoint: nsteps must be >= 0");
   if (!(h > 0.0) || !std::isfinite(h)) return fail(CRB_E_ARG, "crb_midpoint: step h must be positive and finite");
   if (Y_out && save_every < 1) return fail(CRB_E_ARG, "crb_midpoint: save_every must be >= 1 when Y_out is given");
-  if (!(sys->all_linear && !sys->drag && sys->grav_mode == 0 && !sys->gain))
+  if (!(sys->all_linear && !sys->drag && sys->grav_mode == 0 && !sys->gain && !crb_time_varying_input(sys)))
     return fail(CRB_E_ARG, "crb_midpoint: needs an all-linear beam without drag / gravity / feedback "
                            "(the implicit step solves with M + h^2/4 K)");
   if (nsteps == 0) return 0;

@@ -472,7 +472,7 @@ struct LaneCtx {
 };
 
 struct RhsFlags {
-  bool drag, grav_slot, grav_generic, mask, uconst, impulse, gain, fext;
+  bool drag, grav_slot, grav_generic, mask, uconst, impulse, gain, fext, utime;
 };
 
 // Compile-time feature sets: a kernel instantiated for a feature set contains only that code
@@ -500,6 +500,7 @@ __device__ __forceinline__ RhsFlags make_flags(const crb_system_t& s, const KPla
   f.impulse = s.imp_amp != nullptr;
   f.gain = s.gain != nullptr;
   f.fext = s.f_ext != nullptr;
+  f.utime = s.u_sin_amp != nullptr || s.u_tab_v != nullptr;
   return f;
 }
 
@@ -605,6 +606,7 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
   F.uconst = (FEAT & CRB_F_INPUT) && F0.uconst;
   F.impulse = (FEAT & CRB_F_INPUT) && F0.impulse;
   F.fext = (FEAT & CRB_F_INPUT) && F0.fext;
+  F.utime = (FEAT & CRB_F_INPUT) && F0.utime;
   F.gain = (FEAT & (CRB_F_GAINM | CRB_F_GAINS)) && F0.gain;
   constexpr bool kLin = (FEAT & CRB_F_LINEAR) != 0, kNl = (FEAT & CRB_F_NONLIN) != 0;
   // halo: q of the slot left of this lane's first slot (zero at the root / outside the beam)
@@ -807,6 +809,47 @@ __device__ __forceinline__ void beam_accel(const LaneCtx<M>& L, const crb_system
           double u = 0.0;
           if (F.uconst) u += S.u_const[mo + r];
           if (F.fext) u += S.f_ext[mo + r];
+          acc[j][d] += u;
+        }
+      }
+  }
+  // time-varying inputs u(t) at the stage time: sinusoid and piecewise-linear table (crb_system_t.u_sin_* / u_tab_*)
+  if (!ONLY_FORCES && F.utime) {
+    double sv = 0.0, wt = 0.0;
+    int k0 = 0;
+    if (S.u_sin_amp) {
+      double cs;
+      crb_sincos(fma(S.u_sin_omega, t, S.u_sin_phase), sv, cs);
+    }
+    if (S.u_tab_v) {
+      const int K = S.u_tab_k;
+      if (t >= S.u_tab_t[K - 1]) {
+        k0 = K - 2;
+        wt = 1.0;
+      } else if (t > S.u_tab_t[0]) {
+        int lo = 0, hi = K - 1;  // u_tab_t[lo] <= t < u_tab_t[hi]
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (S.u_tab_t[mid] <= t) lo = mid; else hi = mid;
+        }
+        k0 = lo;
+        wt = (t - S.u_tab_t[lo]) / (S.u_tab_t[lo + 1] - S.u_tab_t[lo]);
+      }
+    }
+    const long long mo = S.u_time_shared ? 0ll : (long long)L.member * L.n;
+    const long long ks = S.u_time_shared ? (long long)L.n : (long long)S.n_members * L.n;  // doubles between knots
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int r = L.ri[j][d];
+        if (r >= 0) {
+          double u = 0.0;
+          if (S.u_sin_amp) u = S.u_sin_amp[mo + r] * sv;
+          if (S.u_tab_v) {
+            const double va = S.u_tab_v[k0 * ks + mo + r], vb = S.u_tab_v[(k0 + 1) * ks + mo + r];
+            u += fma(wt, vb - va, va);
+          }
           acc[j][d] += u;
         }
       }

@@ -108,6 +108,10 @@ extern "C" int crb_system_slice(const crb_plan_t* plan, const crb_system_t* sys,
   if (sys->u_const) out->u_const = sys->u_const + lo * n;
   if (sys->f_ext) out->f_ext = sys->f_ext + lo * n;
   if (sys->imp_amp) out->imp_amp = sys->imp_amp + lo;
+  if (!sys->u_time_shared) {
+    if (sys->u_sin_amp) out->u_sin_amp = sys->u_sin_amp + lo * n;
+    if (sys->u_tab_v) return crb_fail(CRB_E_ARG, "crb_system_slice: a per-member input table [K,B,n] cannot be sliced by member (its knot stride is the full ensemble)");
+  }
   if (sys->gain && sys->gain_stride) out->gain = sys->gain + lo * sys->gain_stride;
   if (sys->member_op) out->member_op = sys->member_op + lo * n * (3 * n + 1);
   return 0;

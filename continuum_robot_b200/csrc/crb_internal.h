@@ -14,7 +14,10 @@
 #define CRB_E_CUDA (-2)
 #define CRB_E_LIMIT (-3)
 
-int crb_fail(int code, const char* fmt, ...);  // sets the thread-local error text, returns code
+int crb_fail(int code, const char* fmt, ...);
+
+// inputs that change within a step (sinusoid / table): only the general RHS evaluates them
+inline bool crb_time_varying_input(const crb_system_t* s) { return s->u_sin_amp || s->u_tab_v; }  // sets the thread-local error text, returns code
 
 inline KPlan kplan_of(const crb_plan_t* p) {
   KPlan k;
@@ -59,6 +62,14 @@ inline SmemLayout smem_layout_compact_pm(const crb_plan_t* plan, const crb_syste
   return SL;
 }
 
+// SM count of the current device (queried per call: a cheap attribute read, no global state)
+inline int crb_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+    return 148;
+  return sms;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* who) {
   if (bytes > 48 * 1024) {
@@ -87,7 +98,7 @@ inline unsigned crb_needed_features(const crb_plan_t* plan, const crb_system_t* 
   if (s->grav_mode == 1) f |= CRB_F_GRAVS;
   if (s->grav_mode == 2) f |= CRB_F_GRAVG;
   if (plan->has_mask) f |= CRB_F_MASK;
-  if (s->u_const || s->imp_amp || s->f_ext) f |= CRB_F_INPUT;
+  if (s->u_const || s->imp_amp || s->f_ext || s->u_sin_amp || s->u_tab_v) f |= CRB_F_INPUT;
   if (s->gain) f |= (s->gain_frag && plan->g == 4 && s->gain_stride == 0) ? CRB_F_GAINM : CRB_F_GAINS;
   return f;
 }

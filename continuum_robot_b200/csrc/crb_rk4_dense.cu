@@ -132,7 +132,7 @@ crb_rk4_dense_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
 
 bool crb_dense_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
   return sys->member_op && sys->gain && sys->gain_stride != 0 && sys->all_linear && !sys->drag && !sys->u_const &&
-         !sys->f_ext && !sys->force_general && !sys->force_staged && plan->n_free <= 32 && plan->n_elements <= 16 &&
+         !sys->f_ext && !crb_time_varying_input(sys) && !sys->force_general && !sys->force_staged && plan->n_free <= 32 && plan->n_elements <= 16 &&
          (sys->grav_mode == 0 || sys->seg_half_mass);
 }
 

@@ -17,6 +17,7 @@
 // dynamic_beam_model.py:256-272, 343-362 (forces disabled, u = constant force / tip impulse / none).
 #pragma once
 #include "crb_device.cuh"
+#include "crb_tile.cuh"
 
 #ifndef CRB_FAST_WARPS
 #define CRB_FAST_WARPS 2      // warps per block of the fast kernel
@@ -560,6 +561,291 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
+}
+
+// ==========================================================================================
+// Persistent form of the paired kernel (shared mass factors): every warp loops over tiles of `mpw` consecutive
+// members; the next tile's state rows and stiffness coefficients arrive by 1-D bulk copies (crb_tile.cuh) while the
+// current tile integrates in registers, results leave through a shared-memory buffer as one bulk store per tile
+// (and per recorded frame).  Same arithmetic, statement by statement, as crb_rk4_lin2_kernel.
+//
+// sel_inv (or NULL): lean recording.  sel_inv[r] = output column of state entry r (0 <= r < 2n) or -1; frames are
+// then Y[T, B, n_sel] holding only the selected entries (tip trace, node shapes: what the reference's callers read
+// from sol.y, examples/lqr_control.py:166-183, examples/example_utilities.py:173-205).
+// ==========================================================================================
+template <int M, int LV>
+struct FastTileGeom {
+  static constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
+  static constexpr int FAST_DOUBLES = crb_compact_doubles(M, G, LVE);
+  static constexpr int FAC_PAD = (FAST_DOUBLES + 15) & ~15;  // the tile buffers behind it stay 128-byte aligned
+  static constexpr int ROW_MAX = 2 * 3 * M * G;              // doubles per state row (= 2n on full contiguous plans)
+  static constexpr int KC_ROW = 4 * M * G;                   // stiffness coefficients per member
+  static constexpr int WARP_DOUBLES = mpw * (2 * ROW_MAX + KC_ROW);  // in: state | in: kcoef | out: state
+  static constexpr size_t smem_bytes(int warps) { return sizeof(double) * ((size_t)FAC_PAD + (size_t)warps * WARP_DOUBLES) + 8 * warps; }
+};
+
+template <int M, int LV, bool UC, bool IMP, bool NC = false>
+__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
+crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
+                     double* __restrict__ Y, int save_every, const int* __restrict__ sel_inv, int n_sel) {
+  typedef FastTileGeom<M, LV> TG;
+  constexpr int G = TG::G, mpw = TG::mpw;
+  constexpr bool VEC = !NC && (3 * M) % 2 == 0;  // 128-bit shared-memory accesses of the lane's 3M-double runs
+  extern __shared__ __align__(128) double smem[];
+  typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP || NC) ? 0 : 2), NC> Ctx;
+  Ctx C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ml = lane / G;
+  double* const in_x = smem + TG::FAC_PAD + warp * TG::WARP_DOUBLES;
+  double* const in_k = in_x + mpw * TG::ROW_MAX;
+  double* const out_x = in_k + mpw * TG::KC_ROW;
+  const unsigned bar = crb_smem_u32(smem + TG::FAC_PAD + CRB_FAST_WARPS * TG::WARP_DOUBLES) + 8u * warp;
+  const int n = P.n_free;
+  const unsigned row_bytes = 16u * (unsigned)n;
+  // The tile loop runs on BLOCK tiles (CRB_FAST_WARPS consecutive warp tiles): its control flow depends on blockIdx only,
+  // so the compiler keeps the step loop in uniform control flow (no divergence guards around the shuffles); a warp
+  // whose tile lies beyond the ensemble integrates clamped garbage and moves no data.
+  const int n_tiles = (S.n_members + mpw - 1) / mpw;
+  const int n_btiles = (n_tiles + CRB_FAST_WARPS - 1) / CRB_FAST_WARPS;
+
+  auto tile_count = [&](int bt) -> int {  // members of this warp's tile in block tile bt (0: none)
+    const int m0 = (bt * CRB_FAST_WARPS + warp) * mpw;
+    return max(0, min(mpw, S.n_members - m0));
+  };
+  auto prefetch = [&](int bt) {  // one lane: the tile's state rows (+ stiffness coefficients) -> `in` buffers
+    const int m0 = (bt * CRB_FAST_WARPS + warp) * mpw;
+    const unsigned cnt = (unsigned)tile_count(bt);
+    if (cnt == 0) return;
+    const unsigned xb = cnt * row_bytes, kb = S.stiff_shared ? 0u : cnt * (unsigned)(TG::KC_ROW * 8);
+    crb_mbar_expect_tx(bar, xb + kb);
+    crb_bulk_load(crb_smem_u32(in_x), X + (long long)m0 * 2 * n, xb, bar);
+    if (kb) crb_bulk_load(crb_smem_u32(in_k), S.kcoef + (long long)m0 * TG::KC_ROW, kb, bar);
+  };
+  if (lane == 0) {
+    crb_mbar_init(bar, 1);
+    crb_fence_mbar_init();
+    if ((int)blockIdx.x < n_btiles) prefetch(blockIdx.x);
+  }
+  {  // compact copy of the shared factor set (once per block and launch)
+    const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * TG::LVE * G;
+    for (int k = threadIdx.x; k < TG::FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
+  }
+  __syncthreads();
+  C.g = lane % G;
+  C.n = n;
+  C.fslot = smem;
+  C.fscan = smem + crb_compact_slot_doubles(M, G);
+  fast_pin_load<M, G, Ctx>(C);
+  C.imp_amp = 0.0;
+  C.imp_dur = S.imp_duration;
+  C.imp_local = -1;
+  const int s0 = C.g * M;
+  if (NC) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) C.ri[NC ? j : 0][d] = S.red_index[3 * (s0 + j) + d];
+  }
+  if (S.stiff_shared) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double2 k0 = *reinterpret_cast<const double2*>(S.kcoef + 4 * (s0 + j));
+      const double2 k1 = *reinterpret_cast<const double2*>(S.kcoef + 4 * (s0 + j) + 2);
+      C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
+    }
+  }
+  auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  const double hh = 0.5 * h, h2 = 0.5 * h * h, h3 = h * h * h / 6.0, h4 = h * h * h * h / 24.0;
+  const double h6 = h / 6.0, hx = h * h / 6.0, h12 = h * h * h / 12.0;
+  unsigned phase = 0;
+
+  for (int bt = blockIdx.x; bt < n_btiles; bt += gridDim.x) {
+    const int m0 = (bt * CRB_FAST_WARPS + warp) * mpw;
+    const int member = m0 + ml;
+    C.active = member < S.n_members;
+    C.member = C.active ? member : S.n_members - 1;
+    const unsigned cnt = (unsigned)tile_count(bt);
+    if (cnt) {
+      crb_mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
+    double q[M][3], v[M][3], w[2][M][3];
+    {
+      const double* xs = in_x + ml * 2 * n;
+      if (VEC) {
+        const double2* q2 = reinterpret_cast<const double2*>(xs + 3 * s0);
+        const double2* v2 = reinterpret_cast<const double2*>(xs + n + 3 * s0);
+#pragma unroll
+        for (int i = 0; i < (3 * M) / 2; ++i) {
+          const double2 a = q2[i], b = v2[i];
+          (&q[0][0])[2 * i] = a.x;
+          (&q[0][0])[2 * i + 1] = a.y;
+          (&v[0][0])[2 * i] = b.x;
+          (&v[0][0])[2 * i + 1] = b.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int r = rix(j, d);
+            q[j][d] = (!NC || r >= 0) ? xs[r] : 0.0;
+            v[j][d] = (!NC || r >= 0) ? xs[n + r] : 0.0;
+          }
+      }
+      if (!S.stiff_shared) {
+        const double2* k2 = reinterpret_cast<const double2*>(in_k + ml * TG::KC_ROW + 4 * s0);
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          const double2 k0 = k2[2 * j], k1 = k2[2 * j + 1];
+          C.kc[j] = make_double4(k0.x, k0.y, k1.x, k1.y);
+        }
+      }
+    }
+    __syncwarp();  // every lane has its tile in registers: the `in` buffers are free for the next tile
+    if (lane == 0 && bt + (int)gridDim.x < n_btiles) prefetch(bt + gridDim.x);
+    // Aligned block barrier, for the COMPILER: after the barrier spin and the one-lane prefetch it cannot prove that
+    // the warp is converged and would guard every shuffle of the step loop (BRA.DIV + register copies, +8 %
+    // instructions, measured 15 % slower); both warps of the block walk the same block tiles, so it costs nothing.
+    __syncthreads();
+
+    // forcing in acceleration space: cu = M^-1 (u_const + f_ext), ci = amp * M^-1 e_k
+    double cu[UC ? M : 1][3], ci[IMP ? M : 1][3];
+    if (UC || IMP) {
+      const long long mo = (long long)C.member * n;
+      const double amp = IMP ? S.imp_amp[C.member] : 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int r = rix(j, d);
+          double u = 0.0;
+          if (!NC || r >= 0) {
+            if (UC && S.u_const) u += S.u_const[mo + r];
+            if (UC && S.f_ext) u += S.f_ext[mo + r];
+          }
+          w[0][j][d] = u;
+          w[1][j][d] = (IMP && r == S.imp_dof) ? amp : 0.0;
+        }
+      fast_solve_r<M, LV, 2>(w, C);
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (UC) cu[j][d] = w[0][j][d];
+          if (IMP) ci[j][d] = w[1][j][d];
+        }
+    }
+    // registers -> `out` buffer -> one bulk store of the tile's rows to dst (row-major like X)
+    auto store_tile = [&](double* dst) {
+      if (lane == 0) crb_bulk_wait_read<0>();  // the previous store has drained the buffer
+      __syncwarp();
+      double* xo = out_x + ml * 2 * n;
+      if (VEC) {
+        double2* q2 = reinterpret_cast<double2*>(xo + 3 * s0);
+        double2* v2 = reinterpret_cast<double2*>(xo + n + 3 * s0);
+#pragma unroll
+        for (int i = 0; i < (3 * M) / 2; ++i) {
+          q2[i] = make_double2((&q[0][0])[2 * i], (&q[0][0])[2 * i + 1]);
+          v2[i] = make_double2((&v[0][0])[2 * i], (&v[0][0])[2 * i + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int r = rix(j, d);
+            if (!NC || r >= 0) {
+              xo[r] = q[j][d];
+              xo[n + r] = v[j][d];
+            }
+          }
+      }
+      crb_fence_proxy_async();  // generic-proxy writes above -> visible to the bulk-copy (async) proxy
+      __syncwarp();
+      if (lane == 0 && cnt) {
+        crb_bulk_store(dst, crb_smem_u32(out_x), cnt * row_bytes);
+        crb_bulk_commit();
+      }
+      __syncthreads();  // aligned barrier: the compiler knows the warps are converged again (uniform step loop)
+    };
+
+    for (int k = 0; k < nsteps; ++k) {
+      const double t = t0 + k * h;
+      const double g1 = (IMP && t < S.imp_duration) ? 1.0 : 0.0;
+      const double g2 = (IMP && t + hh < S.imp_duration) ? 1.0 : 0.0;
+      const double g4 = (IMP && t + h < S.imp_duration) ? 1.0 : 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          w[0][j][d] = q[j][d];
+          w[1][j][d] = v[j][d];
+        }
+#pragma unroll 1
+      for (int round = 0; round < 2; ++round) {
+        fast_apply2<M, LV>(C, w);
+        if (round == 0) {  // w = (L, p)
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const double Lq = w[0][j][d], p = w[1][j][d];
+              if (!UC && !IMP) {
+                q[j][d] = fma(h3, p, fma(h2, Lq, fma(h, v[j][d], q[j][d])));
+                v[j][d] = fma(h2, p, fma(h, Lq, v[j][d]));
+              } else {
+                const double cuv = UC ? cu[j][d] : 0.0, civ = IMP ? ci[j][d] : 0.0;
+                const double a1 = Lq + fma(g1, civ, cuv);
+                const double a2 = fma(hh, p, Lq) + fma(g2, civ, cuv);
+                q[j][d] = fma(hx, fma(2.0, a2, a1), fma(h, v[j][d], q[j][d]));
+                v[j][d] = fma(h6, fma(5.0, a2, a1) + fma(hh, p, (g4 - g2) * civ), v[j][d]);
+                w[0][j][d] = a1;
+                w[1][j][d] = a2;
+              }
+            }
+        } else {  // w = (r, s) or (r1, r2)
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const double r = w[0][j][d], s = w[1][j][d];
+              if (!UC && !IMP) {
+                q[j][d] = fma(h4, r, q[j][d]);
+                v[j][d] = fma(h4, s, fma(h3, r, v[j][d]));
+              } else {
+                q[j][d] = fma(h4, r, q[j][d]);
+                v[j][d] = fma(h12, r + s, v[j][d]);
+              }
+            }
+        }
+      }
+      if (Y && save_every > 0 && (k + 1) % save_every == 0) {
+        const long long frame = (k + 1) / save_every - 1;
+        if (sel_inv) {  // lean frame: only the selected state entries
+          if (C.active) {
+            double* ym = Y + (frame * S.n_members + C.member) * n_sel;
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                const int r = rix(j, d);
+                if (!NC || r >= 0) {
+                  const int cq = sel_inv[r], cv = sel_inv[n + r];
+                  if (cq >= 0) ym[cq] = q[j][d];
+                  if (cv >= 0) ym[cv] = v[j][d];
+                }
+              }
+          }
+          __syncthreads();
+        } else {
+          store_tile(Y + (frame * S.n_members + m0) * 2 * n);
+        }
+      }
+    }
+    store_tile(X + (long long)m0 * 2 * n);
+  }
+  if (lane == 0) crb_bulk_wait<0>();  // the last stores have left shared memory before the block retires
 }
 
 // ==========================================================================================

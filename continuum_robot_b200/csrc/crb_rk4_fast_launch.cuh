@@ -4,23 +4,46 @@
 #include "crb_internal.h"
 #include "crb_rk4_fast.cuh"
 
+#include <algorithm>
+
 template <int M, int LV, bool PM>
 static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
-                  double* Y_out, int save_every, cudaStream_t stream) {
+                  double* Y_out, int save_every, cudaStream_t stream, const int32_t* sel_inv = nullptr, int n_sel = 0) {
   const int mpb = CRB_FAST_WARPS * (32 >> LV);
   // compact factor copy: ONE shared set, or (PM) one region per member of the block
   const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
+  // shared mass factors: persistent paired kernel (bulk-copy tiles; needs 16-byte aligned rows); per-member factors
+  // (PM) and lean-recording requests it cannot serve keep the one-tile-per-block kernel
+  const bool bulk_ok = !PM && (((uintptr_t)X | (uintptr_t)Y_out | (uintptr_t)sys->kcoef) & 15) == 0;
+  if (sel_inv && !bulk_ok) return 1;
 #define CRB_LIN2N(UCV, IMPV, NCV)                                                                             \
   {                                                                                                            \
-    if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_rk4")) return rc;        \
-    crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
-                                                                                             Y_out, save_every); \
+    if constexpr (!PM) {                                                                                       \
+      if (bulk_ok) {                                                                                           \
+        typedef FastTileGeom<M, LV> TG;                                                                        \
+        const size_t pbytes = TG::smem_bytes(CRB_FAST_WARPS);                                                  \
+        const int n_tiles = (sys->n_members + TG::mpw - 1) / TG::mpw;                                          \
+        const int pgrid = std::min((n_tiles + CRB_FAST_WARPS - 1) / CRB_FAST_WARPS, crb_sm_count() * CRB_FAST_MINBLOCKS); \
+        if (int rc = set_smem(crb_rk4_lin2p_kernel<M, LV, UCV, IMPV, NCV>, pbytes, "crb_rk4")) return rc;      \
+        crb_rk4_lin2p_kernel<M, LV, UCV, IMPV, NCV><<<pgrid, CRB_FAST_THREADS, pbytes, stream>>>(              \
+            P, *sys, X, t0, h, nsteps, Y_out, save_every, sel_inv, n_sel);                                     \
+        return 0;                                                                                              \
+      }                                                                                                        \
+    }                                                                                                          \
+    if constexpr (PM) {                                                                                        \
+      if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_rk4")) return rc;      \
+      crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
+                                                                                               Y_out, save_every); \
+    } else {                                                                                                   \
+      return 1; /* rows not 16-byte aligned: general kernel */                                                 \
+    }                                                                                                          \
   }
 #define CRB_LIN2(UCV, IMPV) CRB_LIN2N(UCV, IMPV, false)
   const bool nc = !(plan->contiguous && plan->p_act == plan->p);
+  if (sel_inv && (sys->grav_mode == 1 || sys->force_staged)) return 1;  // lean recording: paired persistent kernel only
   if (sys->grav_mode == 1) {  // slot-space gravity: stage-by-stage kernel (the force is nonlinear in the rotations)
     if (PM || uc) return 1;
     if constexpr (!PM) {

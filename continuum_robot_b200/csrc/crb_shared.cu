@@ -307,7 +307,7 @@ crb_rk4_shared_kernel(SharedArgs A, double* __restrict__ X, double t0, double h,
 
 bool crb_shared_eligible(const crb_plan_t* plan, const crb_system_t* sys) {
   return sys->shared_op && !sys->force_general && sys->all_linear && sys->mass_shared && sys->stiff_shared && sys->gain_stride == 0 &&
-         !sys->drag && !sys->u_const && !sys->f_ext && plan->n_free <= 4 * CRB_SH_MAX_KQ;
+         !sys->drag && !sys->u_const && !sys->f_ext && !crb_time_varying_input(sys) && plan->n_free <= 4 * CRB_SH_MAX_KQ;
 }
 
 int crb_launch_rk4_shared(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,

@@ -109,6 +109,94 @@ class TipImpulse:
         return u
 
 
+class SinusoidInput:
+    """Time-varying input ``u(t)[b, r] = amplitude[b, r] * sin(omega * t + phase)`` fused into the RHS kernels
+    (crb_system_t.u_sin_*): the form the reference's own integration tests drive the beam with,
+    ``u(t) = np.sin(t) * np.ones(n)`` (tests/test_dynamic_beam.py:214-215, 234-235).
+
+    ``amplitude``: torch tensor ``[n]`` (shared by the ensemble) or ``[B, n]``.  Also callable, ``u(t)``, so it can
+    be passed wherever the reference passes a callable input (``get_dynamic_system()(t, X, u)``).
+    """
+
+    def __init__(self, amplitude, omega: float = 1.0, phase: float = 0.0):
+        torch = _torch()
+        if not isinstance(amplitude, torch.Tensor):
+            amplitude = torch.as_tensor(np.asarray(amplitude, dtype=np.float64))
+        if amplitude.ndim not in (1, 2):
+            raise ValueError("SinusoidInput amplitude must have shape [n] or [B, n]")
+        self.amplitude = amplitude
+        self.omega = float(omega)
+        self.phase = float(phase)
+
+    def __call__(self, t):
+        torch = _torch()
+        tt = torch.as_tensor(t, dtype=torch.float64, device=self.amplitude.device)
+        if tt.ndim == 1:  # per-member times [B] -> [B, 1]
+            tt = tt.unsqueeze(-1)
+        return self.amplitude * torch.sin(self.omega * tt + self.phase)
+
+
+class PiecewiseLinearInput:
+    """Time-varying input interpolated linearly from a table (``numpy.interp`` semantics: held constant outside
+    the knots), fused into the RHS kernels (crb_system_t.u_tab_*).  ``times``: ascending ``[K]`` (K >= 2);
+    ``values``: torch tensor ``[K, n]`` (shared) or ``[K, B, n]``."""
+
+    def __init__(self, times, values):
+        torch = _torch()
+        tk = np.ascontiguousarray(np.asarray(times, dtype=np.float64))
+        if tk.ndim != 1 or len(tk) < 2 or np.any(np.diff(tk) <= 0):
+            raise ValueError("PiecewiseLinearInput times must be a strictly ascending 1-D array with at least 2 knots")
+        if not isinstance(values, torch.Tensor):
+            values = torch.as_tensor(np.asarray(values, dtype=np.float64))
+        if values.ndim not in (2, 3) or values.shape[0] != len(tk):
+            raise ValueError("PiecewiseLinearInput values must have shape [K, n] or [K, B, n]")
+        self.times = tk
+        self.values = values
+
+    def __call__(self, t):
+        torch = _torch()
+        v = self.values
+        tk = torch.as_tensor(self.times, dtype=torch.float64, device=v.device)
+        tt = torch.as_tensor(t, dtype=torch.float64, device=v.device).reshape(-1)  # [1] or [B]
+        tc = tt.clamp(float(self.times[0]), float(self.times[-1]))
+        k0 = (torch.searchsorted(tk, tc, right=True) - 1).clamp(0, len(self.times) - 2)
+        w = ((tc - tk[k0]) / (tk[k0 + 1] - tk[k0])).unsqueeze(-1)
+        if v.ndim == 2:
+            out = v[k0] + w * (v[k0 + 1] - v[k0])  # [len(tt), n]
+        else:
+            b = torch.arange(v.shape[1], device=v.device)
+            out = v[k0, b] + w * (v[k0 + 1, b] - v[k0, b])
+        return out[0] if (v.ndim == 2 and tt.numel() == 1 and np.ndim(t) == 0) else out
+
+
+def split_input(u):
+    """Decompose an input ``u`` into the parts the kernels fuse: (constant tensor or None, TipImpulse or None,
+    [SinusoidInput / PiecewiseLinearInput ...], other callable or None).  ``u`` may be one part or a list / tuple of
+    parts (their sum)."""
+    torch = _torch()
+    parts = list(u) if isinstance(u, (list, tuple)) else ([] if u is None else [u])
+    uc, imp, tv, other = None, None, [], None
+    for part in parts:
+        if isinstance(part, TipImpulse):
+            if imp is not None:
+                raise ValueError("at most one TipImpulse per input")
+            imp = part
+        elif isinstance(part, (SinusoidInput, PiecewiseLinearInput)):
+            if any(type(x) is type(part) for x in tv):
+                raise ValueError(f"at most one {type(part).__name__} per input")
+            tv.append(part)
+        elif isinstance(part, torch.Tensor):
+            uc = part if uc is None else uc + part
+        elif callable(part):
+            if other is not None:
+                raise ValueError("at most one free-form callable per input")
+            other = part
+        else:
+            raise TypeError(f"input parts must be torch tensors, TipImpulse, SinusoidInput, PiecewiseLinearInput or "
+                            f"torch callables u(t), got {type(part).__name__}")
+    return uc, imp, tv, other
+
+
 # --------------------------------------------------------------------------------------------
 # Parameter ingestion
 # --------------------------------------------------------------------------------------------
@@ -473,7 +561,7 @@ class BatchedDynamicEulerBernoulliBeam:
 
     def make_system(self, B: int, *, drag: Optional[FluidDragForce] = None, gravity: Optional[GravityForce] = None,
                     u_const=None, impulse: Optional[TipImpulse] = None, gain=None, ref=None, f_ext=None,
-                    member_range=None):
+                    member_range=None, time_inputs=()):
         """Fill a crb_system_t; returns (struct, keepalive list).
 
         ``member_range=(lo, hi)`` describes the sub-ensemble lo..hi-1 of a B-member ensemble (every
@@ -536,6 +624,30 @@ class BatchedDynamicEulerBernoulliBeam:
                 raise ValueError(f"impulse dof {impulse.dof} outside the {n} position DOFs")
             s.imp_dof = dof
             s.imp_duration = impulse.duration
+        shared_flags = []
+        for part in time_inputs:  # fused time-varying inputs (SinusoidInput / PiecewiseLinearInput)
+            if isinstance(part, SinusoidInput):
+                a = part.amplitude
+                shared_flags.append(a.ndim == 1)
+                s.u_sin_amp = dev64(a, (n,) if a.ndim == 1 else (B, n), "sinusoid amplitude").data_ptr() + (0 if a.ndim == 1 else 8 * lo * n)
+                s.u_sin_omega, s.u_sin_phase = part.omega, part.phase
+            elif isinstance(part, PiecewiseLinearInput):
+                v = part.values
+                K = len(part.times)
+                shared_flags.append(v.ndim == 2)
+                if v.ndim == 3 and (lo, hi) != (0, B):
+                    raise ValueError("a per-member input table cannot be sliced by member_range")
+                s.u_tab_v = dev64(v, (K, n) if v.ndim == 2 else (K, B, n), "input table").data_ptr()
+                tk = torch.from_numpy(part.times).to(self.device)
+                keep.append(tk)
+                s.u_tab_t = tk.data_ptr()
+                s.u_tab_k = K
+            else:
+                raise TypeError(f"unsupported fused input {type(part).__name__}")
+        if shared_flags:
+            if len(set(shared_flags)) != 1:
+                raise ValueError("fused time-varying inputs must all be shared ([n]) or all per member ([B, n])")
+            s.u_time_shared = int(shared_flags[0])
         if gain is not None:
             if not isinstance(gain, torch.Tensor):
                 gain = torch.as_tensor(np.asarray(gain, dtype=np.float64))
@@ -553,7 +665,7 @@ class BatchedDynamicEulerBernoulliBeam:
                     rdev = dev64(ref.reshape(-1), (2 * n,), "reference")
                     s.ref = rdev.data_ptr()
                 # all-linear designs: the closed loop of every member as one dense operator (crb_member_operators)
-                if (getattr(self, "use_member_operators", True) and self._all_linear and drag is None and u_const is None and f_ext is None and n <= 32
+                if (getattr(self, "use_member_operators", True) and self._all_linear and drag is None and u_const is None and f_ext is None and not time_inputs and n <= 32
                         and self.n_elements <= 16 and not self.force_general_kernels and not self.force_staged_kernels):
                     op = self._member_operators(gdev, rdev)
                     keep.append(op)
@@ -589,7 +701,7 @@ class BatchedDynamicEulerBernoulliBeam:
             # one design + one gain shared by every member: the closed-loop RHS is a dense contraction
             # with member-independent operators (crb_shared_operator -> FP64 tensor cores)
             if (self._mass_shared and self._stiff_shared and self._all_linear and drag is None and u_const is None
-                    and f_ext is None and n <= 24 and (gravity is None or self.n_elements <= 8)
+                    and f_ext is None and not time_inputs and n <= 24 and (gravity is None or self.n_elements <= 8)
                     and not self.force_general_kernels):
                 blob = self._shared_operator(gdev, rdev, (s.gx, s.gy) if gravity is not None else None,
                                              int(s.imp_dof) if impulse is not None else -1)
@@ -687,12 +799,13 @@ class BatchedDynamicEulerBernoulliBeam:
             raise TypeError("force callables must return torch tensors on the CUDA device (no CPU fallback)")
         return f
 
-    def _rhs(self, t: float, x, u=None, impulse=None, gain=None, ref=None):
+    def _rhs(self, t: float, x, u=None, impulse=None, gain=None, ref=None, time_inputs=()):
         torch = _torch()
         B = x.shape[0]
         drag, grav, user = self._active_forces()
         f_ext = self._external_forces(x, user)
-        sysm, keep = self.make_system(B, drag=drag, gravity=grav, u_const=u, impulse=impulse, gain=gain, ref=ref, f_ext=f_ext)
+        sysm, keep = self.make_system(B, drag=drag, gravity=grav, u_const=u, impulse=impulse, gain=gain, ref=ref, f_ext=f_ext,
+                                      time_inputs=time_inputs)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
             rc = _lib.load().crb_rhs(C.byref(self._plan), C.byref(sysm), x.data_ptr(), float(t), out.data_ptr(), self._stream())

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 105
+#define CRB_VERSION 106
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 #define CRB_LQR_MAX_ELEMENTS 128 /* crb_dense_matrices_batched: elements per beam */
@@ -124,10 +124,26 @@ typedef struct crb_system_t {
    * gain / gain_stride / ref describing the same feedback), crb_rk4 evaluates the closed-loop RHS as ONE dense
    * product per member (one lane per free DOF, the operator row in registers). */
   const double* member_op;
+  /* Time-varying generalized force, evaluated at every stage time: `force = u(t)` of
+   * dynamic_beam_model.py:357-360 for the input families that can be fused (the reference's tests drive
+   * u(t) = sin(t) * ones(n), tests/test_dynamic_beam.py:214-215, 234-235):
+   *   u(t)[r] += u_sin_amp[m, r] * sin(u_sin_omega * t + u_sin_phase)
+   *   u(t)[r] += linear interpolation of u_tab_v[k, m, r] over the ascending knots u_tab_t[k], held constant
+   *              outside [u_tab_t[0], u_tab_t[u_tab_k - 1]]   (numpy.interp semantics)
+   * u_time_shared = 1: the tables have no member axis (u_sin_amp [n], u_tab_v [u_tab_k, n]). */
+  const double* u_sin_amp;  /* [B, n] (or [n]), or NULL */
+  double u_sin_omega, u_sin_phase;
+  const double* u_tab_t;    /* [u_tab_k], or NULL */
+  const double* u_tab_v;    /* [u_tab_k, B, n] (or [u_tab_k, n]) */
+  int32_t u_tab_k;          /* >= 2 when u_tab_v is set */
+  int32_t u_time_shared;
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */
 int crb_version(void);
+/* sizeof(crb_plan_t), sizeof(crb_system_t) of the build: a binding that mirrors the structs (ctypes, cgo ...) checks
+ * its own layout against these before the first call */
+int crb_abi_sizes(int32_t* plan_bytes, int32_t* system_bytes);
 /* thread-local text of the last error returned on this thread ("" if none) */
 const char* crb_last_error(void);
 

@@ -463,8 +463,12 @@ def test_lqr_entry_points_validate_arguments_on_the_host():
     assert "mismatch" in err()
     assert lib.crb_member_operators(18, 4, None, 0, None, 0, None, None, None, None, None) == -1
     assert lib.crb_member_operators(33, 4, one, 0, one, 0, one, None, one, one, None) == -3 and "one lane per DOF" in err()
-    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.member_op.offset == C.sizeof(L.CrbSystem) - 8
-    assert L.CrbSystem.gain_stride.offset == C.sizeof(L.CrbSystem) - 16
+    # the ctypes mirror has the compiled layout (crb_abi_sizes), fields in header order
+    pb, sb = C.c_int32(), C.c_int32()
+    assert lib.crb_abi_sizes(C.byref(pb), C.byref(sb)) == 0
+    assert (pb.value, sb.value) == (C.sizeof(L.CrbPlan), C.sizeof(L.CrbSystem))
+    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.u_time_shared.offset == C.sizeof(L.CrbSystem) - 4
+    assert L.CrbSystem.member_op.offset == L.CrbSystem.gain_stride.offset + 8 == L.CrbSystem.u_sin_amp.offset - 8
 
 
 def test_header_is_plain_c_and_the_library_serves_a_c_client(tmp_path):
