@@ -28,9 +28,13 @@ def params(e, B, fluid=True):
     return par
 
 
-def timed(fn, reps=3):
+_REPS = [3]
+
+
+def timed(fn, reps=None):
     import torch
 
+    reps = reps or _REPS[0]
     fn()
     torch.cuda.synchronize()
     best = 1e30
@@ -44,7 +48,8 @@ def timed(fn, reps=3):
     return best
 
 
-def main():
+def run(names, slots=0, reps=3):
+    """Yield one result dict per measured configuration (names: see the `if name == ...` blocks)."""
     import torch
 
     from continuum_robot_b200 import (BatchedDynamicEulerBernoulliBeam, ForceParams, FullStateLinear,
@@ -52,12 +57,14 @@ def main():
     from continuum_robot_b200 import ensembles as ens
     from continuum_robot_b200.integrate import rk4_steps
 
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg2,cfg4,cfg5,cfg3g")
-    ap.add_argument("--slots", type=int, default=0)
-    a = ap.parse_args()
+    class _A:
+        pass
+
+    a = _A()
+    a.slots = slots
     dev = "cuda"
-    for name in a.only.split(","):
+    _REPS[0] = reps
+    for name in names:
         if name == "cfg2":  # nonlinear 20-element + drag, replicated: RK4 h = 2.5e-5
             B, steps = 32768, 200
             e = ens.config2()
@@ -69,8 +76,8 @@ def main():
             X = torch.zeros(B, 120, dtype=torch.float64, device=dev)
             imp = TipImpulse(torch.full((B,), 0.1, dtype=torch.float64, device=dev))
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
-            print(json.dumps({"config": "cfg2 x%d (nonlinear 20 el + drag), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
-                              "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg2 x%d (nonlinear 20 el + drag), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
+                              "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg3p":  # config 3 shape with a PINNED root (constrained DOFs inside an active slot: NC variant of the paired kernel)
             B, steps = 65536, 50
             e = ens.config3(B, 32)
@@ -81,8 +88,8 @@ def main():
             rng = np.random.default_rng(4)
             X = torch.from_numpy(np.concatenate([1e-3 * rng.standard_normal((B, n)), 1e-1 * rng.standard_normal((B, n))], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
-            print(json.dumps({"config": "cfg3 shape with a pinned root (NC variant of the paired kernel)", "m": beam._plan.m, "g": beam._plan.g, "n_free": n,
-                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg3 shape with a pinned root (NC variant of the paired kernel)", "m": beam._plan.m, "g": beam._plan.g, "n_free": n,
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}
         if name == "lqr":  # batched LQR synthesis + rollout with one gain per member
             from continuum_robot_b200 import BatchedLinearQuadraticRegulator
             B, steps, N = 8192, 200, 6
@@ -101,8 +108,8 @@ def main():
             def synth():
                 out["K"] = BatchedLinearQuadraticRegulator(Kd, Md, Q, R).compute_gain_matrix()
             ms = timed(synth)
-            print(json.dumps({"config": "LQR synthesis, %d designs x %d elements (n = %d, Hamiltonian %d^2), 1 correction pass" % (B, N, n, 4 * n),
-                              "designs_per_s": B / (ms * 1e-3), "ms": ms}))
+            yield {"config": "LQR synthesis, %d designs x %d elements (n = %d, Hamiltonian %d^2), 1 correction pass" % (B, N, n, 4 * n),
+                              "designs_per_s": B / (ms * 1e-3), "ms": ms}
             # rollout: 8 disturbance realisations per design so that the ensemble fills the GPU (65536 members)
             rep = 8
             Bb = B * rep
@@ -114,8 +121,8 @@ def main():
             imp = TipImpulse(torch.from_numpy(rng.uniform(1, 20, Bb)).to(dev))
             for bm in (big, big.with_slots(2)):
                 ms = timed(lambda: rk4_steps(bm, X, 0.0, 5e-6, steps, u=imp, controller=ctrl))
-                print(json.dumps({"config": "LQR rollout with one gain per member, %d x %d el" % (Bb, N), "m": bm._plan.m, "g": bm._plan.g,
-                                  "member_steps_per_s": Bb * steps / (ms * 1e-3), "ms": ms}))
+                yield {"config": "LQR rollout with one gain per member, %d x %d el" % (Bb, N), "m": bm._plan.m, "g": bm._plan.g,
+                                  "member_steps_per_s": Bb * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg1e":  # config 1 as an ensemble: linear 10-element cantilever, gravity, tip impulse, per-member E
             B, steps = 131072, 100
             rng = np.random.default_rng(2)
@@ -127,8 +134,8 @@ def main():
             X = torch.zeros(B, 60, dtype=torch.float64, device=dev)
             imp = TipImpulse(torch.full((B,), 0.1, dtype=torch.float64, device=dev))
             ms = timed(lambda: rk4_steps(beam, X, 0.0, 2.5e-5, steps, u=imp))
-            print(json.dumps({"config": "cfg1 x%d (linear 10 el + gravity + impulse), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
-                              "element_steps_per_s": B * 10 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg1 x%d (linear 10 el + gravity + impulse), RK4" % B, "m": beam._plan.m, "g": beam._plan.g,
+                              "element_steps_per_s": B * 10 * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg2m":  # config 2 shape with PER-MEMBER density and stiffness (no shared factor set)
             B, steps = 32768, 100
             e = ens.config2()
@@ -142,8 +149,8 @@ def main():
             X = torch.zeros(B, 120, dtype=torch.float64, device=dev)
             imp = TipImpulse(torch.full((B,), 0.1, dtype=torch.float64, device=dev))
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
-            print(json.dumps({"config": "cfg2 x%d with per-member density and stiffness, RK4" % B,
-                              "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg2 x%d with per-member density and stiffness, RK4" % B,
+                              "element_steps_per_s": B * 20 * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg3g":  # config 3 through the GENERAL kernel (comparison)
             B, steps = 65536, 50
             e = ens.config3(B, 32)
@@ -152,7 +159,7 @@ def main():
             beam.force_general_kernels = True
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
-            print(json.dumps({"config": "cfg3 general kernel", "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg3 general kernel", "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg3mid":  # config 3 with the implicit midpoint rule (h = 10 x the RK4 step)
             from continuum_robot_b200 import midpoint_steps
             B, steps = 65536, 50
@@ -162,9 +169,9 @@ def main():
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             hm = 10 * e.h
             ms = timed(lambda: midpoint_steps(beam, X, 0.0, hm, steps))
-            print(json.dumps({"config": "cfg3 implicit midpoint, h = 2e-4 (per-member factors of M + h^2/4 K)",
+            yield {"config": "cfg3 implicit midpoint, h = 2e-4 (per-member factors of M + h^2/4 K)",
                               "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms,
-                              "simulated_seconds_per_second_per_member": steps * hm / (ms * 1e-3)}))
+                              "simulated_seconds_per_second_per_member": steps * hm / (ms * 1e-3)}
         if name == "cfg3i":  # config 3 with a per-member tip impulse (the reference examples' input): IMP variant
             B, steps = 65536, 50
             e = ens.config3(B, 32)
@@ -173,8 +180,8 @@ def main():
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             imp = TipImpulse(torch.from_numpy(np.random.default_rng(3).uniform(0.05, 0.5, B)).to(dev), duration=1.0)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp))
-            print(json.dumps({"config": "cfg3 + tip impulse (paired fast kernel, forcing variant)",
-                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg3 + tip impulse (paired fast kernel, forcing variant)",
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg3m":  # config 3 with PER-MEMBER mass (density varies per member): no shared factors
             B, steps = 65536, 50
             e = ens.config3(B, 32)
@@ -184,8 +191,8 @@ def main():
             beam.create_system_func(); beam.create_input_func()
             X = torch.from_numpy(np.concatenate([e.q0, e.v0], axis=1)).to(dev)
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
-            print(json.dumps({"config": "cfg3 with per-member mass (paired fast kernel, per-member factor sets in shared memory)",
-                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}))
+            yield {"config": "cfg3 with per-member mass (paired fast kernel, per-member factor sets in shared memory)",
+                              "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}
         if name == "cfg4":  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
             B = 4096
             e = ens.config4(B)
@@ -204,9 +211,9 @@ def main():
             ms = timed(run, reps=2)
             r = out["r"]
             att = (r.naccept + r.nreject).double()
-            print(json.dumps({"config": "cfg4 4096 x 64 nonlinear RK45 to 3 ms", "m": beam._plan.m, "g": beam._plan.g, "ms": ms,
+            yield {"config": "cfg4 4096 x 64 nonlinear RK45 to 3 ms", "m": beam._plan.m, "g": beam._plan.g, "ms": ms,
                               "attempts_mean": float(att.mean()), "attempts_max": float(att.max()),
-                              "element_attempts_per_s": float(att.sum()) * 64 / (ms * 1e-3), "success": r.success}))
+                              "element_attempts_per_s": float(att.sum()) * 64 / (ms * 1e-3), "success": r.success}
         if name == "cfg5":  # LQR rollout, shared N = 6 design, 131072 members per GPU
             B, steps = 131072, 200
             e = ens.config5(B)
@@ -223,9 +230,18 @@ def main():
                 beam.force_general_kernels = general
                 X.zero_()
                 ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps, u=imp, controller=ctrl))
-                print(json.dumps({"config": "cfg5 LQR rollout 131072 x 6 el, RK4, " + ("banded kernel + DMMA feedback" if general else "shared-operator DMMA kernel"),
-                                  "element_steps_per_s": B * 6 * steps / (ms * 1e-3), "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}))
+                yield {"config": "cfg5 LQR rollout 131072 x 6 el, RK4, " + ("banded kernel + DMMA feedback" if general else "shared-operator DMMA kernel"),
+                                  "element_steps_per_s": B * 6 * steps / (ms * 1e-3), "member_steps_per_s": B * steps / (ms * 1e-3), "ms": ms}
             beam.force_general_kernels = False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="cfg2,cfg4,cfg5,cfg3g")
+    ap.add_argument("--slots", type=int, default=0)
+    a = ap.parse_args()
+    for r in run(a.only.split(","), a.slots):
+        print(json.dumps(r), flush=True)
 
 
 if __name__ == "__main__":

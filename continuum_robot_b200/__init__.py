@@ -19,7 +19,8 @@ from .force_registry import ForceRegistry, InputRegistry  # noqa: F401
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import continuum_robot_b200.ensembles`
     # stays NumPy-only.
-    if name in ("BatchedDynamicEulerBernoulliBeam", "BatchedEulerBernoulliBeam", "FluidDragForce", "GravityForce", "TipImpulse"):
+    if name in ("BatchedDynamicEulerBernoulliBeam", "BatchedEulerBernoulliBeam", "FluidDragForce", "GravityForce", "TipImpulse",
+                "SinusoidInput", "PiecewiseLinearInput"):
         from . import dynamic_beam
 
         return getattr(dynamic_beam, name)
@@ -31,7 +32,7 @@ def __getattr__(name):
         from . import control
 
         return getattr(control, name)
-    if name in ("tip_displacement", "beam_shapes", "cantilever_frequencies"):
+    if name in ("tip_displacement", "beam_shapes", "cantilever_frequencies", "output_selection"):
         from . import outputs
 
         return getattr(outputs, name)

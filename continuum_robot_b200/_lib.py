@@ -74,12 +74,16 @@ class CrbSystem(C.Structure):
         ("u_tab_v", C.c_void_p),
         ("u_tab_k", C.c_int32),
         ("u_time_shared", C.c_int32),
+        ("tile_counter", C.c_void_p),
+        ("out_sel_inv", C.c_void_p),
+        ("out_n_sel", C.c_int32),
     ]
 
 
 _SIGNATURES = {
     "crb_version": (C.c_int, []),
     "crb_abi_sizes": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "crb_probe_dfma": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "crb_last_error": (C.c_char_p, []),
     "crb_plan": (C.c_int, [C.c_int32, C.c_char_p, C.c_int32, C.POINTER(CrbPlan)]),
     "crb_assemble": (
@@ -99,6 +103,11 @@ _SIGNATURES = {
          C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_int32, C.c_void_p],
     ),
+    "crb_rk45_stage": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crb_rk45_control": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "crb_assemble_shifted": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32,
                                        C.c_double, C.c_void_p, C.c_void_p]),
     "crb_midpoint": (C.c_int, [C.POINTER(CrbPlan), C.POINTER(CrbSystem), C.c_void_p, C.c_int32, C.c_void_p, C.c_double,

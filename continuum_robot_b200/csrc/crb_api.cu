@@ -216,6 +216,9 @@ static int check_system(const char* who, const crb_plan_t* plan, const crb_syste
     return fail(CRB_E_ARG, "%s: per-member gains (gain_stride != 0) exclude gain_frag / shared_op", who);
   if (sys->imp_amp && (sys->imp_dof < 0 || sys->imp_dof >= plan->n_free))
     return fail(CRB_E_ARG, "%s: imp_dof %d outside [0,%d)", who, sys->imp_dof, plan->n_free);
+  if (sys->out_sel_inv && (sys->out_n_sel < 1 || sys->out_n_sel > 2 * plan->n_free))
+    return fail(CRB_E_ARG, "%s: out_n_sel must be in [1, 2n = %d] when out_sel_inv is set, got %d", who, 2 * plan->n_free,
+                sys->out_n_sel);
   if (sys->u_tab_v && (!sys->u_tab_t || sys->u_tab_k < 2))
     return fail(CRB_E_ARG, "%s: the input table needs its knots u_tab_t and u_tab_k >= 2 (got %d)", who, sys->u_tab_k);
   return 0;
@@ -326,7 +329,8 @@ extern "C" int crb_rk4(const crb_plan_t* plan, const crb_system_t* sys, double* 
       quiet.imp_amp = nullptr;
       if (k_off > 0)
         if (int rc = rk4_dispatch(plan, sys, X, t0, h, (int32_t)k_off, Y_out, save_every, st)) return rc;
-      double* Y2 = Y_out ? Y_out + (k_off / save_every) * (long long)sys->n_members * 2 * plan->n_free : nullptr;
+      const long long width = sys->out_sel_inv ? sys->out_n_sel : 2 * plan->n_free;
+      double* Y2 = Y_out ? Y_out + (k_off / save_every) * (long long)sys->n_members * width : nullptr;
       return rk4_dispatch(plan, &quiet, X, t0 + (double)k_off * h, h, nsteps - (int32_t)k_off, Y2, save_every, st);
     }
   }

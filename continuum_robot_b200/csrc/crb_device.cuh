@@ -24,6 +24,7 @@
 // Scalars of crb_plan_t that kernels need (the red_index table travels as a device array).
 struct KPlan {
   int N, n_free, n0, p_act, m, g, p, levels, contiguous, has_mask;
+  int n_sm;  // SMs of the device (persistent kernels)
   long long mfac_doubles;
 };
 
@@ -928,6 +929,21 @@ __device__ __forceinline__ void stage_compact_pm(const crb_system_t& S, const KP
   fm.fscan = dst + crb_compact_slot_doubles(M, G);
 }
 
+// One (q, v) pair of a recorded frame.  Full frames are state rows [q ; v]; lean frames (crb_system_t.out_sel_inv)
+// hold only the selected entries, at the columns the inverse selection table names.
+__device__ __forceinline__ int frame_width(const crb_system_t& S, int n) { return S.out_sel_inv ? S.out_n_sel : 2 * n; }
+__device__ __forceinline__ void frame_put(const int* __restrict__ sel_inv, double* __restrict__ ym, int n, int r, double qv,
+                                          double vv) {
+  if (sel_inv) {
+    const int cq = sel_inv[r], cv = sel_inv[n + r];
+    if (cq >= 0) ym[cq] = qv;
+    if (cv >= 0) ym[cv] = vv;
+  } else {
+    ym[r] = qv;
+    ym[n + r] = vv;
+  }
+}
+
 template <int M>
 __device__ __forceinline__ void load_state(const LaneCtx<M>& L, const double* __restrict__ X,
                                            double (&q)[M][3], double (&v)[M][3]) {
@@ -939,6 +955,20 @@ __device__ __forceinline__ void load_state(const LaneCtx<M>& L, const double* __
       const int r = L.ri[j][d];
       q[j][d] = r >= 0 ? x[r] : 0.0;
       v[j][d] = r >= 0 ? x[L.n + r] : 0.0;
+    }
+}
+// frame `frame` of a recording Y[T, B, width] (full or lean)
+template <int M>
+__device__ __forceinline__ void store_frame(const LaneCtx<M>& L, const crb_system_t& S, double* __restrict__ Y, long long frame,
+                                            const double (&q)[M][3], const double (&v)[M][3]) {
+  if (!L.active) return;
+  double* ym = Y + (frame * S.n_members + L.member) * frame_width(S, L.n);
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int r = L.ri[j][d];
+      if (r >= 0) frame_put(S.out_sel_inv, ym, L.n, r, q[j][d], v[j][d]);
     }
 }
 template <int M>

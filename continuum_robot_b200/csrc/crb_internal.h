@@ -32,6 +32,7 @@ inline KPlan kplan_of(const crb_plan_t* p) {
   k.contiguous = p->contiguous;
   k.has_mask = p->has_mask;
   k.mfac_doubles = p->mfac_doubles;
+  k.n_sm = 0;
   return k;
 }
 

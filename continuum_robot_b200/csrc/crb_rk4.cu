@@ -95,8 +95,7 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
         v[j][d] = av[j][d];
       }
     if (Y && save_every > 0 && (k + 1) % save_every == 0) {
-      const long long frame = (k + 1) / save_every - 1;
-      store_state<M>(L, Y + frame * (long long)S.n_members * 2 * L.n, q, v);
+      store_frame<M>(L, S, Y, (k + 1) / save_every - 1, q, v);
     }
   }
   store_state<M>(L, X, q, v);

@@ -160,7 +160,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   while (ie < A.n_eval && A.t_eval[ie] < t) ++ie;  // outputs before the current time are not ours
   if (ie < A.n_eval && A.t_eval[ie] == t && running) {
     // SciPy emits t_eval == t0 from the first step's interpolant at x = 0, i.e. y_old itself
-    store_state<M>(L, A.Y_eval + (long long)ie * S.n_members * 2 * L.n, q, v);
+    store_frame<M>(L, S, A.Y_eval, ie, q, v);
     ++ie;
   }
 
@@ -342,7 +342,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
         while (ie < A.n_eval && A.t_eval[ie] <= t_new) {
           const double x = (A.t_eval[ie] - t) / h;
           const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
-          double* out = A.Y_eval + ((long long)ie * S.n_members + L.member) * 2 * L.n;
+          double* out = A.Y_eval + ((long long)ie * S.n_members + L.member) * frame_width(S, L.n);
 #pragma unroll
           for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -360,8 +360,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
                 }
               }
               const double wcs = fma(T.pcs[0], x, fma(T.pcs[1], x2, fma(T.pcs[2], x3, T.pcs[3] * x4)));
-              out[r] = fma(h, fma(h, pq, wcs * v[j][d]), q[j][d]);
-              out[L.n + r] = fma(h, pv, v[j][d]);
+              frame_put(S.out_sel_inv, out, L.n, r, fma(h, fma(h, pq, wcs * v[j][d]), q[j][d]), fma(h, pv, v[j][d]));
             }
           ++ie;
         }

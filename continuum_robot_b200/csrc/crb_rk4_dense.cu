@@ -119,9 +119,8 @@ crb_rk4_dense_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
     q = fma(h6, v + 2.0 * v2 + 2.0 * v3 + v4, q);
     v = fma(h6, a1 + 2.0 * a2 + 2.0 * a3 + a4, v);
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && active && own) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + member) * 2 * n;
-      ym[lane] = q;
-      ym[n + lane] = v;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + member) * frame_width(S, n);
+      frame_put(S.out_sel_inv, ym, n, lane, q, v);
     }
   }
   if (active && own) {

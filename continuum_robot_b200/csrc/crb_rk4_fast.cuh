@@ -339,16 +339,13 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
       }
     }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * frame_width(S, n);
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const int r = rix(j, d);
-          if (!NC || r >= 0) {
-            ym[r] = w[j][d];
-            ym[n + r] = v[j][d];
-          }
+          if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, w[j][d], v[j][d]);
         }
     }
   }
@@ -536,16 +533,13 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
       }
     }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * frame_width(S, n);
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const int r = rix(j, d);
-          if (!NC || r >= 0) {
-            ym[r] = q[j][d];
-            ym[n + r] = v[j][d];
-          }
+          if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, q[j][d], v[j][d]);
         }
     }
   }
@@ -569,10 +563,11 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
 // current tile integrates in registers, results leave through a shared-memory buffer as one bulk store per tile
 // (and per recorded frame).  Same arithmetic, statement by statement, as crb_rk4_lin2_kernel.
 //
-// sel_inv (or NULL): lean recording.  sel_inv[r] = output column of state entry r (0 <= r < 2n) or -1; frames are
-// then Y[T, B, n_sel] holding only the selected entries (tip trace, node shapes: what the reference's callers read
-// from sol.y, examples/lqr_control.py:166-183, examples/example_utilities.py:173-205).
+// Lean recording (crb_system_t.out_sel_inv): frames are Y[T, B, out_n_sel] holding only the selected entries (tip
+// trace, node shapes: what the reference's callers read from sol.y, examples/lqr_control.py:166-183,
+// examples/example_utilities.py:173-205), written straight from the registers.
 // ==========================================================================================
+#define CRB_PERSIST_WARPS 1  // warps per block of the persistent kernels (see the barrier note in the kernel)
 template <int M, int LV>
 struct FastTileGeom {
   static constexpr int G = 1 << LV, mpw = 32 / G, LVE = LV > 0 ? LV : 1;
@@ -585,9 +580,9 @@ struct FastTileGeom {
 };
 
 template <int M, int LV, bool UC, bool IMP, bool NC = false>
-__global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(32 * CRB_PERSIST_WARPS, CRB_FAST_MINBLOCKS * CRB_FAST_WARPS / CRB_PERSIST_WARPS)
 crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
-                     double* __restrict__ Y, int save_every, const int* __restrict__ sel_inv, int n_sel) {
+                     double* __restrict__ Y, int save_every, int* __restrict__ tile_counter) {
   typedef FastTileGeom<M, LV> TG;
   constexpr int G = TG::G, mpw = TG::mpw;
   constexpr bool VEC = !NC && (3 * M) % 2 == 0;  // 128-bit shared-memory accesses of the lane's 3M-double runs
@@ -599,23 +594,23 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
   double* const in_x = smem + TG::FAC_PAD + warp * TG::WARP_DOUBLES;
   double* const in_k = in_x + mpw * TG::ROW_MAX;
   double* const out_x = in_k + mpw * TG::KC_ROW;
-  const unsigned bar = crb_smem_u32(smem + TG::FAC_PAD + CRB_FAST_WARPS * TG::WARP_DOUBLES) + 8u * warp;
+  const unsigned bar = crb_smem_u32(smem + TG::FAC_PAD + CRB_PERSIST_WARPS * TG::WARP_DOUBLES);
   const int n = P.n_free;
   const unsigned row_bytes = 16u * (unsigned)n;
-  // The tile loop runs on BLOCK tiles (CRB_FAST_WARPS consecutive warp tiles): its control flow depends on blockIdx only,
-  // so the compiler keeps the step loop in uniform control flow (no divergence guards around the shuffles); a warp
-  // whose tile lies beyond the ensemble integrates clamped garbage and moves no data.
+  // One warp per block, one tile (mpw consecutive members) at a time.  The first tile of a block is blockIdx.x; the
+  // following ones come from a global ticket counter (tile_counter, zeroed by the launcher) when the caller provides
+  // one: the warp schedulers are not fair (a warp that is favoured finishes a static share of the tiles up to 25 %
+  // early and leaves its sub-partition with a single warp and no latency hiding for the rest of the launch --
+  // measured 7.0 instead of 7.9 warps active per SM and 7 % more time per step), tickets keep every warp busy to
+  // the end.  Without a counter the tiles are dealt round-robin.
   const int n_tiles = (S.n_members + mpw - 1) / mpw;
-  const int n_btiles = (n_tiles + CRB_FAST_WARPS - 1) / CRB_FAST_WARPS;
 
-  auto tile_count = [&](int bt) -> int {  // members of this warp's tile in block tile bt (0: none)
-    const int m0 = (bt * CRB_FAST_WARPS + warp) * mpw;
-    return max(0, min(mpw, S.n_members - m0));
+  auto tile_count = [&](int bt) -> int {  // members of tile bt
+    return max(0, min(mpw, S.n_members - bt * mpw));
   };
   auto prefetch = [&](int bt) {  // one lane: the tile's state rows (+ stiffness coefficients) -> `in` buffers
-    const int m0 = (bt * CRB_FAST_WARPS + warp) * mpw;
+    const int m0 = bt * mpw;
     const unsigned cnt = (unsigned)tile_count(bt);
-    if (cnt == 0) return;
     const unsigned xb = cnt * row_bytes, kb = S.stiff_shared ? 0u : cnt * (unsigned)(TG::KC_ROW * 8);
     crb_mbar_expect_tx(bar, xb + kb);
     crb_bulk_load(crb_smem_u32(in_x), X + (long long)m0 * 2 * n, xb, bar);
@@ -624,7 +619,7 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
   if (lane == 0) {
     crb_mbar_init(bar, 1);
     crb_fence_mbar_init();
-    if ((int)blockIdx.x < n_btiles) prefetch(blockIdx.x);
+    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x);
   }
   {  // compact copy of the shared factor set (once per block and launch)
     const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * TG::LVE * G;
@@ -659,16 +654,14 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
   const double h6 = h / 6.0, hx = h * h / 6.0, h12 = h * h * h / 12.0;
   unsigned phase = 0;
 
-  for (int bt = blockIdx.x; bt < n_btiles; bt += gridDim.x) {
-    const int m0 = (bt * CRB_FAST_WARPS + warp) * mpw;
+  for (int bt = blockIdx.x; bt < n_tiles;) {
+    const int m0 = bt * mpw;
     const int member = m0 + ml;
     C.active = member < S.n_members;
     C.member = C.active ? member : S.n_members - 1;
     const unsigned cnt = (unsigned)tile_count(bt);
-    if (cnt) {
-      crb_mbar_wait(bar, phase);
-      phase ^= 1u;
-    }
+    crb_mbar_wait(bar, phase);
+    phase ^= 1u;
     double q[M][3], v[M][3], w[2][M][3];
     {
       const double* xs = in_x + ml * 2 * n;
@@ -703,10 +696,18 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
       }
     }
     __syncwarp();  // every lane has its tile in registers: the `in` buffers are free for the next tile
-    if (lane == 0 && bt + (int)gridDim.x < n_btiles) prefetch(bt + gridDim.x);
-    // Aligned block barrier, for the COMPILER: after the barrier spin and the one-lane prefetch it cannot prove that
-    // the warp is converged and would guard every shuffle of the step loop (BRA.DIV + register copies, +8 %
-    // instructions, measured 15 % slower); both warps of the block walk the same block tiles, so it costs nothing.
+    int nxt = bt + (int)gridDim.x;
+    if (tile_counter) {
+      int ticket = 0;
+      if (lane == 0) ticket = atomicAdd(tile_counter, 1);
+      nxt = __shfl_sync(CRB_FULL_MASK, ticket, 0) + (int)gridDim.x;
+    }
+    if (lane == 0 && nxt < n_tiles) prefetch(nxt);
+    // One-warp blocks: this block barrier is a WARP convergence point that costs nothing, and it is there for the
+    // compiler -- after the barrier spin and the one-lane prefetch it cannot prove that the warp is converged and
+    // would guard every shuffle of the step loop (BRA.DIV + register copies: +8 % instructions, measured 15 % slower).
+    // Blocks of several warps would be tied together by it and run their identical instruction streams in lockstep,
+    // colliding on the FP64 and shuffle pipes instead of interleaving (measured 8 % slower than free-running warps).
     __syncthreads();
 
     // forcing in acceleration space: cu = M^-1 (u_const + f_ext), ci = amp * M^-1 e_k
@@ -763,11 +764,11 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
       }
       crb_fence_proxy_async();  // generic-proxy writes above -> visible to the bulk-copy (async) proxy
       __syncwarp();
-      if (lane == 0 && cnt) {
+      if (lane == 0) {
         crb_bulk_store(dst, crb_smem_u32(out_x), cnt * row_bytes);
         crb_bulk_commit();
       }
-      __syncthreads();  // aligned barrier: the compiler knows the warps are converged again (uniform step loop)
+      __syncthreads();
     };
 
     for (int k = 0; k < nsteps; ++k) {
@@ -822,19 +823,15 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
       }
       if (Y && save_every > 0 && (k + 1) % save_every == 0) {
         const long long frame = (k + 1) / save_every - 1;
-        if (sel_inv) {  // lean frame: only the selected state entries
+        if (S.out_sel_inv) {  // lean frame: only the selected state entries
           if (C.active) {
-            double* ym = Y + (frame * S.n_members + C.member) * n_sel;
+            double* ym = Y + (frame * S.n_members + C.member) * S.out_n_sel;
 #pragma unroll
             for (int j = 0; j < M; ++j)
 #pragma unroll
               for (int d = 0; d < 3; ++d) {
                 const int r = rix(j, d);
-                if (!NC || r >= 0) {
-                  const int cq = sel_inv[r], cv = sel_inv[n + r];
-                  if (cq >= 0) ym[cq] = q[j][d];
-                  if (cv >= 0) ym[cv] = v[j][d];
-                }
+                if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, q[j][d], v[j][d]);
               }
           }
           __syncthreads();
@@ -844,6 +841,7 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
       }
     }
     store_tile(X + (long long)m0 * 2 * n);
+    bt = nxt;
   }
   if (lane == 0) crb_bulk_wait<0>();  // the last stores have left shared memory before the block retires
 }
@@ -907,16 +905,13 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         v[j][d] += dv;
       }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * 2 * n;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * frame_width(S, n);
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const int r = rix(j, d);
-          if (!NC || r >= 0) {
-            ym[r] = q[j][d];
-            ym[n + r] = v[j][d];
-          }
+          if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, q[j][d], v[j][d]);
         }
     }
   }

@@ -5,31 +5,36 @@
 #include "crb_rk4_fast.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 template <int M, int LV, bool PM>
 static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
-                  double* Y_out, int save_every, cudaStream_t stream, const int32_t* sel_inv = nullptr, int n_sel = 0) {
+                  double* Y_out, int save_every, cudaStream_t stream) {
   const int mpb = CRB_FAST_WARPS * (32 >> LV);
   // compact factor copy: ONE shared set, or (PM) one region per member of the block
   const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
   const int grid = (sys->n_members + mpb - 1) / mpb;
-  const KPlan P = kplan_of(plan);
+  KPlan P = kplan_of(plan);
+  P.n_sm = crb_sm_count();
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
   // shared mass factors: persistent paired kernel (bulk-copy tiles; needs 16-byte aligned rows); per-member factors
   // (PM) and lean-recording requests it cannot serve keep the one-tile-per-block kernel
-  const bool bulk_ok = !PM && (((uintptr_t)X | (uintptr_t)Y_out | (uintptr_t)sys->kcoef) & 15) == 0;
-  if (sel_inv && !bulk_ok) return 1;
+  const bool bulk_ok = !PM && (((uintptr_t)X | (uintptr_t)(sys->out_sel_inv ? nullptr : Y_out) | (uintptr_t)sys->kcoef) & 15) == 0;
 #define CRB_LIN2N(UCV, IMPV, NCV)                                                                             \
   {                                                                                                            \
     if constexpr (!PM) {                                                                                       \
       if (bulk_ok) {                                                                                           \
         typedef FastTileGeom<M, LV> TG;                                                                        \
-        const size_t pbytes = TG::smem_bytes(CRB_FAST_WARPS);                                                  \
+        const size_t pbytes = TG::smem_bytes(CRB_PERSIST_WARPS);                                               \
         const int n_tiles = (sys->n_members + TG::mpw - 1) / TG::mpw;                                          \
-        const int pgrid = std::min((n_tiles + CRB_FAST_WARPS - 1) / CRB_FAST_WARPS, crb_sm_count() * CRB_FAST_MINBLOCKS); \
+        const int pgrid = std::min((n_tiles + CRB_PERSIST_WARPS - 1) / CRB_PERSIST_WARPS,                      \
+                                   P.n_sm * CRB_FAST_MINBLOCKS * CRB_FAST_WARPS / CRB_PERSIST_WARPS);          \
         if (int rc = set_smem(crb_rk4_lin2p_kernel<M, LV, UCV, IMPV, NCV>, pbytes, "crb_rk4")) return rc;      \
-        crb_rk4_lin2p_kernel<M, LV, UCV, IMPV, NCV><<<pgrid, CRB_FAST_THREADS, pbytes, stream>>>(              \
-            P, *sys, X, t0, h, nsteps, Y_out, save_every, sel_inv, n_sel);                                     \
+        if (sys->tile_counter && n_tiles > pgrid)                                                              \
+          if (cudaMemsetAsync(sys->tile_counter, 0, sizeof(int32_t), stream) != cudaSuccess)                   \
+            return crb_fail(CRB_E_CUDA, "crb_rk4: cannot reset the tile counter");                             \
+        crb_rk4_lin2p_kernel<M, LV, UCV, IMPV, NCV><<<pgrid, 32 * CRB_PERSIST_WARPS, pbytes, stream>>>(        \
+            P, *sys, X, t0, h, nsteps, Y_out, save_every, n_tiles > pgrid ? sys->tile_counter : nullptr);      \
         return 0;                                                                                              \
       }                                                                                                        \
     }                                                                                                          \
@@ -43,7 +48,6 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   }
 #define CRB_LIN2(UCV, IMPV) CRB_LIN2N(UCV, IMPV, false)
   const bool nc = !(plan->contiguous && plan->p_act == plan->p);
-  if (sel_inv && (sys->grav_mode == 1 || sys->force_staged)) return 1;  // lean recording: paired persistent kernel only
   if (sys->grav_mode == 1) {  // slot-space gravity: stage-by-stage kernel (the force is nonlinear in the rotations)
     if (PM || uc) return 1;
     if constexpr (!PM) {

@@ -193,6 +193,8 @@ struct SharedArgs {
   double imp_duration;
   int n_members, n, blob_doubles;
   int o_wq, o_wv, o_pf, o_gc, o_gs, o_c0, o_mi;
+  const int* sel_inv;  // lean recording (crb_system_t.out_sel_inv) or NULL
+  int n_sel;
 };
 
 template <int KQ, int GKP, bool IMP>
@@ -282,14 +284,11 @@ crb_rk4_shared_kernel(SharedArgs A, double* __restrict__ X, double t0, double h,
       v[i] = av[i];
     }
     if (Y && save_every > 0 && (k + 1) % save_every == 0 && active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * A.n_members + mem) * 2 * n;
+      double* ym = Y + ((long long)((k + 1) / save_every - 1) * A.n_members + mem) * (A.sel_inv ? A.n_sel : 2 * n);
 #pragma unroll
       for (int i = 0; i < KQ; ++i) {
         const int r = 4 * i + j;
-        if (r < n) {
-          ym[r] = q[i];
-          ym[n + r] = v[i];
-        }
+        if (r < n) frame_put(A.sel_inv, ym, n, r, q[i], v[i]);
       }
     }
   }
@@ -323,6 +322,8 @@ int crb_launch_rk4_shared(const crb_plan_t* plan, const crb_system_t* sys, doubl
   A.imp_amp = sys->imp_amp;
   A.imp_duration = sys->imp_duration;
   A.n_members = sys->n_members;
+  A.sel_inv = sys->out_sel_inv;
+  A.n_sel = sys->out_n_sel;
   A.n = n;
   A.blob_doubles = (int)D.total;
   A.o_wq = (int)D.o_wq; A.o_wv = (int)D.o_wv; A.o_pf = (int)D.o_pf; A.o_gc = (int)D.o_gc; A.o_gs = (int)D.o_gs;

@@ -588,6 +588,10 @@ class BatchedDynamicEulerBernoulliBeam:
         s.all_nonlinear = int(bool(np.all(self._etype == 1)))
         s.force_general = int(self.force_general_kernels)
         s.force_staged = int(self.force_staged_kernels)
+        tc = self.__dict__.get("_tile_counter")
+        if tc is None:  # ticket counter of the persistent kernels (one per beam object: its launches share a stream)
+            tc = self.__dict__["_tile_counter"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        s.tile_counter = tc.data_ptr()
         if drag is not None:
             if drag.fluid_density != self.force_params.fluid_density:
                 raise ValueError("FluidDragForce.fluid_density differs from the assembled ForceParams.fluid_density")
@@ -799,14 +803,17 @@ class BatchedDynamicEulerBernoulliBeam:
             raise TypeError("force callables must return torch tensors on the CUDA device (no CPU fallback)")
         return f
 
-    def _rhs(self, t: float, x, u=None, impulse=None, gain=None, ref=None, time_inputs=()):
+    def _rhs(self, t: float, x, u=None, impulse=None, gain=None, ref=None, time_inputs=(), out=None):
         torch = _torch()
         B = x.shape[0]
         drag, grav, user = self._active_forces()
         f_ext = self._external_forces(x, user)
         sysm, keep = self.make_system(B, drag=drag, gravity=grav, u_const=u, impulse=impulse, gain=gain, ref=ref, f_ext=f_ext,
                                       time_inputs=time_inputs)
-        out = torch.empty_like(x)
+        if out is None:
+            out = torch.empty_like(x)
+        elif out.shape != x.shape or not out.is_contiguous() or out.dtype != torch.float64:
+            raise ValueError("out must be a contiguous float64 tensor shaped like x")
         with torch.cuda.device(self.device):
             rc = _lib.load().crb_rhs(C.byref(self._plan), C.byref(sysm), x.data_ptr(), float(t), out.data_ptr(), self._stream())
         _lib.check(rc)
@@ -870,21 +877,22 @@ class BatchedDynamicEulerBernoulliBeam:
 
     def get_dynamic_system(self) -> Callable:
         """dynamic_beam_model.py:332-364: f(t, x[B,2n], u) with u a tensor [B,n] / [n], a callable
-        of t returning one, a TipImpulse, or None."""
+        of t returning one, a TipImpulse / SinusoidInput / PiecewiseLinearInput (evaluated inside the kernel), a
+        list of such parts (their sum), or None."""
         if self.system_func is None or self.input_func is None:
             raise RuntimeError("System and input functions must be created first")
         torch = _torch()
 
         def dynamic_system(t, x, u=None):
             xs, squeeze = self._as_state(x)
-            impulse = None
-            if isinstance(u, TipImpulse):
-                impulse, force = u, None
-            else:
-                force = u(t) if callable(u) else u
-            if force is not None:
-                if not isinstance(force, torch.Tensor):
+            uc, impulse, tv, other = split_input(u)
+            force = uc
+            if other is not None:
+                val = other(t)
+                if not isinstance(val, torch.Tensor):
                     raise ValueError("State and input must be torch tensors")
+                force = val if force is None else force + val
+            if force is not None:
                 if force.shape[-1] != self.n_free:
                     raise ValueError(
                         f"Input vector length {force.shape[-1]} must match position DOFs {self.n_free}. "
@@ -892,7 +900,7 @@ class BatchedDynamicEulerBernoulliBeam:
                     )
                 if force.ndim == 1:
                     force = force.unsqueeze(0)
-            out = self._rhs(float(t), xs, u=force, impulse=impulse)
+            out = self._rhs(float(t), xs, u=force, impulse=impulse, time_inputs=tv)
             return out[0] if squeeze else out
 
         return dynamic_system

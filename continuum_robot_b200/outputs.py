@@ -14,6 +14,31 @@ from __future__ import annotations
 import numpy as np
 
 
+def output_selection(beam, what):
+    """State indices a lean recording keeps (``solve_ensemble(..., outputs=...)`` / ``rk4_steps(..., out_sel=...)``):
+    the kernels then write frames ``[T, B, len(selection)]`` instead of the whole state ``[T, B, 2n]``.
+
+      * ``"tip"``             ``[n - 2]``: the tip trace ``sol.y[n_pos - 2]`` of examples/lqr_control.py:166-183
+      * ``"shape"``           transverse displacement ``w`` of every node that has one, in node order
+      * ``"shape_velocity"``  ``y[n_pos + 1 :: 3]``: what examples/example_utilities.py:173-205 actually reads (Q7)
+      * a sequence of state indices (0 <= r < 2n, no repeats)
+    """
+    n = beam.n_free
+    if isinstance(what, str):
+        if what == "tip":
+            return [n - 2]
+        if what == "shape":
+            nodes = sorted(nd for (prm, nd) in beam.node_param_to_state if prm == "w")
+            return [beam.node_param_to_state[("w", nd)] for nd in nodes]
+        if what == "shape_velocity":
+            return list(range(n + 1, 2 * n, 3))
+        raise ValueError(f"unknown output selection {what!r} (expected 'state', 'tip', 'shape', 'shape_velocity' or indices)")
+    idx = [int(r) for r in what]
+    if not idx or min(idx) < 0 or max(idx) >= 2 * n or len(set(idx)) != len(idx):
+        raise ValueError(f"output selection must be distinct state indices in [0, {2 * n})")
+    return idx
+
+
 def tip_displacement(y):
     """y[B, 2n, T] (or [2n, T]) -> tip transverse displacement [B, T] (reduced DOF n-2)."""
     n = y.shape[-2] // 2

@@ -137,6 +137,18 @@ typedef struct crb_system_t {
   const double* u_tab_v;    /* [u_tab_k, B, n] (or [u_tab_k, n]) */
   int32_t u_tab_k;          /* >= 2 when u_tab_v is set */
   int32_t u_time_shared;
+  /* Optional scratch for the persistent kernels: ONE device int32, caller-owned, used as the ticket counter of
+   * their dynamic tile scheduling (zeroed on the stream by every launch that uses it, so launches that share a
+   * counter must be ordered: same stream, or distinct counters).  NULL: tiles are dealt round-robin (7 % slower on
+   * config 3: the warp schedulers are not fair, see crb_rk4_fast.cuh). */
+  int32_t* tile_counter;
+  /* Lean recording.  Callers of the reference read a few rows of sol.y after the step loop -- the tip trace
+   * y[n-2] (examples/lqr_control.py:166-183) or one entry per node for the beam shape
+   * (examples/example_utilities.py:173-205) -- not the whole state.  out_sel_inv (device int32 [2n], or NULL):
+   * column of state entry r in a recorded frame, or -1 for entries that are not recorded; frames written by
+   * crb_rk4 / crb_midpoint (Y_out) and crb_rk45 (Y_eval) are then [T, B, out_n_sel] instead of [T, B, 2n]. */
+  const int32_t* out_sel_inv;
+  int32_t out_n_sel;
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */
@@ -144,6 +156,10 @@ int crb_version(void);
 /* sizeof(crb_plan_t), sizeof(crb_system_t) of the build: a binding that mirrors the structs (ctypes, cgo ...) checks
  * its own layout against these before the first call */
 int crb_abi_sizes(int32_t* plan_bytes, int32_t* system_bytes);
+/* Machine probe for the roofline denominator of FP64-bound kernels: enqueues `iters` rounds of 8 independent FMA chains
+ * per thread on every SM and reports the flops that launch executes in *flops_out (the caller times it with events).
+ * scratch: device, at least *flops_out / (16 iters) doubles (one per thread); scratch = NULL only queries flops_out. */
+int crb_probe_dfma(int32_t iters, double* scratch, int64_t scratch_doubles, int64_t* flops_out, void* stream);
 /* thread-local text of the last error returned on this thread ("" if none) */
 const char* crb_last_error(void);
 
@@ -234,6 +250,26 @@ int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double*
              double* h_abs, double t_bound, double rtol, double atol, const double* t_eval,
              int32_t n_eval, double* Y_eval, int32_t* status, int64_t* counters,
              int32_t max_attempts, void* stream);
+
+/* Building blocks of the UNFUSED adaptive driver, for right-hand sides that contain user code (torch force
+ * plug-ins, models/abstractions.py:153-173; free-form input callables u(t) as in the reference's own tests,
+ * tests/test_dynamic_beam.py:201-244).  The host evaluates the stage derivatives K[s] = f(ts, Ys) (crb_rhs plus
+ * the user's code); stage combination, error norm, SciPy's step controller (scipy/integrate/_ivp/rk.py:111-176),
+ * dense output at t_eval and the set-up of the next attempt run on the device, one (t, h) per member, without a
+ * host synchronisation inside an attempt.  All arrays are device memory: Y, Ys, Ynew [B, n2]; K [7, B, n2];
+ * t, t_next, h_abs, h_step, ts [B]; ie, status, flags int32 [B]; counters int64 [B, 3] (nfev, accepted, rejected).
+ *   crb_rk45_stage   Ys = Y + h_step * sum_{l < stage} a[stage][l] K[l], ts = t + c[stage] h_step;
+ *                    stage = 1..5, or 6 for y_new (the 5th-order weights)
+ *   crb_rk45_control begin_only = 1: only set up the first attempt (h_abs must hold the initial step; flags = 5:
+ *                    running | first attempt of a step); begin_only = 0: close the attempt whose K[0..6], Ynew are
+ *                    complete (accept: Y <- Ynew, K[0] <- K[6], t <- t_next, outputs for t_eval in (t, t_next])
+ *                    and set up the next one (h_step = 0 for members that are finished or failed). */
+int crb_rk45_stage(int32_t n2, int32_t n_members, int32_t stage, const double* Y, const double* K, const double* t,
+                   const double* h_step, double* Ys, double* ts, void* stream);
+int crb_rk45_control(int32_t n2, int32_t n_members, double* Y, double* K, const double* Ynew, double* t,
+                     double* t_next, double* h_abs, double* h_step, double t_bound, double rtol, double atol,
+                     const double* t_eval, int32_t n_eval, int32_t* ie, double* Y_eval, int32_t* status,
+                     int64_t* counters, int32_t* flags, int32_t begin_only, void* stream);
 
 /* Host only.  Re-tile a shared feedback gain[n,2n] (control/full_state_linear.py:58) into the
  * B-fragment order of mma.sync.m8n8k4.f64 for the lane layout of `plan` (requires plan->g == 4):

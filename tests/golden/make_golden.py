@@ -336,11 +336,101 @@ def gen_cfg5():
     np.savez_compressed(os.path.join(HERE, "cfg5_samples.npz"), **d)
     print("cfg5 done", d["Y"].shape, "max Re(eig A_cl) =", np.max(np.linalg.eigvals(A - Bm @ gain).real))
 
+# ------------------------------------------------------------------------------------------
+# RK45 with time-varying inputs u(t) and state-aware plug-in forces (the drop-in boundary's callable paths)
+def _run_inputs(task):
+    from scipy.integrate import solve_ivp
+
+    name, eps = task  # eps: relative perturbation of the input (rounding-sensitivity study of the reference itself)
+
+    from continuum_robot.models.abstractions import AbstractForce
+
+    out = {}
+    if name in ("sin_lin4", "sin_nl4"):
+        # tests/test_dynamic_beam.py:19-41 beam files, :201-244 integration: u(t) = sin(t) * ones(n), default RK45
+        tname = "linear" if name == "sin_lin4" else "nonlinear"
+        csv = write_csv([0.25] * 4, [75e9] * 4, [4.91e-10] * 4, [6450] * 4, [7.85e-5] * 4, [tname] * 4,
+                        ["FIXED", "NONE", "NONE", "NONE"], [0.001] * 4, [0.5] * 4)
+        beam = make_beam(csv)
+        os.unlink(csv)
+        n = beam.beam_model.M.shape[0]
+        f = beam.get_dynamic_system()
+        fun = lambda t, x: f(t, x, (1.0 + eps) * np.sin(t) * np.ones(n))  # noqa: E731
+        t_span, rtol, atol = (0.0, 0.1), 1e-3, 1e-6
+        t_eval = np.linspace(0.0, 0.1, 11)
+    else:
+        # tests/test_advanced_composition.py:13-20 mixed beam, :36-65 StateAwareForce (spring-damper on the tip),
+        # drag + gravity on (:91-93), plus a sinusoidal input on every DOF
+        csv = write_csv([0.2] * 5, [200e9] * 5, [1e-8] * 5, [8000] * 5, [1e-4] * 5,
+                        ["linear", "linear", "nonlinear", "nonlinear", "nonlinear"],
+                        ["FIXED", "NONE", "NONE", "NONE", "NONE"], [1e-4] * 5, [1.2] * 5)
+        from continuum_robot.models.dynamic_beam_model import DynamicEulerBernoulliBeam
+        from continuum_robot.models.force_params import ForceParams
+
+        beam = DynamicEulerBernoulliBeam(csv, force_params=ForceParams(
+            fluid_density=1000.0, enable_fluid_effects=True, enable_gravity_effects=True))
+        os.unlink(csv)
+
+        class StateAwareForce(AbstractForce):
+            def __init__(self, stiffness, damping):
+                self.stiffness, self.damping = stiffness, damping
+
+            def compute_forces(self, x, t):
+                ns = len(x) // 2
+                forces = np.zeros(ns)
+                forces[ns - 2] = -self.stiffness * x[ns - 2] - self.damping * x[ns + ns - 2]
+                return forces
+
+            def is_enabled(self):
+                return True
+
+        beam.force_registry.register(StateAwareForce(500.0, 5.0))
+        beam.create_system_func()
+        beam.create_input_func()
+        n = beam.beam_model.M.shape[0]
+        f = beam.get_dynamic_system()
+        amp = 2.0 + np.arange(n) % 3
+        fun = lambda t, x: f(t, x, (1.0 + eps) * amp * np.sin(2 * np.pi * 120.0 * t + 0.3))  # noqa: E731
+        out["amp"] = amp
+        t_span, rtol, atol = (0.0, 0.004), 1e-6, 1e-9
+        t_eval = np.linspace(0.0, 0.004, 9)
+    x0 = np.zeros(2 * n)
+    sol = solve_ivp(fun, t_span, x0, method="RK45", t_eval=t_eval, rtol=rtol, atol=atol)
+    if eps != 0.0:
+        return (name, eps), {"y": sol.y}
+    sol2 = solve_ivp(fun, t_span, x0, method="RK45", rtol=rtol, atol=atol)
+    out.update({f"{k}": v for k, v in parsed(beam).items()})
+    out.update({"y": sol.y, "t_eval": t_eval, "nfev": np.array(sol.nfev), "status": np.array(sol.status),
+                "steps_t": sol2.t, "final": sol2.y[:, -1], "rtol": np.array(rtol), "atol": np.array(atol),
+                "t_span": np.array(t_span)})
+    return (name, eps), out
+
+
+def gen_inputs():
+    names = ["sin_lin4", "sin_nl4", "plugin_mixed5"]
+    # `noise`: how far the REFERENCE's own outputs move when u is scaled by (1 + eps), eps at rounding level.  At
+    # rtol = 1e-3 these beams are integrated at the stability limit and the accept / reject sequence amplifies
+    # rounding, so the reference solution is only determined up to this band; parity tests add it to the tolerance.
+    perturb = [1e-14, -1e-14, 1e-13, -1e-13]
+    tasks = [(nm, 0.0) for nm in names] + [(nm, e) for nm in names for e in perturb]
+    with Pool(min(len(tasks), os.cpu_count())) as p:
+        res = dict(p.map(_run_inputs, tasks))
+    d = {}
+    for name in names:
+        out = res[(name, 0.0)]
+        out["noise"] = np.max([np.abs(res[(name, e)]["y"] - out["y"]) for e in perturb], axis=0)
+        for k, v in out.items():
+            d[f"{name}/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "rk45_inputs.npz"), **d)
+    print("rk45_inputs done", {k: (v.shape, ) for k, v in d.items() if k.endswith("/y")},
+          {k: int(v) for k, v in d.items() if k.endswith("nfev")},
+          {k: float((v / (d[k[:-5] + "atol"] + d[k[:-5] + "rtol"] * np.abs(d[k[:-5] + "y"]))).max()) for k, v in d.items() if k.endswith("noise")})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="rhs,cfg12,cfg3,cfg4,cfg5")
+    ap.add_argument("--only", default="rhs,cfg12,cfg3,cfg4,cfg5,inputs")
     a = ap.parse_args()
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     for name in a.only.split(","):
-        {"rhs": gen_rhs, "cfg12": gen_cfg12, "cfg3": gen_cfg3, "cfg4": gen_cfg4, "cfg5": gen_cfg5}[name]()
+        {"rhs": gen_rhs, "cfg12": gen_cfg12, "cfg3": gen_cfg3, "cfg4": gen_cfg4, "cfg5": gen_cfg5, "inputs": gen_inputs}[name]()
