@@ -417,8 +417,9 @@ def test_midpoint_entry_points_validate_before_touching_the_device():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (CPU port, no GPU needed): one JSON line with the driver-contract keys;
-    under a multi-rank launch only rank 0 prints."""
+    """`bench.py --impl reference` (the reference from oracle/_ref where oracle/build_ref.py installed it, else the
+    CPU port; no GPU needed): one JSON line with the driver-contract keys; under a multi-rank launch only rank 0
+    prints."""
     import json
     import subprocess
     import sys
@@ -432,7 +433,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    have_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "continuum_robot"))
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and "workload" in d["config"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
