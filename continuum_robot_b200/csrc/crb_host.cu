@@ -44,31 +44,39 @@ static int ensure_events(crb_pipeline* p, size_t n) {
   return 0;
 }
 
-extern "C" int crb_pipeline_create(crb_pipeline_t** out) {
-  if (!out) return crb_fail(CRB_E_ARG, "crb_pipeline_create: null output");
-  crb_pipeline* p = new crb_pipeline();
+extern "C" int crb_pipeline_destroy(crb_pipeline_t* p);
+
+static int pipeline_build(crb_pipeline* p) {
   CRB_CUDA(cudaGetDevice(&p->device), "crb_pipeline_create");
   CRB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking), "crb_pipeline_create");
   CRB_CUDA(cudaStreamCreateWithFlags(&p->s_cmp, cudaStreamNonBlocking), "crb_pipeline_create");
   CRB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking), "crb_pipeline_create");
   CRB_CUDA(cudaEventCreateWithFlags(&p->ev_entry, cudaEventDisableTiming), "crb_pipeline_create");
   CRB_CUDA(cudaEventCreateWithFlags(&p->ev_all_out, cudaEventDisableTiming), "crb_pipeline_create");
+  return 0;
+}
+
+extern "C" int crb_pipeline_create(crb_pipeline_t** out) {
+  if (!out) return crb_fail(CRB_E_ARG, "crb_pipeline_create: null output");
+  crb_pipeline* p = new crb_pipeline();
+  if (int rc = pipeline_build(p)) {  // release whatever was created before the failure (the error text is kept)
+    crb_pipeline_destroy(p);
+    return rc;
+  }
   *out = p;
   return 0;
 }
 
 extern "C" int crb_pipeline_destroy(crb_pipeline_t* p) {
   if (!p) return 0;
-  cudaStreamSynchronize(p->s_in);
-  cudaStreamSynchronize(p->s_cmp);
-  cudaStreamSynchronize(p->s_out);
+  for (cudaStream_t st : {p->s_in, p->s_cmp, p->s_out})
+    if (st) cudaStreamSynchronize(st);
   for (auto v : {&p->ev_in, &p->ev_cmp, &p->ev_out})
     for (cudaEvent_t e : *v) cudaEventDestroy(e);
-  cudaEventDestroy(p->ev_entry);
-  cudaEventDestroy(p->ev_all_out);
-  cudaStreamDestroy(p->s_in);
-  cudaStreamDestroy(p->s_cmp);
-  cudaStreamDestroy(p->s_out);
+  if (p->ev_entry) cudaEventDestroy(p->ev_entry);
+  if (p->ev_all_out) cudaEventDestroy(p->ev_all_out);
+  for (cudaStream_t st : {p->s_in, p->s_cmp, p->s_out})
+    if (st) cudaStreamDestroy(st);
   delete p;
   return 0;
 }
@@ -144,7 +152,7 @@ extern "C" int crb_rk4_host(crb_pipeline_t* p, const crb_plan_t* plan, const crb
   CRB_CUDA(cudaEventRecord(p->ev_entry, (cudaStream_t)stream), "crb_rk4_host");
   CRB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_entry, 0), "crb_rk4_host");
   if (p->pending && !same) CRB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_all_out, 0), "crb_rk4_host");
-  for (size_t c = 0; c < nchunks; ++c) {
+  auto enqueue_chunk = [&](size_t c) -> int {
     const long long lo = (long long)c * chunk;
     const int cnt = (int)((lo + chunk <= B) ? chunk : B - lo);
     const size_t bytes = sizeof(double) * (size_t)cnt * row;
@@ -161,6 +169,24 @@ extern "C" int crb_rk4_host(crb_pipeline_t* p, const crb_plan_t* plan, const crb
     CRB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[c], 0), "crb_rk4_host");
     CRB_CUDA(cudaMemcpyAsync(xh, xd, bytes, cudaMemcpyDeviceToHost, p->s_out), "crb_rk4_host");
     CRB_CUDA(cudaEventRecord(p->ev_out[c], p->s_out), "crb_rk4_host");
+    return 0;
+  };
+  for (size_t c = 0; c < nchunks; ++c) {
+    if (int rc = enqueue_chunk(c)) {
+      // chunks < c are already in flight: close the call so that crb_pipeline_wait covers them, and forget the layout
+      // so that the next call takes the full-wait path instead of the chunk-wise cross-call ordering
+      cudaStreamWaitEvent(p->s_out, p->ev_entry, 0);
+      cudaStreamWaitEvent(p->s_out, p->ev_in[c], 0);  // may be stale: harmless, it only adds ordering
+      for (cudaStream_t st : {p->s_in, p->s_cmp}) {
+        cudaEvent_t tail = p->ev_cmp[c];
+        if (cudaEventRecord(tail, st) == cudaSuccess) cudaStreamWaitEvent(p->s_out, tail, 0);
+      }
+      cudaEventRecord(p->ev_all_out, p->s_out);
+      p->last_host = p->last_dev = nullptr;
+      p->last_members = 0;
+      p->pending = true;
+      return rc;
+    }
   }
   CRB_CUDA(cudaEventRecord(p->ev_all_out, p->s_out), "crb_rk4_host");
   p->last_host = X_host;

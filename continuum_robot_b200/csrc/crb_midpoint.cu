@@ -1,4 +1,6 @@
 // crb_midpoint.cu -- launcher of the implicit-midpoint kernels (own translation unit: parallel nvcc builds).
+#include <algorithm>
+
 #include "crb_internal.h"
 #include "crb_rk4_fast.cuh"
 
@@ -9,7 +11,14 @@ template <int M, int LV, bool PM>
 static int launch_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* afac, double* X, double t0,
                            double h, int nsteps, double* Y_out, int save_every, cudaStream_t stream) {
   const int mpb = CRB_FAST_WARPS * (32 >> LV);
-  const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
+  // compact factor copy (one shared set, or one region per member of the block), then the staging rows of recorded
+  // full-state frames (FrameWriter)
+  const int fac_doubles = ((crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1)) + 1) & ~1;
+  // per warp: staging rows of full frames [mpw][2n], or the column table of a lean recording [6M][32] int32
+  const bool stage = Y_out && (sys->out_sel_inv || ((uintptr_t)Y_out & 15) == 0);
+  const int stage_off = stage ? fac_doubles : 0;
+  const int stage_stride = (std::max((32 >> LV) * 2 * plan->n_free, 96 * M) + 1) & ~1;
+  const size_t bytes = sizeof(double) * ((size_t)fac_doubles + (stage ? (size_t)CRB_FAST_WARPS * stage_stride : 0));
   const int grid = (sys->n_members + mpb - 1) / mpb;
   const KPlan P = kplan_of(plan);
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
@@ -17,7 +26,7 @@ static int launch_midpoint(const crb_plan_t* plan, const crb_system_t* sys, cons
   {                                                                                                           \
     if (int rc = set_smem(crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_midpoint")) return rc;  \
     crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, afac, X, t0, h, nsteps, \
-                                                                                             Y_out, save_every); \
+                                                                                             Y_out, save_every, stage_off, stage_stride); \
   }
   if (!(plan->contiguous && plan->p_act == plan->p)) {  // any boundary conditions / phantom slots: NC variants
     if (uc || imp) CRB_MID(true, true, true)

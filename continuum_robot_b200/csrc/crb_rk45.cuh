@@ -110,8 +110,11 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 // slowest member, so the adaptive kernel runs with small blocks (2 warps; the hardware block scheduler
 // then balances the ragged ensemble) where the fixed-step kernels use 4.
 // PM: per-member mass factors (shape-specialised kernels): compact solve on per-member shared-memory regions.
+#ifndef CRB_RK45_MINBLOCKS
+#define CRB_RK45_MINBLOCKS 1  // resident blocks per SM the register allocation is sized for (1: no cap)
+#endif
 template <int M, unsigned FEAT, int LV, int WPB, bool PM = false>
-__global__ void __launch_bounds__(32 * WPB)
+__global__ void __launch_bounds__(32 * WPB, CRB_RK45_MINBLOCKS)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   constexpr int THREADS = 32 * WPB;
   extern __shared__ __align__(16) double smem[];

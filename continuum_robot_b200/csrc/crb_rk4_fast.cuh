@@ -256,13 +256,133 @@ __device__ __forceinline__ void fast_ctx_impulse(CT& C, const crb_system_t& S, i
   if (rel >= 0 && rel < 3 * M) C.imp_local = rel;
 }
 
+// Recorded frames of the fused integrators of this file (one warp = mpw consecutive members = consecutive rows of Y).
+//   full state   registers -> the warp's staging rows in shared memory -> ONE bulk store (cp.async.bulk shared ->
+//                global) per frame: every byte leaves coalesced and the copy engine, not the LSU pipe the step loop
+//                lives on, moves it (one 8-byte store per lane and entry touched 32 sectors per instruction and ran
+//                the implicit-midpoint kernel at 2.0 TB/s of frames; 128-bit stores through the LSU reach 3.1 TB/s)
+//   lean         (crb_system_t.out_sel_inv) a per-lane bit mask of the own entries that are selected plus their output
+//                columns in a small shared-memory table, both built once per launch: most lanes own no selected entry
+//                and a frame costs them one test; the others store straight from their registers
+// The staging rows double as the column table (a launch records full or lean frames, not both).
+template <int M, bool NC>
+struct FrameWriter {
+  unsigned selmask;
+  double* stage;  // the warp's staging rows [mpw][2n] (16-byte aligned), or NULL: direct stores
+  template <typename RIX>
+  __device__ __forceinline__ void init(const crb_system_t& S, const double* Y, int n, double* stage_rows, RIX rix) {
+    selmask = 0;
+    stage = stage_rows;
+    if (Y && S.out_sel_inv) {
+      int* col = reinterpret_cast<int*>(stage_rows) + (threadIdx.x & 31);  // [entry][lane]
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int r = rix(j, d);
+          if (!NC || r >= 0) {
+            const int cq = S.out_sel_inv[r], cv = S.out_sel_inv[n + r];
+            if (cq >= 0) selmask |= 1u << (3 * j + d);
+            if (cv >= 0) selmask |= 1u << (3 * M + 3 * j + d);
+            if (stage_rows) {
+              col[(3 * j + d) * 32] = cq;
+              col[(3 * M + 3 * j + d) * 32] = cv;
+            }
+          }
+        }
+    }
+  }
+  // m0: first member of the warp, ml: this lane's member within the warp, cnt: members of the warp inside the ensemble
+  template <typename RIX>
+  __device__ __forceinline__ void write(const crb_system_t& S, double* __restrict__ Y, long long frame, int m0, int ml, int cnt,
+                                        int n, const double (&q)[M][3], const double (&v)[M][3], RIX rix) const {
+    const int lane = threadIdx.x & 31;
+    if (S.out_sel_inv) {
+      if (selmask && ml < cnt) {
+        double* ym = Y + (frame * S.n_members + m0 + ml) * S.out_n_sel;
+        const int* col = reinterpret_cast<const int*>(stage) + lane;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            if (selmask & (1u << (3 * j + d))) ym[stage ? col[(3 * j + d) * 32] : S.out_sel_inv[rix(j, d)]] = q[j][d];
+            if (selmask & (1u << (3 * M + 3 * j + d)))
+              ym[stage ? col[(3 * M + 3 * j + d) * 32] : S.out_sel_inv[n + rix(j, d)]] = v[j][d];
+          }
+      }
+      return;
+    }
+    if (!stage) {  // no staging rows (Y rows not 16-byte aligned): direct stores
+      if (ml < cnt) {
+        double* ym = Y + (frame * S.n_members + m0 + ml) * 2 * n;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int r = rix(j, d);
+            if (!NC || r >= 0) {
+              ym[r] = q[j][d];
+              ym[n + r] = v[j][d];
+            }
+          }
+      }
+      return;
+    }
+    put_rows(ml, n, q, v, rix);
+    send(Y + (frame * S.n_members + m0) * 2 * n, cnt, n);
+  }
+  // registers -> staging rows (after the previous bulk store has drained them)
+  template <typename RIX>
+  __device__ __forceinline__ void put_rows(int ml, int n, const double (&q)[M][3], const double (&v)[M][3], RIX rix) const {
+    constexpr bool VEC = !NC && (3 * M) % 2 == 0;
+    if ((threadIdx.x & 31) == 0) crb_bulk_wait_read<0>();
+    __syncwarp();
+    double* xo = stage + ml * 2 * n;
+    if (VEC) {
+      const int r0 = rix(0, 0);
+      double2* q2 = reinterpret_cast<double2*>(xo + r0);
+      double2* v2 = reinterpret_cast<double2*>(xo + n + r0);
+#pragma unroll
+      for (int i = 0; i < (3 * M) / 2; ++i) {
+        q2[i] = make_double2((&q[0][0])[2 * i], (&q[0][0])[2 * i + 1]);
+        v2[i] = make_double2((&v[0][0])[2 * i], (&v[0][0])[2 * i + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int r = rix(j, d);
+          if (!NC || r >= 0) {
+            xo[r] = q[j][d];
+            xo[n + r] = v[j][d];
+          }
+        }
+    }
+  }
+  // staging rows -> cnt rows of 2n doubles at dst, as one bulk store
+  __device__ __forceinline__ void send(double* dst, int cnt, int n) const {
+    crb_fence_proxy_async();  // generic-proxy writes above -> visible to the bulk-copy (async) proxy
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+      crb_bulk_store(dst, crb_smem_u32(stage), (unsigned)cnt * 16u * (unsigned)n);
+      crb_bulk_commit();
+    }
+  }
+  // before the block retires: the last bulk store has read the staging rows
+  __device__ __forceinline__ void drain() const {
+    if (stage && (threadIdx.x & 31) == 0) crb_bulk_wait_read<0>();
+  }
+};
+
 // GRAV: slot-space gravity (config 1 as an ensemble: linear beams under gravity; the force depends on the stage
 // positions only, so the Nystrom form still applies).  NC: see FastCtx.
 template <int M, int LV, bool IMP, bool GRAV = false, bool NC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h,
-                    int nsteps, double* __restrict__ Y, int save_every) {
+                    int nsteps, double* __restrict__ Y, int save_every, int stage_off, int stage_stride) {
   extern __shared__ __align__(16) double smem[];
+  double* const stage_rows = stage_off ? smem + stage_off : nullptr;  // staging rows of recorded frames (FrameWriter)
   typedef FastCtx<M, 0, 0, 0, NC> Ctx;
   Ctx C;
   const int s0 = fast_ctx_init<M, LV, false>(C, P, S, S.mfac, smem);
@@ -273,6 +393,13 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
   // reduced index of own DOF (j, d): consecutive on contiguous plans without phantom slots, else the plan's table
   const int n = C.n;
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter)
+  constexpr int fw_mpw = 32 >> LV;
+  const int fw_ml = (threadIdx.x & 31) >> LV;
+  const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
+  const int fw_cnt = max(0, min(fw_mpw, S.n_members - fw_m0));
+  FrameWriter<M, NC> FW;
+  FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
   double* xm = X + (long long)C.member * 2 * n;
   double Q0[M][3], v[M][3], Sa[M][3], Aa[M][3], w[M][3];
 #pragma unroll
@@ -338,16 +465,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * frame_width(S, n);
-#pragma unroll
-      for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int r = rix(j, d);
-          if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, w[j][d], v[j][d]);
-        }
-    }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) FW.write(S, Y, (k + 1) / save_every - 1, fw_m0, fw_ml, fw_cnt, n, w, v, rix);
   }
   if (C.active) {
 #pragma unroll
@@ -361,6 +479,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
+  FW.drain();
 }
 
 // ==========================================================================================
@@ -434,8 +553,9 @@ __device__ __forceinline__ void fast_apply2(const CT& C, double (&w)[2][M][3]) {
 template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
-                    double* __restrict__ Y, int save_every) {
+                    double* __restrict__ Y, int save_every, int stage_off, int stage_stride) {
   extern __shared__ __align__(16) double smem[];
+  double* const stage_rows = stage_off ? smem + stage_off : nullptr;  // staging rows of recorded frames (FrameWriter)
   typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP || NC) ? 0 : 2), NC> Ctx;  // forcing vectors / index tables need the registers
   Ctx C;
   const int s0 = fast_ctx_init<M, LV, PM>(C, P, S, S.mfac, smem);
@@ -443,6 +563,13 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
   // reduced index of own DOF (j, d): 3 (s0 + j) + d on contiguous plans without phantom slots, else the
   // plan's table (-1: constrained or phantom, held at zero)
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter)
+  constexpr int fw_mpw = 32 >> LV;
+  const int fw_ml = (threadIdx.x & 31) >> LV;
+  const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
+  const int fw_cnt = max(0, min(fw_mpw, S.n_members - fw_m0));
+  FrameWriter<M, NC> FW;
+  FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
   double* xm = X + (long long)C.member * 2 * n;
   double q[M][3], v[M][3], w[2][M][3];
 #pragma unroll
@@ -532,16 +659,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * frame_width(S, n);
-#pragma unroll
-      for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int r = rix(j, d);
-          if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, q[j][d], v[j][d]);
-        }
-    }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) FW.write(S, Y, (k + 1) / save_every - 1, fw_m0, fw_ml, fw_cnt, n, q, v, rix);
   }
   if (C.active) {
 #pragma unroll
@@ -555,6 +673,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
+  FW.drain();
 }
 
 // ==========================================================================================
@@ -576,33 +695,40 @@ struct FastTileGeom {
   static constexpr int ROW_MAX = 2 * 3 * M * G;              // doubles per state row (= 2n on full contiguous plans)
   static constexpr int KC_ROW = 4 * M * G;                   // stiffness coefficients per member
   static constexpr int WARP_DOUBLES = mpw * (2 * ROW_MAX + KC_ROW);  // in: state | in: kcoef | out: state
-  static constexpr size_t smem_bytes(int warps) { return sizeof(double) * ((size_t)FAC_PAD + (size_t)warps * WARP_DOUBLES) + 8 * warps; }
+  static constexpr int SEL_DOUBLES = 3 * M * 32;  // lean recording: output columns [6M entries][32 lanes] as int32
+  static constexpr size_t smem_bytes(int warps) {  // factors | tile buffers | mbarrier (+ pad) | column table
+    return sizeof(double) * ((size_t)FAC_PAD + (size_t)warps * (WARP_DOUBLES + 2 + SEL_DOUBLES));
+  }
 };
 
-template <int M, int LV, bool UC, bool IMP, bool NC = false>
-__global__ void __launch_bounds__(32 * CRB_PERSIST_WARPS, CRB_FAST_MINBLOCKS * CRB_FAST_WARPS / CRB_PERSIST_WARPS)
-crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
-                     double* __restrict__ Y, int save_every, int* __restrict__ tile_counter) {
+// Persistent tile driver shared by the fused integrators of this file.  One warp per block, one tile (mpw
+// consecutive members) at a time:
+//   * the first tile of a block is blockIdx.x, the following ones come from a global ticket counter (tile_counter,
+//     zeroed by the launcher) when the caller provides one: the warp schedulers are not fair (a favoured warp finishes
+//     a static share of the tiles up to 25 % early and leaves its sub-partition with a single warp and no latency
+//     hiding for the rest of the launch -- measured 7.0 instead of 7.9 warps active per SM and 7 % more time per
+//     step); tickets keep every warp busy to the end.  Without a counter the tiles are dealt round-robin;
+//   * the next tile's state rows and stiffness coefficients arrive by bulk copies while the current tile integrates;
+//   * the final state leaves as one bulk store per tile; recorded full-state frames go registers -> shared memory ->
+//     128-bit stores that are contiguous across the warp (generic proxy: no async-proxy fence per frame); lean frames
+//     (crb_system_t.out_sel_inv) are written straight from the registers of the few lanes that own a selected entry.
+// tile_setup(q, v): per-tile preparation (forcing vectors ...); step(k, q, v): one time step in registers.
+template <int M, int LV, bool NC, typename Ctx, typename TileSetup, typename Step>
+__device__ __forceinline__ void fast_persistent_run(const KPlan& P, const crb_system_t& S, const double* __restrict__ fac_set,
+                                                    double* __restrict__ X, int nsteps, double* __restrict__ Y, int save_every,
+                                                    int* __restrict__ tile_counter, double* smem, Ctx& C, TileSetup&& tile_setup,
+                                                    Step&& step) {
   typedef FastTileGeom<M, LV> TG;
   constexpr int G = TG::G, mpw = TG::mpw;
   constexpr bool VEC = !NC && (3 * M) % 2 == 0;  // 128-bit shared-memory accesses of the lane's 3M-double runs
-  extern __shared__ __align__(128) double smem[];
-  typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP || NC) ? 0 : 2), NC> Ctx;
-  Ctx C;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int ml = lane / G;
-  double* const in_x = smem + TG::FAC_PAD + warp * TG::WARP_DOUBLES;
+  double* const in_x = smem + TG::FAC_PAD;
   double* const in_k = in_x + mpw * TG::ROW_MAX;
   double* const out_x = in_k + mpw * TG::KC_ROW;
-  const unsigned bar = crb_smem_u32(smem + TG::FAC_PAD + CRB_PERSIST_WARPS * TG::WARP_DOUBLES);
+  const unsigned bar = crb_smem_u32(smem + TG::FAC_PAD + TG::WARP_DOUBLES);
   const int n = P.n_free;
   const unsigned row_bytes = 16u * (unsigned)n;
-  // One warp per block, one tile (mpw consecutive members) at a time.  The first tile of a block is blockIdx.x; the
-  // following ones come from a global ticket counter (tile_counter, zeroed by the launcher) when the caller provides
-  // one: the warp schedulers are not fair (a warp that is favoured finishes a static share of the tiles up to 25 %
-  // early and leaves its sub-partition with a single warp and no latency hiding for the rest of the launch --
-  // measured 7.0 instead of 7.9 warps active per SM and 7 % more time per step), tickets keep every warp busy to
-  // the end.  Without a counter the tiles are dealt round-robin.
   const int n_tiles = (S.n_members + mpw - 1) / mpw;
 
   auto tile_count = [&](int bt) -> int {  // members of tile bt
@@ -621,10 +747,7 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
     crb_fence_mbar_init();
     if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x);
   }
-  {  // compact copy of the shared factor set (once per block and launch)
-    const double* src = S.mfac + 2 * CRB_SLOT_PAIRS * (M * G) + 2 * CRB_SCAN_PAIRS * TG::LVE * G;
-    for (int k = threadIdx.x; k < TG::FAST_DOUBLES; k += blockDim.x) smem[k] = src[k];
-  }
+  for (int k = threadIdx.x; k < TG::FAST_DOUBLES; k += blockDim.x) smem[k] = fac_set[k];  // compact factor copy, once per launch
   __syncthreads();
   C.g = lane % G;
   C.n = n;
@@ -650,8 +773,11 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
     }
   }
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
-  const double hh = 0.5 * h, h2 = 0.5 * h * h, h3 = h * h * h / 6.0, h4 = h * h * h * h / 24.0;
-  const double h6 = h / 6.0, hx = h * h / 6.0, h12 = h * h * h / 12.0;
+  // recorded frames and the final state leave through the `out` rows (FrameWriter); lean recordings keep their column
+  // table in a region of its own, because the `out` rows are rewritten by every tile's final store
+  FrameWriter<M, NC> FW, FS;
+  FW.init(S, Y, n, (Y && S.out_sel_inv) ? smem + TG::FAC_PAD + TG::WARP_DOUBLES + 2 : out_x, rix);
+  FS.init(S, nullptr, n, out_x, rix);
   unsigned phase = 0;
 
   for (int bt = blockIdx.x; bt < n_tiles;) {
@@ -662,7 +788,7 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
     const unsigned cnt = (unsigned)tile_count(bt);
     crb_mbar_wait(bar, phase);
     phase ^= 1u;
-    double q[M][3], v[M][3], w[2][M][3];
+    double q[M][3], v[M][3];
     {
       const double* xs = in_x + ml * 2 * n;
       if (VEC) {
@@ -709,17 +835,48 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
     // Blocks of several warps would be tied together by it and run their identical instruction streams in lockstep,
     // colliding on the FP64 and shuffle pipes instead of interleaving (measured 8 % slower than free-running warps).
     __syncthreads();
+    tile_setup(q, v);
 
-    // forcing in acceleration space: cu = M^-1 (u_const + f_ext), ci = amp * M^-1 e_k
-    double cu[UC ? M : 1][3], ci[IMP ? M : 1][3];
+    for (int k = 0; k < nsteps; ++k) {
+      step(k, q, v);
+      if (Y && save_every > 0 && (k + 1) % save_every == 0) {
+        FW.write(S, Y, (k + 1) / save_every - 1, m0, ml, (int)cnt, n, q, v, rix);
+        __syncthreads();  // convergence point for the compiler (see above)
+      }
+    }
+    // final state of the tile: one bulk store
+    FS.put_rows(ml, n, q, v, rix);
+    FS.send(X + (long long)m0 * 2 * n, (int)cnt, n);
+    __syncthreads();
+    bt = nxt;
+  }
+  if (lane == 0) crb_bulk_wait<0>();  // the last store has left shared memory before the block retires
+}
+
+template <int M, int LV, bool UC, bool IMP, bool NC = false>
+__global__ void __launch_bounds__(32 * CRB_PERSIST_WARPS, CRB_FAST_MINBLOCKS * CRB_FAST_WARPS / CRB_PERSIST_WARPS)
+crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
+                     double* __restrict__ Y, int save_every, int* __restrict__ tile_counter) {
+  typedef FastTileGeom<M, LV> TG;
+  extern __shared__ __align__(128) double smem[];
+  typedef FastCtx<M, ((UC || IMP) ? 0 : 4), ((UC || IMP) ? 0 : 1), ((UC || IMP || NC) ? 0 : 2), NC> Ctx;
+  Ctx C;
+  const int n = P.n_free;
+  const double hh = 0.5 * h, h2 = 0.5 * h * h, h3 = h * h * h / 6.0, h4 = h * h * h * h / 24.0;
+  const double h6 = h / 6.0, hx = h * h / 6.0, h12 = h * h * h / 12.0;
+  // forcing in acceleration space: cu = M^-1 (u_const + f_ext), ci = amp * M^-1 e_k (per tile)
+  double cu[UC ? M : 1][3], ci[IMP ? M : 1][3];
+  auto tile_setup = [&](double (&q)[M][3], double (&v)[M][3]) {
     if (UC || IMP) {
+      double w[2][M][3];
+      const int s0 = C.g * M;
       const long long mo = (long long)C.member * n;
       const double amp = IMP ? S.imp_amp[C.member] : 0.0;
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const int r = rix(j, d);
+          const int r = NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d;
           double u = 0.0;
           if (!NC || r >= 0) {
             if (UC && S.u_const) u += S.u_const[mo + r];
@@ -737,113 +894,61 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
           if (IMP) ci[j][d] = w[1][j][d];
         }
     }
-    // registers -> `out` buffer -> one bulk store of the tile's rows to dst (row-major like X)
-    auto store_tile = [&](double* dst) {
-      if (lane == 0) crb_bulk_wait_read<0>();  // the previous store has drained the buffer
-      __syncwarp();
-      double* xo = out_x + ml * 2 * n;
-      if (VEC) {
-        double2* q2 = reinterpret_cast<double2*>(xo + 3 * s0);
-        double2* v2 = reinterpret_cast<double2*>(xo + n + 3 * s0);
+  };
+  auto step = [&](int k, double (&q)[M][3], double (&v)[M][3]) {
+    const double t = t0 + k * h;
+    const double g1 = (IMP && t < S.imp_duration) ? 1.0 : 0.0;
+    const double g2 = (IMP && t + hh < S.imp_duration) ? 1.0 : 0.0;
+    const double g4 = (IMP && t + h < S.imp_duration) ? 1.0 : 0.0;
+    double w[2][M][3];
 #pragma unroll
-        for (int i = 0; i < (3 * M) / 2; ++i) {
-          q2[i] = make_double2((&q[0][0])[2 * i], (&q[0][0])[2 * i + 1]);
-          v2[i] = make_double2((&v[0][0])[2 * i], (&v[0][0])[2 * i + 1]);
-        }
-      } else {
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        w[0][j][d] = q[j][d];
+        w[1][j][d] = v[j][d];
+      }
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+      fast_apply2<M, LV>(C, w);
+      if (round == 0) {  // w = (L, p)
 #pragma unroll
         for (int j = 0; j < M; ++j)
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            const int r = rix(j, d);
-            if (!NC || r >= 0) {
-              xo[r] = q[j][d];
-              xo[n + r] = v[j][d];
+            const double Lq = w[0][j][d], p = w[1][j][d];
+            if (!UC && !IMP) {
+              q[j][d] = fma(h3, p, fma(h2, Lq, fma(h, v[j][d], q[j][d])));
+              v[j][d] = fma(h2, p, fma(h, Lq, v[j][d]));
+            } else {
+              const double cuv = UC ? cu[j][d] : 0.0, civ = IMP ? ci[j][d] : 0.0;
+              const double a1 = Lq + fma(g1, civ, cuv);
+              const double a2 = fma(hh, p, Lq) + fma(g2, civ, cuv);
+              q[j][d] = fma(hx, fma(2.0, a2, a1), fma(h, v[j][d], q[j][d]));
+              v[j][d] = fma(h6, fma(5.0, a2, a1) + fma(hh, p, (g4 - g2) * civ), v[j][d]);
+              w[0][j][d] = a1;
+              w[1][j][d] = a2;
             }
           }
-      }
-      crb_fence_proxy_async();  // generic-proxy writes above -> visible to the bulk-copy (async) proxy
-      __syncwarp();
-      if (lane == 0) {
-        crb_bulk_store(dst, crb_smem_u32(out_x), cnt * row_bytes);
-        crb_bulk_commit();
-      }
-      __syncthreads();
-    };
-
-    for (int k = 0; k < nsteps; ++k) {
-      const double t = t0 + k * h;
-      const double g1 = (IMP && t < S.imp_duration) ? 1.0 : 0.0;
-      const double g2 = (IMP && t + hh < S.imp_duration) ? 1.0 : 0.0;
-      const double g4 = (IMP && t + h < S.imp_duration) ? 1.0 : 0.0;
+      } else {  // w = (r, s) or (r1, r2)
 #pragma unroll
-      for (int j = 0; j < M; ++j)
+        for (int j = 0; j < M; ++j)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          w[0][j][d] = q[j][d];
-          w[1][j][d] = v[j][d];
-        }
-#pragma unroll 1
-      for (int round = 0; round < 2; ++round) {
-        fast_apply2<M, LV>(C, w);
-        if (round == 0) {  // w = (L, p)
-#pragma unroll
-          for (int j = 0; j < M; ++j)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const double Lq = w[0][j][d], p = w[1][j][d];
-              if (!UC && !IMP) {
-                q[j][d] = fma(h3, p, fma(h2, Lq, fma(h, v[j][d], q[j][d])));
-                v[j][d] = fma(h2, p, fma(h, Lq, v[j][d]));
-              } else {
-                const double cuv = UC ? cu[j][d] : 0.0, civ = IMP ? ci[j][d] : 0.0;
-                const double a1 = Lq + fma(g1, civ, cuv);
-                const double a2 = fma(hh, p, Lq) + fma(g2, civ, cuv);
-                q[j][d] = fma(hx, fma(2.0, a2, a1), fma(h, v[j][d], q[j][d]));
-                v[j][d] = fma(h6, fma(5.0, a2, a1) + fma(hh, p, (g4 - g2) * civ), v[j][d]);
-                w[0][j][d] = a1;
-                w[1][j][d] = a2;
-              }
+          for (int d = 0; d < 3; ++d) {
+            const double r = w[0][j][d], s = w[1][j][d];
+            if (!UC && !IMP) {
+              q[j][d] = fma(h4, r, q[j][d]);
+              v[j][d] = fma(h4, s, fma(h3, r, v[j][d]));
+            } else {
+              q[j][d] = fma(h4, r, q[j][d]);
+              v[j][d] = fma(h12, r + s, v[j][d]);
             }
-        } else {  // w = (r, s) or (r1, r2)
-#pragma unroll
-          for (int j = 0; j < M; ++j)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const double r = w[0][j][d], s = w[1][j][d];
-              if (!UC && !IMP) {
-                q[j][d] = fma(h4, r, q[j][d]);
-                v[j][d] = fma(h4, s, fma(h3, r, v[j][d]));
-              } else {
-                q[j][d] = fma(h4, r, q[j][d]);
-                v[j][d] = fma(h12, r + s, v[j][d]);
-              }
-            }
-        }
-      }
-      if (Y && save_every > 0 && (k + 1) % save_every == 0) {
-        const long long frame = (k + 1) / save_every - 1;
-        if (S.out_sel_inv) {  // lean frame: only the selected state entries
-          if (C.active) {
-            double* ym = Y + (frame * S.n_members + C.member) * S.out_n_sel;
-#pragma unroll
-            for (int j = 0; j < M; ++j)
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                const int r = rix(j, d);
-                if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, q[j][d], v[j][d]);
-              }
           }
-          __syncthreads();
-        } else {
-          store_tile(Y + (frame * S.n_members + m0) * 2 * n);
-        }
       }
     }
-    store_tile(X + (long long)m0 * 2 * n);
-    bt = nxt;
-  }
-  if (lane == 0) crb_bulk_wait<0>();  // the last stores have left shared memory before the block retires
+  };
+  const double* fac_set = S.mfac + 2 * CRB_SLOT_PAIRS * (M * TG::G) + 2 * CRB_SCAN_PAIRS * TG::LVE * TG::G;
+  fast_persistent_run<M, LV, NC>(P, S, fac_set, X, nsteps, Y, save_every, tile_counter, smem, C, tile_setup, step);
 }
 
 // ==========================================================================================
@@ -864,8 +969,9 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
 template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_MID_MINBLOCKS)
 crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, double* __restrict__ X, double t0,
-                    double h, int nsteps, double* __restrict__ Y, int save_every) {
+                    double h, int nsteps, double* __restrict__ Y, int save_every, int stage_off, int stage_stride) {
   extern __shared__ __align__(16) double smem[];
+  double* const stage_rows = stage_off ? smem + stage_off : nullptr;  // staging rows of recorded frames (FrameWriter)
   typedef FastCtx<M, CRB_MID_PINS, (CRB_MID_PINS > 0 ? 1 : 0), (NC ? 0 : CRB_MID_PINS), NC> Ctx;  // one solve per step: the constants of the solve stay in registers
   Ctx C;
   const int s0 = fast_ctx_init<M, LV, PM>(C, P, S, afac, smem);
@@ -873,6 +979,13 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
   const int n = C.n;
   // reduced index of own DOF (j, d); NC: the plan's table (-1: constrained or phantom, held at zero)
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
+  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter)
+  constexpr int fw_mpw = 32 >> LV;
+  const int fw_ml = (threadIdx.x & 31) >> LV;
+  const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
+  const int fw_cnt = max(0, min(fw_mpw, S.n_members - fw_m0));
+  FrameWriter<M, NC> FW;
+  FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
   double* xm = X + (long long)C.member * 2 * n;
   double q[M][3], v[M][3], w[M][3], uc[UC ? M : 1][3];
 #pragma unroll
@@ -904,16 +1017,7 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         q[j][d] = fma(hh, dv, fma(h, v[j][d], q[j][d]));
         v[j][d] += dv;
       }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0 && C.active) {
-      double* ym = Y + ((long long)((k + 1) / save_every - 1) * S.n_members + C.member) * frame_width(S, n);
-#pragma unroll
-      for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int r = rix(j, d);
-          if (!NC || r >= 0) frame_put(S.out_sel_inv, ym, n, r, q[j][d], v[j][d]);
-        }
-    }
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) FW.write(S, Y, (k + 1) / save_every - 1, fw_m0, fw_ml, fw_cnt, n, q, v, rix);
   }
   if (C.active) {
 #pragma unroll
@@ -927,4 +1031,5 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         }
       }
   }
+  FW.drain();
 }

@@ -11,8 +11,14 @@ template <int M, int LV, bool PM>
 static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, double t0, double h, int nsteps,
                   double* Y_out, int save_every, cudaStream_t stream) {
   const int mpb = CRB_FAST_WARPS * (32 >> LV);
-  // compact factor copy: ONE shared set, or (PM) one region per member of the block
-  const size_t bytes = sizeof(double) * (size_t)crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1);
+  // compact factor copy: ONE shared set, or (PM) one region per member of the block; behind it the staging rows of
+  // recorded full-state frames (FrameWriter), when Y_out rows are 16-byte aligned
+  const int fac_doubles = ((crb_compact_doubles(plan->m, plan->g, plan->levels) * (PM ? mpb : 1)) + 1) & ~1;
+  // per warp: staging rows of full frames [mpw][2n], or the column table of a lean recording [6M][32] int32
+  const bool stage = Y_out && (sys->out_sel_inv || ((uintptr_t)Y_out & 15) == 0);
+  const int stage_off = stage ? fac_doubles : 0;
+  const int stage_stride = (std::max((32 >> LV) * 2 * plan->n_free, 96 * M) + 1) & ~1;
+  const size_t bytes = sizeof(double) * ((size_t)fac_doubles + (stage ? (size_t)CRB_FAST_WARPS * stage_stride : 0));
   const int grid = (sys->n_members + mpb - 1) / mpb;
   KPlan P = kplan_of(plan);
   P.n_sm = crb_sm_count();
@@ -41,7 +47,7 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
     if constexpr (PM) {                                                                                        \
       if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_rk4")) return rc;      \
       crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
-                                                                                               Y_out, save_every); \
+                                                                                               Y_out, save_every, stage_off, stage_stride); \
     } else {                                                                                                   \
       return 1; /* rows not 16-byte aligned: general kernel */                                                 \
     }                                                                                                          \
@@ -55,7 +61,7 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   {                                                                                                           \
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, IMPV, true, NCV>, bytes, "crb_rk4")) return rc;          \
     crb_rk4_fast_kernel<M, LV, IMPV, true, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
-                                                                                          Y_out, save_every); \
+                                                                                          Y_out, save_every, stage_off, stage_stride); \
   }
       if (imp && nc) CRB_FASTG(true, true)
       else if (imp) CRB_FASTG(true, false)
@@ -86,10 +92,10 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
     return 1;  // the stage-by-stage fast kernel has no constant-force path: use the general kernel
   } else if (imp) {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
+    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);
   } else {
     if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every);
+    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);
   }
 #undef CRB_LIN2
 #undef CRB_LIN2N

@@ -47,6 +47,13 @@ class EnsembleResult:
     x_final: "object" = None  # torch [B, 2n] full state at the end of the interval
 
 
+def with_selection(beam, system, out_sel):
+    """``(crb_system_t, keepalive)`` of ``beam.make_system`` with the lean-recording table of ``out_sel`` attached: for
+    callers that step repeatedly with ``rk4_steps(..., system=...)`` and want the table uploaded once."""
+    s2, keep, _ = _with_selection(beam, system[0], system[1], out_sel)
+    return s2, keep
+
+
 def _with_selection(beam, sysm, keep, out_sel):
     """Copy of the crb_system_t with the lean-recording table of ``out_sel`` (state indices) attached."""
     import torch
@@ -123,21 +130,28 @@ def rk4_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, ns
 
 
 def midpoint_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, nsteps: int, *, u=None,
-                   Y_out=None, save_every: int = 0, out_sel=None):
+                   Y_out=None, save_every: int = 0, out_sel=None, system=None):
     """Advance X[B,2n] in place by ``nsteps`` implicit-midpoint steps (Newmark average acceleration) in ONE
     kernel launch (crb_midpoint).  All-linear beams without drag / gravity / feedback; ``u``: constant
     tensor [B,n] or TipImpulse, evaluated at the step midpoints.  Unconditionally stable: ``h`` is chosen
     for accuracy (the rule is second order), not for the highest element frequency as with RK4 -- the
-    reason the reference's examples integrate with LSODA (examples/example_utilities.py:153-159)."""
+    reason the reference's examples integrate with LSODA (examples/example_utilities.py:153-159).
+    ``system``: a prebuilt ``(crb_system_t, keepalive)`` (``beam.make_system``, optionally with a lean-recording table
+    from ``with_selection``) to skip the per-call struct fill."""
     import torch
 
-    drag, grav, user = beam._active_forces()
-    if user or beam._forces_func is not None or drag is not None or grav is not None:
-        raise TypeError("the implicit midpoint rule supports force-free all-linear beams (inputs: tensor or TipImpulse)")
-    uc, impulse, tv, other = split_input(u)
-    if tv or other is not None:
-        raise TypeError("implicit midpoint needs a constant tensor or TipImpulse input")
-    sysm, _keep = beam.make_system(X.shape[0], u_const=uc, impulse=impulse)
+    if system is None:
+        drag, grav, user = beam._active_forces()
+        if user or beam._forces_func is not None or drag is not None or grav is not None:
+            raise TypeError("the implicit midpoint rule supports force-free all-linear beams (inputs: tensor or TipImpulse)")
+        uc, impulse, tv, other = split_input(u)
+        if tv or other is not None:
+            raise TypeError("implicit midpoint needs a constant tensor or TipImpulse input")
+        sysm, _keep = beam.make_system(X.shape[0], u_const=uc, impulse=impulse)
+    else:
+        if u is not None:
+            raise ValueError("midpoint_steps: `u` is part of a prebuilt `system`; pass one or the other")
+        sysm, _keep = system
     if out_sel is not None:
         sysm, _keep, width = _with_selection(beam, sysm, _keep, out_sel)
         if Y_out is not None and (Y_out.shape[-1] != width or not Y_out.is_contiguous()):

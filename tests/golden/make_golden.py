@@ -273,6 +273,34 @@ def gen_cfg4():
     print("cfg4 done", d["y"].shape, d["nfev"])
 
 
+def gen_cfg4_5ms():
+    """Config 4 pinned also at 5 ms, where the reference is still finite but already growing fast (max |v| ~ 1e2):
+    a controller mismatch would show here first.  4 sampled members, 6 outputs."""
+    e = ens.config4()
+    idx = ens.sample_members(e.n_members, 16, 99)[:4]
+    rk45 = {"t_span": (0.0, 0.005), "t_eval": np.linspace(0, 0.005, 6), "rtol": 1e-6, "atol": 1e-9}
+    tasks = [
+        (int(i), e.n_elements, e.E[i], "nonlinear", 1000.0, True, float(e.impulse_amp[i]), 0.01, 0.0, 0, 0,
+         np.zeros(2 * e.n_free), rk45)
+        for i in idx
+    ]
+    with Pool(min(4, os.cpu_count())) as p:
+        res = dict(p.map(_run_single, tasks))
+    d = {
+        "idx": idx, "amp": e.impulse_amp[idx], "E": e.E[idx],
+        "E_parsed": np.array([res[int(i)]["params"]["elastic_modulus"] for i in idx]),
+        "y": np.array([res[int(i)]["rk45_y"] for i in idx]),
+        "t_eval": rk45["t_eval"],
+        "nfev": np.array([res[int(i)]["rk45_nfev"] for i in idx]),
+        "rtol": np.array(1e-6), "atol": np.array(1e-9),
+    }
+    p0 = res[int(idx[0])]["params"]
+    for k in ("length", "moment_inertia", "density", "cross_area", "wetted_area", "drag_coef"):
+        d[k] = p0[k]
+    np.savez_compressed(os.path.join(HERE, "cfg4_5ms.npz"), **d)
+    print("cfg4 5 ms done", d["y"].shape, d["nfev"], "max |y|", np.abs(d["y"]).max())
+
+
 def _run_lqr(args):
     i, amp, gain, nsteps, h, save_every = args
     spec = importlib.util.spec_from_file_location(
@@ -433,4 +461,4 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     for name in a.only.split(","):
-        {"rhs": gen_rhs, "cfg12": gen_cfg12, "cfg3": gen_cfg3, "cfg4": gen_cfg4, "cfg5": gen_cfg5, "inputs": gen_inputs}[name]()
+        {"rhs": gen_rhs, "cfg12": gen_cfg12, "cfg3": gen_cfg3, "cfg4": gen_cfg4, "cfg5": gen_cfg5, "inputs": gen_inputs, "cfg4_5ms": gen_cfg4_5ms}[name]()

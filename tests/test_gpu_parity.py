@@ -172,6 +172,30 @@ def test_rk45_config4_samples():
     assert len(set(nfev.tolist())) > 4
 
 
+def test_rk45_config4_at_5ms():
+    """Config 4 also pinned at 5 ms (tests/golden/cfg4_5ms.npz, 4 members): the reference is still finite there but
+    already growing fast (max |y| ~ 2.5e2), which is where a controller mismatch would show first."""
+    from continuum_robot_b200 import TipImpulse, solve_ensemble
+
+    g = load("cfg4_5ms.npz")
+    B, N = g["E_parsed"].shape
+    par = np.zeros((B, N, 7))
+    for col, key in ((0, "length"), (2, "moment_inertia"), (3, "density"), (4, "cross_area"), (5, "wetted_area"), (6, "drag_coef")):
+        par[:, :, col] = g[key][None, :]
+    par[:, :, 1] = g["E_parsed"]
+    beam = make_gpu_beam(par, np.ones(N, dtype=int), np.array([1] + [0] * N), 1000.0, True)
+    n = beam.n_free
+    rtol, atol = float(g["rtol"]), float(g["atol"])
+    res = solve_ensemble(beam, (0.0, 0.005), torch.zeros(B, 2 * n, dtype=torch.float64, device="cuda"), method="RK45",
+                         t_eval=g["t_eval"], rtol=rtol, atol=atol, u=TipImpulse(torch.from_numpy(g["amp"]).cuda()))
+    assert res.success
+    got, ref = res.y.cpu().numpy(), g["y"]
+    assert got.shape == ref.shape and np.abs(ref).max() > 50.0
+    assert np.all(np.abs(got - ref) <= 10 * (atol + rtol * np.abs(ref))), (np.abs(got - ref) / (atol + rtol * np.abs(ref))).max()
+    nfev = res.nfev.cpu().numpy()
+    assert np.all(np.abs(nfev - g["nfev"]) <= np.maximum(12, 0.02 * g["nfev"])), (nfev, g["nfev"])
+
+
 def test_lqr_rollout_config5_samples():
     """BASELINE config 5: closed-loop LQR rollout (shared gain from the golden file, u = K(0 - x)
     plus a per-member tip disturbance, gravity on), 2000 RK4 steps, <= 1e-9 at 4 checkpoints."""
