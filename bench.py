@@ -453,6 +453,14 @@ def run_gpu(args):
             except Exception:
                 traffic, fp64, dram = None, None, None
         state_bytes = X.numel() * 8
+        # plain-copy ceiling of the box for this many GPUs (benchmarks/host_ceiling.py, profiles/r2_host_ceiling_8gpu.json)
+        ceiling = None
+        try:
+            hc = json.load(open(os.path.join(ROOT, "profiles", "r2_host_ceiling_8gpu.json")))
+            ceiling = hc["duplex_aggregate_gbs_by_gpus"].get(str(world))
+        except Exception:
+            pass
+        host_gbs = 2.0 * state_bytes * e2e_calls * world / (e2e_ms * 1e-3) / 1e9
         line = {
             "metric": "beam-element RK4 steps/sec", "value": value, "unit": "element-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -477,6 +485,9 @@ def run_gpu(args):
                     "call": f"HostPipeline.run x {e2e_calls} ({timed_chunks} fused RK4 steps per call): each call H2D state "
                             f"{state_bytes} B (pinned) + kernels + D2H state, chunks of {pipe.chunk_members} members on 3 "
                             f"streams, native pipeline crb_rk4_host",
+                    "host_traffic_gbs": host_gbs, "ceiling_gbs": ceiling,
+                    "ceiling_note": "aggregate H2D + D2H bytes per second of this leg vs the plain-copy duplex ceiling measured on "
+                                    "an 8 x B200 box of this pool with the same number of GPUs copying at once (no kernels)",
                     "finite": e2e_ok},
             "gpu_launches": len(timed_chunks),
             "numa_bound": numa_bound,
