@@ -289,9 +289,289 @@ __device__ double gj_inverse_reg(double* a, int m, double* colb, double* prowb, 
   return logdet;
 }
 
-// Inverse of a (m x m, shared memory) in place: register-resident elimination up to m = 80, shared-memory one beyond.
+// ------------------------------------------------------------------------------------------
+// Blocked Gauss-Jordan inverse for matrices that do not fit shared memory (long beams: the 4n x 4n Hamiltonian of a
+// 32-element cantilever is 384 x 384 = 1.2 MB).  The unblocked elimination streams the whole matrix once per pivot
+// (384 passes: HBM / L2 bound, 122 designs/s at 32 elements); here the matrix is eliminated in panels of NB columns:
+//   1. the panel (all m rows x NB columns) is copied to shared memory (transposed: Wt[c][i]) and eliminated there with
+//      implicit row pivoting over the rows not used yet -- afterwards it holds the NB special columns W of the
+//      accumulated transformation T = I + (W - E_R) E_R^T (E_R selects the panel's pivot rows R);
+//   2. the OLD pivot rows A[R, :] are saved in shared memory (Rr[c][j]);
+//   3. every other column is updated with ONE pass over the matrix, a rank-NB product from shared memory:
+//      A[i, j] <- (i in R ? 0 : A[i, j]) + sum_c W[i, c] A[r_c, j]        (register tile 4 x 4 per thread);
+//   4. the panel is written back.
+// m / NB passes over the matrix instead of m, 2 m^3 flops as before.  Implicit pivoting leaves
+// inverse(p, piv[c]) = storage(piv[p], c), undone while the result is written to the scratch matrix `tmp`.
+// ------------------------------------------------------------------------------------------
+#define CRB_LQR_NB 32
+__host__ __device__ inline size_t lqr_blk_doubles(int m) {  // Wt | Rr | prow | flag (int) of gj_inverse_blocked
+  const size_t mp = ((size_t)m + 7) & ~(size_t)7, mr = ((size_t)m + 127) & ~(size_t)127;
+  return CRB_LQR_NB * (mp + mr) + CRB_LQR_NB + (mp + 1) / 2 + 2;
+}
+
+// Streaming helpers for the long-beam path: with one block of 256 threads per SM a plain `dst[k] = src[k]` loop keeps
+// too few bytes in flight (measured 5 GB/s per SM); 128-bit accesses, eight per thread and trip.
+__device__ __forceinline__ void big_copy(double* __restrict__ dst, const double* __restrict__ src, int count) {
+  const int tid = threadIdx.x, n2 = count >> 1;
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  for (int k0 = 0; k0 < n2; k0 += 8 * CRB_LQR_THREADS) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * CRB_LQR_THREADS + tid;
+      if (k < n2) v[u] = s2[k];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * CRB_LQR_THREADS + tid;
+      if (k < n2) d2[k] = v[u];
+    }
+  }
+  if ((count & 1) && tid == 0) dst[count - 1] = src[count - 1];
+}
+
+// Returns log|det a|; the INVERSE IS LEFT IN `tmp` (one pass less than copying it back), `a` is destroyed.
+__device__ __noinline__ double gj_inverse_blocked(double* a, double* tmp, int m, double* blk, int* piv, int* pinfo, double* red,
+                                                  bool* singular) {
+  constexpr int NB = CRB_LQR_NB, T = CRB_LQR_THREADS;
+  constexpr int RPT = (4 * CRB_LQR_MAX_N + T - 1) / T;  // rows a thread owns during the panel elimination (i = tid + T k)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mp = (m + 7) & ~7;      // row stride of Wt: whole 8-row tiles of the update
+  const int mr = (m + 127) & ~127;  // row stride of Rr: whole 128-column sweeps of the update, no index clamps
+  double* Wt = blk;               // [NB][mp]
+  double* Rr = Wt + NB * mp;      // [NB][mr]
+  double* prs = Rr + NB * mr;     // [NB] panel part of the pivot row
+  int* flag = reinterpret_cast<int*>(prs + NB);  // [mp]: 0 = row not used yet, else 1 + the column it is the pivot row of
+  double det_m = 1.0;  // |det| = det_m * 2^det_e (one log at the end instead of one per pivot and thread)
+  int det_e = 0;
+  *singular = false;
+  for (int i = tid; i < mp; i += T) flag[i] = 0;
+  for (int i = tid; i < NB * mr; i += T) Rr[i] = 0.0;
+  __syncthreads();
+  for (int k0 = 0; k0 < m; k0 += NB) {
+    const int nb = min(NB, m - k0);
+    // ---- 1. panel elimination.  Thread t owns rows t, t + T, ... and keeps its NB panel entries of each IN REGISTERS
+    // for the whole panel: a pivot is 2 block barriers, one broadcast row in shared memory and NB register FMAs per
+    // owned row (the shared-memory form spent 30 % of the kernel here) ----
+    double W[RPT][NB];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {  // the thread's own rows: 256 contiguous bytes each, straight into registers
+      const int i = tid + T * k;
+      const double* prow_g = a + (long long)i * m + k0;
+      if (i < m && nb == NB && (m & 1) == 0) {  // 16-byte aligned (m even, k0 a multiple of NB)
+#pragma unroll
+        for (int c2 = 0; c2 < NB; c2 += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(prow_g + c2);
+          W[k][c2] = v.x;
+          W[k][c2 + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int c2 = 0; c2 < NB; ++c2) W[k][c2] = (i < m && c2 < nb) ? prow_g[c2] : 0.0;
+      }
+    }
+    bool mine_used[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) mine_used[k] = (tid + T * k < m) ? flag[tid + T * k] != 0 : true;
+    // The pivot loop runs 4 pivots per trip on the FIRST four register columns and then rotates the register panel by
+    // four columns (static register indices without unrolling 32 pivot bodies: that much code thrashed the
+    // instruction cache); after the 8 trips the columns are back in place.
+#pragma unroll 1
+    for (int o = 0; o < NB / 4; ++o) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = 4 * o + cc;
+        if (c < nb) {  // block-uniform
+          double best = -1.0;
+          int bi = m;
+#pragma unroll
+          for (int k = 0; k < RPT; ++k)
+            if (!mine_used[k]) {
+              const double v = fabs(W[k][cc]);
+              if (v > best) { best = v; bi = tid + T * k; }
+            }
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) {
+            const double ob = __shfl_down_sync(0xffffffffu, best, sh);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, sh);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+          }
+          if (lane == 0) {
+            red[warp] = best;
+            reinterpret_cast<int*>(red + 8)[warp] = bi;
+          }
+          __syncthreads();  // (1) warp maxima visible
+          best = red[0];
+          int r = reinterpret_cast<int*>(red + 8)[0];
+#pragma unroll
+          for (int w = 1; w < T / 32; ++w) {
+            const double ob = red[w];
+            const int oi = reinterpret_cast<int*>(red + 8)[w];
+            if (ob > best || (ob == best && oi < r)) { best = ob; r = oi; }
+          }
+          if (!(best > 0.0) || !isfinite(best) || r >= m) { *singular = true; return 0.0; }  // block-uniform
+#pragma unroll
+          for (int k = 0; k < RPT; ++k)
+            if (tid + T * k == r) {  // the owner publishes the pivot row (panel part, rotated frame) and retires the row
+#pragma unroll
+              for (int c2 = 0; c2 < NB; ++c2) prs[c2] = W[k][c2];
+              mine_used[k] = true;
+              flag[r] = k0 + c + 1;
+              piv[k0 + c] = r;
+            }
+          __syncthreads();  // (2) pivot row visible (red may be rewritten after this point)
+          const double pv = prs[cc], ipv = 1.0 / pv;
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) {
+            const bool isr = (tid + T * k == r);
+            const double fi = isr ? 0.0 : -W[k][cc] * ipv;
+#pragma unroll
+            for (int c2 = 0; c2 < NB; ++c2) {
+              const double pr = prs[c2];
+              if (c2 == cc) W[k][c2] = isr ? ipv : fi;
+              else W[k][c2] = isr ? pr * ipv : fma(fi, pr, W[k][c2]);
+            }
+          }
+          {
+            int e;
+            det_m = frexp(det_m * fabs(pv), &e);
+            det_e += e;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {  // rotate the register panel left by four columns
+        const double t0 = W[k][0], t1 = W[k][1], t2 = W[k][2], t3 = W[k][3];
+#pragma unroll
+        for (int c2 = 0; c2 < NB - 4; ++c2) W[k][c2] = W[k][c2 + 4];
+        W[k][NB - 4] = t0;
+        W[k][NB - 3] = t1;
+        W[k][NB - 2] = t2;
+        W[k][NB - 1] = t3;
+      }
+    }
+    // the eliminated panel, transposed, for the update (Wt[c][i])
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int i = tid + T * k;
+      if (i < m) {
+#pragma unroll
+        for (int c2 = 0; c2 < NB; ++c2) Wt[c2 * mp + i] = W[k][c2];
+      }
+    }
+    __syncthreads();
+    // ---- 2. the panel's pivot rows as they are BEFORE this block step ----
+    for (int c = warp; c < nb; c += T / 32) {
+      const double* srow = a + (long long)piv[k0 + c] * m;
+      if ((m & 1) == 0) {  // rows are 16-byte aligned
+        const double2* src = reinterpret_cast<const double2*>(srow);
+        double2* dst = reinterpret_cast<double2*>(Rr + c * mr);
+        for (int j = lane; j < (m >> 1); j += 32) dst[j] = src[j];
+      } else {
+        for (int j = lane; j < m; j += 32) Rr[c * mr + j] = srow[j];
+      }
+    }
+    __syncthreads();
+    // ---- 3. rank-nb update of every column outside the panel: warp = 8 rows, lane = 4 columns (stride 32); the
+    // next tile's matrix entries are loaded while the current tile is being multiplied ----
+    {
+      constexpr int TR = 8;
+      const int n_jb = mr / 128, rows_per_sweep = TR * (T / 32);
+      const int n_ib = (m + rows_per_sweep - 1) / rows_per_sweep, n_tiles = n_ib * n_jb;
+      double nxt[TR][4];
+      auto load_tile = [&](int tile, double (&dst)[TR][4]) {
+        const int i0 = (tile / n_jb) * rows_per_sweep + TR * warp, jb = (tile % n_jb) * 128;
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii) {
+          const int i = i0 + ii;
+          const int fl = (i < m) ? flag[i] : 0;
+          const bool isp = fl > k0 && fl <= k0 + nb;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = jb + lane + 32 * jj;
+            dst[ii][jj] = (i < m && j < m && !isp) ? a[(long long)i * m + j] : 0.0;
+          }
+        }
+      };
+      load_tile(0, nxt);
+      for (int tile = 0; tile < n_tiles; ++tile) {
+        const int i0 = (tile / n_jb) * rows_per_sweep + TR * warp, jb = (tile % n_jb) * 128;
+        double acc[TR][4];
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = nxt[ii][jj];
+        if (tile + 1 < n_tiles) load_tile(tile + 1, nxt);
+        if (i0 < m) {
+          const double* wp = Wt + i0;  // (i0 is a multiple of 8 <= mp - 8; rows past m hold garbage that is never stored)
+          const double* rp = Rr + jb + lane;
+#pragma unroll 4
+          for (int c = 0; c < nb; ++c) {
+            const double4 w0 = *reinterpret_cast<const double4*>(wp + c * mp);      // broadcast loads
+            const double4 w1 = *reinterpret_cast<const double4*>(wp + c * mp + 4);
+            double rv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) rv[jj] = rp[c * mr + 32 * jj];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              acc[0][jj] = fma(w0.x, rv[jj], acc[0][jj]);
+              acc[1][jj] = fma(w0.y, rv[jj], acc[1][jj]);
+              acc[2][jj] = fma(w0.z, rv[jj], acc[2][jj]);
+              acc[3][jj] = fma(w0.w, rv[jj], acc[3][jj]);
+              acc[4][jj] = fma(w1.x, rv[jj], acc[4][jj]);
+              acc[5][jj] = fma(w1.y, rv[jj], acc[5][jj]);
+              acc[6][jj] = fma(w1.z, rv[jj], acc[6][jj]);
+              acc[7][jj] = fma(w1.w, rv[jj], acc[7][jj]);
+            }
+          }
+#pragma unroll
+          for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int i = i0 + ii, j = jb + lane + 32 * jj;
+              if (i < m && j < m && (j < k0 || j >= k0 + nb)) a[(long long)i * m + j] = acc[ii][jj];
+            }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 4. panel back ----
+    for (int idx = tid; idx < nb * m; idx += T) {
+      const int i = idx / nb, c = idx - i * nb;
+      a[(long long)i * m + k0 + c] = Wt[c * mp + i];
+    }
+    __syncthreads();
+  }
+  // implicit pivoting: inverse(p, piv[c]) = storage(piv[p], c); one row per warp, coalesced reads
+  for (int p = warp; p < m; p += T / 32) {
+    const double* src = a + (long long)piv[p] * m;
+    double* dst = tmp + (long long)p * m;
+    for (int c0 = 0; c0 < m; c0 += 128) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < m) v[u] = src[c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < m) dst[piv[c]] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  return log(det_m) + det_e * 0.69314718055994530942;
+}
+
+// The inverse is left in `a`, or (BIG) in `gtmp`: inv_of<BIG>(a, gtmp) names the place.
+template <bool BIG>
+__device__ __forceinline__ double* inv_of(double* a, double* gtmp) { return BIG ? gtmp : a; }
+template <bool BIG = false>
 __device__ double gj_inverse_any(double* a, int m, double* col, double* prow, int* piv, int* rinv, int* pinfo, double* red,
-                                 bool* singular) {
+                                 bool* singular, double* blk = nullptr, double* gtmp = nullptr) {
+  if (BIG) return gj_inverse_blocked(a, gtmp, m, blk, piv, pinfo, red, singular);
   switch ((m + 15) >> 4) {
     case 1: return gj_inverse_reg<1>(a, m, col, prow, piv, rinv, pinfo, singular);
     case 2: return gj_inverse_reg<2>(a, m, col, prow, piv, rinv, pinfo, singular);
@@ -303,25 +583,55 @@ __device__ double gj_inverse_any(double* a, int m, double* col, double* prow, in
 }
 
 // Z (global, m x m) <- sign(Z).  Returns the number of iterations, or -1 (singular iterate / no convergence).
-__device__ int sign_iteration(double* Z, int m, double* sm, double* col, double* prow, int* piv, int* rinv, int* pinfo, double* red) {
+template <bool BIG>
+__device__ int sign_iteration(double* Z, int m, double* sm, double* col, double* prow, int* piv, int* rinv, int* pinfo, double* red,
+                              double* blk, double* gtmp) {
   const int tid = threadIdx.x;
   double dprev = 1e300;
   bool scaling = true;
   for (int it = 1; it <= CRB_LQR_MAX_ITERS; ++it) {
-    for (int k = tid; k < m * m; k += CRB_LQR_THREADS) sm[k] = Z[k];
+    if (BIG) big_copy(sm, Z, m * m);
+    else
+      for (int k = tid; k < m * m; k += CRB_LQR_THREADS) sm[k] = Z[k];
     __syncthreads();
     bool singular;
-    const double logdet = gj_inverse_any(sm, m, col, prow, piv, rinv, pinfo, red, &singular);
+    const double logdet = gj_inverse_any<BIG>(sm, m, col, prow, piv, rinv, pinfo, red, &singular, blk, gtmp);
     if (singular) return -1;
     const double c = scaling ? exp(-logdet / m) : 1.0, ic = 1.0 / c;
+    const double* inv = inv_of<BIG>(sm, gtmp);
     double dd = 0.0, nn = 0.0;
-    for (int k = tid; k < m * m; k += CRB_LQR_THREADS) {
-      const double z = Z[k];
-      const double zn = 0.5 * fma(c, z, ic * sm[k]);
-      const double e = zn - z;
-      dd = fma(e, e, dd);
-      nn = fma(zn, zn, nn);
-      Z[k] = zn;
+    if (BIG && ((m * m) & 1) == 0) {  // 128-bit accesses, four per thread and trip (bytes in flight, see big_copy)
+      double2* Z2 = reinterpret_cast<double2*>(Z);
+      const double2* I2 = reinterpret_cast<const double2*>(inv);
+      const int cnt = (m * m) >> 1;
+      for (int k0 = 0; k0 < cnt; k0 += 4 * CRB_LQR_THREADS) {
+        double2 zv[4], iv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * CRB_LQR_THREADS + tid;
+          if (k < cnt) { zv[u] = Z2[k]; iv[u] = I2[k]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * CRB_LQR_THREADS + tid;
+          if (k < cnt) {
+            const double z0 = 0.5 * fma(c, zv[u].x, ic * iv[u].x), z1 = 0.5 * fma(c, zv[u].y, ic * iv[u].y);
+            const double e0 = z0 - zv[u].x, e1 = z1 - zv[u].y;
+            dd = fma(e0, e0, fma(e1, e1, dd));
+            nn = fma(z0, z0, fma(z1, z1, nn));
+            Z2[k] = make_double2(z0, z1);
+          }
+        }
+      }
+    } else {
+      for (int k = tid; k < m * m; k += CRB_LQR_THREADS) {
+        const double z = Z[k];
+        const double zn = 0.5 * fma(c, z, ic * inv[k]);
+        const double e = zn - z;
+        dd = fma(e, e, dd);
+        nn = fma(zn, zn, nn);
+        Z[k] = zn;
+      }
     }
     dd = block_sum(dd, red);
     nn = block_sum(nn, red);
@@ -341,8 +651,9 @@ __device__ int sign_iteration(double* Z, int m, double* sm, double* col, double*
 // on m x m matrices: one inversion of the closed loop plus two products per iteration, against one inversion of the
 // twice as large Hamiltonian for a full Riccati solve.  A (global, in: Ac, destroyed), W (global, in: residual, out:
 // 2 dS), Tm: scratch.  Returns the iteration count or -1.
+template <bool BIG>
 __device__ int lyapunov_sign_iteration(double* A, double* W, double* Tm, int m, double* sm, double* col, double* prow, int* piv,
-                                       int* rinv, int* pinfo, double* red) {
+                                       int* rinv, int* pinfo, double* red, double* blk, double* gtmp) {
   const int tid = threadIdx.x;
   double dprev = 1e300;
   bool scaling = true;
@@ -350,14 +661,15 @@ __device__ int lyapunov_sign_iteration(double* A, double* W, double* Tm, int m, 
     for (int k = tid; k < m * m; k += CRB_LQR_THREADS) sm[k] = A[k];
     __syncthreads();
     bool singular;
-    const double logdet = gj_inverse_any(sm, m, col, prow, piv, rinv, pinfo, red, &singular);
+    const double logdet = gj_inverse_any<BIG>(sm, m, col, prow, piv, rinv, pinfo, red, &singular, blk, gtmp);
     if (singular) return -1;
     const double c = scaling ? exp(-logdet / m) : 1.0, ic = 1.0 / c;
+    const double* inv = inv_of<BIG>(sm, gtmp);
     // Tm = W A^-1
     for (int idx = tid; idx < m * m; idx += CRB_LQR_THREADS) {
       const int i = idx / m, j = idx - i * m;
       double acc = 0.0;
-      for (int k = 0; k < m; ++k) acc = fma(W[i * m + k], sm[k * m + j], acc);
+      for (int k = 0; k < m; ++k) acc = fma(W[i * m + k], inv[k * m + j], acc);
       Tm[idx] = acc;
     }
     __syncthreads();
@@ -366,10 +678,10 @@ __device__ int lyapunov_sign_iteration(double* A, double* W, double* Tm, int m, 
     for (int idx = tid; idx < m * m; idx += CRB_LQR_THREADS) {
       const int i = idx / m, j = idx - i * m;
       double acc = 0.0;
-      for (int k = 0; k < m; ++k) acc = fma(sm[k * m + i], Tm[k * m + j], acc);
+      for (int k = 0; k < m; ++k) acc = fma(inv[k * m + i], Tm[k * m + j], acc);
       W[idx] = 0.5 * fma(c, W[idx], ic * acc);
       const double z = A[idx];
-      const double zn = 0.5 * fma(c, z, ic * sm[idx]);
+      const double zn = 0.5 * fma(c, z, ic * inv[idx]);
       const double e = zn - z;
       dd = fma(e, e, dd);
       nn = fma(zn, zn, nn);
@@ -411,19 +723,24 @@ __device__ void riccati_residual(int n2, const double* A, const double* G, const
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) {
+// BIG: the 4n x 4n work matrix does not fit shared memory (n > 42): it lives in the block's global workspace and is
+// inverted by the blocked elimination (gj_inverse_blocked), whose panels take the block's shared memory (one block per SM).
+template <bool BIG>
+__global__ void __launch_bounds__(CRB_LQR_THREADS, BIG ? 1 : 3) crb_lqr_kernel(LqrArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int n = a.n, n2 = 2 * n, D = 4 * n, tid = threadIdx.x;
   double* ws = a.ws + (long long)blockIdx.x * a.ws_stride;
-  // D x D work matrix: shared memory up to n = 42, else the tail of the block's global workspace (L2-resident;
-  // the elimination then streams it once per pivot -- a functional path for long beams, not a fast one)
-  double* sm = a.big ? ws + (a.ws_stride - (long long)D * D) : smem;
-  double* col = a.big ? smem : smem + D * D;  // 2 (D + 16): double-buffered pivot column (register-resident elimination)
+  // D x D work matrix: shared memory up to n = 42, else the tail of the block's global workspace, with a second
+  // D x D scratch matrix in front of it (un-permutation of the blocked inverse)
+  double* sm = BIG ? ws + (a.ws_stride - (long long)D * D) : smem;
+  double* gtmp = BIG ? sm - (long long)D * D : nullptr;
+  double* col = BIG ? smem : smem + D * D;  // 2 (D + 16): double-buffered pivot column (register-resident elimination)
   double* prow = col + 2 * (D + 16);  // 2 (D + 16): pivot row
   double* red = prow + 2 * (D + 16);  // 32
   int* piv = reinterpret_cast<int*>(red + 32);  // D
   int* rinv = piv + D;             // D
   int* pinfo = rinv + D;           // 4
+  double* blk = BIG ? reinterpret_cast<double*>(pinfo + 8 + ((2 * D) & 1)) : nullptr;  // panels of the blocked elimination
   double* Z = ws;                 // D^2
   double* A = Z + D * D;          // n2^2 each
   double* G = A + n2 * n2;
@@ -440,9 +757,9 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
   // R^-1 once per block
   for (int k = tid; k < n * n; k += CRB_LQR_THREADS) sm[k] = a.R[k];
   __syncthreads();
-  gj_inverse_any(sm, n, col, prow, piv, rinv, pinfo, red, &singular);
+  gj_inverse_any<BIG>(sm, n, col, prow, piv, rinv, pinfo, red, &singular, blk, gtmp);
   const bool r_singular = singular;
-  for (int k = tid; k < n * n; k += CRB_LQR_THREADS) Rinv[k] = sm[k];
+  for (int k = tid; k < n * n; k += CRB_LQR_THREADS) Rinv[k] = inv_of<BIG>(sm, gtmp)[k];
   __syncthreads();
 
   for (int member = blockIdx.x; member < a.n_members; member += gridDim.x) {
@@ -454,9 +771,9 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
     __syncthreads();
     for (int k = tid; k < n * n; k += CRB_LQR_THREADS) sm[k] = Mb[k];
     __syncthreads();
-    gj_inverse_any(sm, n, col, prow, piv, rinv, pinfo, red, &singular);
+    gj_inverse_any<BIG>(sm, n, col, prow, piv, rinv, pinfo, red, &singular, blk, gtmp);
     if (singular || r_singular) status = 1;
-    for (int k = tid; k < n * n; k += CRB_LQR_THREADS) Minv[k] = sm[k];
+    for (int k = tid; k < n * n; k += CRB_LQR_THREADS) Minv[k] = inv_of<BIG>(sm, gtmp)[k];
     __syncthreads();
     if (status == 0) {
       // A = [[0, I], [-M^-1 K, 0]]   (:84-118);   G = B R^-1 B^T = [[0, 0], [0, M^-1 R^-1 M^-T]]   (:120-146)
@@ -484,7 +801,7 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
           // correction: Newton-Kleinman step on the closed loop of the current solution (Qc holds its residual)
           for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) Z[k] = Ac[k];
           __syncthreads();
-          if (lyapunov_sign_iteration(Z, Qc, T, n2, sm, col, prow, piv, rinv, pinfo, red) < 0) { status = 2; break; }
+          if (lyapunov_sign_iteration<BIG>(Z, Qc, T, n2, sm, col, prow, piv, rinv, pinfo, red, blk, gtmp) < 0) { status = 2; break; }
           __syncthreads();
           for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
             const int i = k / n2, j = k - i * n2;
@@ -506,7 +823,7 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
           Z[k] = v;
         }
         __syncthreads();
-        if (sign_iteration(Z, D, sm, col, prow, piv, rinv, pinfo, red) < 0) { status = 2; break; }
+        if (sign_iteration<BIG>(Z, D, sm, col, prow, piv, rinv, pinfo, red, blk, gtmp) < 0) { status = 2; break; }
         __syncthreads();
         // dS = W21 (W11 - I)^-1
         for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
@@ -514,9 +831,10 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
           sm[k] = Z[i * D + j] - (i == j ? 1.0 : 0.0);
         }
         __syncthreads();
-        gj_inverse_any(sm, n2, col, prow, piv, rinv, pinfo, red, &singular);
+        gj_inverse_any<BIG>(sm, n2, col, prow, piv, rinv, pinfo, red, &singular, blk, gtmp);
         if (singular) { status = 2; break; }
-        mat_mul(n2, n2, n2, [&](int i, int k) { return Z[(n2 + i) * D + k]; }, [&](int k, int j) { return sm[k * n2 + j]; },
+        const double* xinv = inv_of<BIG>(sm, gtmp);
+        mat_mul(n2, n2, n2, [&](int i, int k) { return Z[(n2 + i) * D + k]; }, [&](int k, int j) { return xinv[k * n2 + j]; },
                 [&](int i, int j, double v) { T[i * n2 + j] = v; });
         __syncthreads();
         for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) {
@@ -544,7 +862,7 @@ __global__ void __launch_bounds__(CRB_LQR_THREADS, 3) crb_lqr_kernel(LqrArgs a) 
       // closed-loop eigenvalues (:185-189): sign(A - B K) must be -I
       for (int k = tid; k < n2 * n2; k += CRB_LQR_THREADS) Z[k] = Ac[k];
       __syncthreads();
-      if (sign_iteration(Z, n2, sm, col, prow, piv, rinv, pinfo, red) < 0) {
+      if (sign_iteration<BIG>(Z, n2, sm, col, prow, piv, rinv, pinfo, red, blk, gtmp) < 0) {
         status = 3;
       } else {
         double tr = 0.0;
@@ -581,16 +899,24 @@ inline size_t lqr_smem_small(int n) {  // everything but the D x D work matrix
   return sizeof(double) * (4 * (D + 16) + 32) + sizeof(int) * (2 * D + 8);
 }
 inline bool lqr_big(int n) { return lqr_smem_small(n) + sizeof(double) * 16 * (size_t)n * n > 227 * 1024; }
-inline size_t lqr_smem_bytes(int n) { return lqr_smem_small(n) + (lqr_big(n) ? 0 : sizeof(double) * 16 * (size_t)n * n); }
-inline long long lqr_ws_doubles(int n) { return 16ll * n * n + 7 * 4ll * n * n + 3ll * n * n + (lqr_big(n) ? 16ll * n * n : 0); }
+inline size_t lqr_smem_bytes(int n) {
+  return lqr_smem_small(n) + 16 + sizeof(double) * (lqr_big(n) ? lqr_blk_doubles(4 * n) : 16 * (size_t)n * n);
+}
+inline long long lqr_ws_doubles(int n) {  // (even: the two D x D matrices at the tail of a block's workspace stay 16-byte aligned)
+  return (16ll * n * n + 7 * 4ll * n * n + 3ll * n * n + (lqr_big(n) ? 32ll * n * n : 0) + 1) & ~1ll;
+}
 
 int lqr_grid(int n, int n_members, int* out) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_lqr: %s", cudaGetErrorString(e));
-  if (int rc = set_smem(crb_lqr_kernel, lqr_smem_bytes(n), "crb_lqr_gains")) return rc;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crb_lqr_kernel, CRB_LQR_THREADS, lqr_smem_bytes(n));
+  const bool big = lqr_big(n);
+  if (int rc = big ? set_smem(crb_lqr_kernel<true>, lqr_smem_bytes(n), "crb_lqr_gains")
+                   : set_smem(crb_lqr_kernel<false>, lqr_smem_bytes(n), "crb_lqr_gains"))
+    return rc;
+  e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crb_lqr_kernel<true>, CRB_LQR_THREADS, lqr_smem_bytes(n))
+          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crb_lqr_kernel<false>, CRB_LQR_THREADS, lqr_smem_bytes(n));
   if (e != cudaSuccess || per_sm < 1) return crb_fail(CRB_E_CUDA, "crb_lqr: occupancy query failed (%s)", cudaGetErrorString(e));
   const long long cap = (long long)sms * per_sm;
   *out = (int)(n_members < cap ? n_members : cap);
@@ -780,7 +1106,8 @@ extern "C" int crb_lqr_gains(int32_t n, int32_t n_members, const double* M_beam,
   a.ws = static_cast<double*>(workspace);
   a.ws_stride = lqr_ws_doubles(n);
   a.big = lqr_big(n) ? 1 : 0;
-  crb_lqr_kernel<<<grid, CRB_LQR_THREADS, lqr_smem_bytes(n), static_cast<cudaStream_t>(stream)>>>(a);
+  if (a.big) crb_lqr_kernel<true><<<grid, CRB_LQR_THREADS, lqr_smem_bytes(n), static_cast<cudaStream_t>(stream)>>>(a);
+  else crb_lqr_kernel<false><<<grid, CRB_LQR_THREADS, lqr_smem_bytes(n), static_cast<cudaStream_t>(stream)>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return crb_fail(CRB_E_CUDA, "crb_lqr_gains: %s", cudaGetErrorString(e));
   return 0;

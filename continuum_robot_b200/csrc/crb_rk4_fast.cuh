@@ -393,13 +393,16 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
   // reduced index of own DOF (j, d): consecutive on contiguous plans without phantom slots, else the plan's table
   const int n = C.n;
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
-  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter)
-  constexpr int fw_mpw = 32 >> LV;
-  const int fw_ml = (threadIdx.x & 31) >> LV;
-  const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
-  const int fw_cnt = max(0, min(fw_mpw, S.n_members - fw_m0));
+  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter; only the selection mask lives across
+  // the step loop, everything else is recomputed when a frame is written)
   FrameWriter<M, NC> FW;
   FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
+  auto write_frame = [&](long long frame, const double (&fq)[M][3], const double (&fv)[M][3]) {
+    constexpr int fw_mpw = 32 >> LV;
+    const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
+    FW.stage = stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr;
+    FW.write(S, Y, frame, fw_m0, (threadIdx.x & 31) >> LV, max(0, min(fw_mpw, S.n_members - fw_m0)), n, fq, fv, rix);
+  };
   double* xm = X + (long long)C.member * 2 * n;
   double Q0[M][3], v[M][3], Sa[M][3], Aa[M][3], w[M][3];
 #pragma unroll
@@ -465,7 +468,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) FW.write(S, Y, (k + 1) / save_every - 1, fw_m0, fw_ml, fw_cnt, n, w, v, rix);
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, w, v);
   }
   if (C.active) {
 #pragma unroll
@@ -479,6 +482,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
+  FW.stage = stage_rows;
   FW.drain();
 }
 
@@ -563,13 +567,16 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
   // reduced index of own DOF (j, d): 3 (s0 + j) + d on contiguous plans without phantom slots, else the
   // plan's table (-1: constrained or phantom, held at zero)
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
-  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter)
-  constexpr int fw_mpw = 32 >> LV;
-  const int fw_ml = (threadIdx.x & 31) >> LV;
-  const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
-  const int fw_cnt = max(0, min(fw_mpw, S.n_members - fw_m0));
+  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter; only the selection mask lives across
+  // the step loop, everything else is recomputed when a frame is written)
   FrameWriter<M, NC> FW;
   FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
+  auto write_frame = [&](long long frame, const double (&fq)[M][3], const double (&fv)[M][3]) {
+    constexpr int fw_mpw = 32 >> LV;
+    const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
+    FW.stage = stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr;
+    FW.write(S, Y, frame, fw_m0, (threadIdx.x & 31) >> LV, max(0, min(fw_mpw, S.n_members - fw_m0)), n, fq, fv, rix);
+  };
   double* xm = X + (long long)C.member * 2 * n;
   double q[M][3], v[M][3], w[2][M][3];
 #pragma unroll
@@ -659,7 +666,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) FW.write(S, Y, (k + 1) / save_every - 1, fw_m0, fw_ml, fw_cnt, n, q, v, rix);
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, q, v);
   }
   if (C.active) {
 #pragma unroll
@@ -673,6 +680,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
+  FW.stage = stage_rows;
   FW.drain();
 }
 
@@ -979,13 +987,16 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
   const int n = C.n;
   // reduced index of own DOF (j, d); NC: the plan's table (-1: constrained or phantom, held at zero)
   auto rix = [&](int j, int d) -> int { return NC ? C.ri[NC ? j : 0][d] : 3 * (s0 + j) + d; };
-  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter)
-  constexpr int fw_mpw = 32 >> LV;
-  const int fw_ml = (threadIdx.x & 31) >> LV;
-  const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
-  const int fw_cnt = max(0, min(fw_mpw, S.n_members - fw_m0));
+  // recorded frames: the warp's members are consecutive rows of Y (FrameWriter; only the selection mask lives across
+  // the step loop, everything else is recomputed when a frame is written)
   FrameWriter<M, NC> FW;
   FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
+  auto write_frame = [&](long long frame, const double (&fq)[M][3], const double (&fv)[M][3]) {
+    constexpr int fw_mpw = 32 >> LV;
+    const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
+    FW.stage = stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr;
+    FW.write(S, Y, frame, fw_m0, (threadIdx.x & 31) >> LV, max(0, min(fw_mpw, S.n_members - fw_m0)), n, fq, fv, rix);
+  };
   double* xm = X + (long long)C.member * 2 * n;
   double q[M][3], v[M][3], w[M][3], uc[UC ? M : 1][3];
 #pragma unroll
@@ -1017,7 +1028,7 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         q[j][d] = fma(hh, dv, fma(h, v[j][d], q[j][d]));
         v[j][d] += dv;
       }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) FW.write(S, Y, (k + 1) / save_every - 1, fw_m0, fw_ml, fw_cnt, n, q, v, rix);
+    if (Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, q, v);
   }
   if (C.active) {
 #pragma unroll
@@ -1031,5 +1042,6 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         }
       }
   }
+  FW.stage = stage_rows;
   FW.drain();
 }

@@ -26,6 +26,9 @@
 
 #define CRB_SH_WARPS 4
 #define CRB_SH_THREADS (32 * CRB_SH_WARPS)
+#ifndef CRB_SH_MINBLOCKS
+#define CRB_SH_MINBLOCKS 3  // resident blocks per SM the register allocation is sized for (170 registers: no spills)
+#endif
 #define CRB_SH_MAX_KQ 6      // n_free <= 24
 #define CRB_SH_HEADER 8
 
@@ -198,7 +201,7 @@ struct SharedArgs {
 };
 
 template <int KQ, int GKP, bool IMP>
-__global__ void __launch_bounds__(CRB_SH_THREADS)
+__global__ void __launch_bounds__(CRB_SH_THREADS, CRB_SH_MINBLOCKS)
 crb_rk4_shared_kernel(SharedArgs A, double* __restrict__ X, double t0, double h, int nsteps, double* __restrict__ Y,
                       int save_every) {
   constexpr int NT = (KQ + 1) / 2;
