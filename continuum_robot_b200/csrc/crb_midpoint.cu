@@ -24,9 +24,15 @@ static int launch_midpoint(const crb_plan_t* plan, const crb_system_t* sys, cons
   const bool uc = sys->u_const || sys->f_ext, imp = sys->imp_amp != nullptr;
 #define CRB_MID(UCV, IMPV, NCV)                                                                                \
   {                                                                                                           \
-    if (int rc = set_smem(crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_midpoint")) return rc;  \
-    crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, afac, X, t0, h, nsteps, \
-                                                                                             Y_out, save_every, stage_off, stage_stride); \
+    if (Y_out) {                                                                                               \
+      if (int rc = set_smem(crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV, true>, bytes, "crb_midpoint")) return rc; \
+      crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(         \
+          P, *sys, afac, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);                        \
+    } else {                                                                                                   \
+      if (int rc = set_smem(crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV, false>, bytes, "crb_midpoint")) return rc; \
+      crb_midpoint_kernel<M, LV, UCV, IMPV, PM, NCV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(        \
+          P, *sys, afac, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);                        \
+    }                                                                                                          \
   }
   if (!(plan->contiguous && plan->p_act == plan->p)) {  // any boundary conditions / phantom slots: NC variants
     if (uc || imp) CRB_MID(true, true, true)

@@ -377,7 +377,9 @@ struct FrameWriter {
 
 // GRAV: slot-space gravity (config 1 as an ensemble: linear beams under gravity; the force depends on the stage
 // positions only, so the Nystrom form still applies).  NC: see FastCtx.
-template <int M, int LV, bool IMP, bool GRAV = false, bool NC = false>
+// REC: frames are recorded (FrameWriter code compiled in; without it the step loop keeps the registers of the
+// recording-free kernel: measured 7-9 % on the one-tile-per-block kernels)
+template <int M, int LV, bool IMP, bool GRAV = false, bool NC = false, bool REC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h,
                     int nsteps, double* __restrict__ Y, int save_every, int stage_off, int stage_stride) {
@@ -396,7 +398,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
   // recorded frames: the warp's members are consecutive rows of Y (FrameWriter; only the selection mask lives across
   // the step loop, everything else is recomputed when a frame is written)
   FrameWriter<M, NC> FW;
-  FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
+  if (REC) FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
   auto write_frame = [&](long long frame, const double (&fq)[M][3], const double (&fv)[M][3]) {
     constexpr int fw_mpw = 32 >> LV;
     const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
@@ -468,7 +470,7 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, w, v);
+    if (REC && Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, w, v);
   }
   if (C.active) {
 #pragma unroll
@@ -482,8 +484,10 @@ crb_rk4_fast_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
-  FW.stage = stage_rows;
-  FW.drain();
+  if (REC) {
+    FW.stage = stage_rows;
+    FW.drain();
+  }
 }
 
 // ==========================================================================================
@@ -554,7 +558,7 @@ __device__ __forceinline__ void fast_apply2(const CT& C, double (&w)[2][M][3]) {
 // launch by one paired solve.
 // PM: every member has its OWN mass factors (density / area / lengths differ per member): each lane group stages its member's compact factor copy in its own shared-memory
 // region.
-template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false>
+template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false, bool REC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_FAST_MINBLOCKS)
 crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, double h, int nsteps,
                     double* __restrict__ Y, int save_every, int stage_off, int stage_stride) {
@@ -570,7 +574,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
   // recorded frames: the warp's members are consecutive rows of Y (FrameWriter; only the selection mask lives across
   // the step loop, everything else is recomputed when a frame is written)
   FrameWriter<M, NC> FW;
-  FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
+  if (REC) FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
   auto write_frame = [&](long long frame, const double (&fq)[M][3], const double (&fv)[M][3]) {
     constexpr int fw_mpw = 32 >> LV;
     const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
@@ -666,7 +670,7 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
           }
       }
     }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, q, v);
+    if (REC && Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, q, v);
   }
   if (C.active) {
 #pragma unroll
@@ -680,8 +684,10 @@ crb_rk4_lin2_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0, 
         }
       }
   }
-  FW.stage = stage_rows;
-  FW.drain();
+  if (REC) {
+    FW.stage = stage_rows;
+    FW.drain();
+  }
 }
 
 // ==========================================================================================
@@ -974,7 +980,7 @@ crb_rk4_lin2p_kernel(KPlan P, crb_system_t S, double* __restrict__ X, double t0,
 #ifndef CRB_MID_PINS
 #define CRB_MID_PINS 4
 #endif
-template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false>
+template <int M, int LV, bool UC, bool IMP, bool PM, bool NC = false, bool REC = false>
 __global__ void __launch_bounds__(CRB_FAST_THREADS, CRB_MID_MINBLOCKS)
 crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, double* __restrict__ X, double t0,
                     double h, int nsteps, double* __restrict__ Y, int save_every, int stage_off, int stage_stride) {
@@ -990,7 +996,7 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
   // recorded frames: the warp's members are consecutive rows of Y (FrameWriter; only the selection mask lives across
   // the step loop, everything else is recomputed when a frame is written)
   FrameWriter<M, NC> FW;
-  FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
+  if (REC) FW.init(S, Y, n, stage_rows ? stage_rows + (threadIdx.x >> 5) * stage_stride : nullptr, rix);
   auto write_frame = [&](long long frame, const double (&fq)[M][3], const double (&fv)[M][3]) {
     constexpr int fw_mpw = 32 >> LV;
     const int fw_m0 = blockIdx.x * (CRB_FAST_WARPS * fw_mpw) + (threadIdx.x >> 5) * fw_mpw;
@@ -1028,7 +1034,7 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         q[j][d] = fma(hh, dv, fma(h, v[j][d], q[j][d]));
         v[j][d] += dv;
       }
-    if (Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, q, v);
+    if (REC && Y && save_every > 0 && (k + 1) % save_every == 0) write_frame((k + 1) / save_every - 1, q, v);
   }
   if (C.active) {
 #pragma unroll
@@ -1042,6 +1048,8 @@ crb_midpoint_kernel(KPlan P, crb_system_t S, const double* __restrict__ afac, do
         }
       }
   }
-  FW.stage = stage_rows;
-  FW.drain();
+  if (REC) {
+    FW.stage = stage_rows;
+    FW.drain();
+  }
 }

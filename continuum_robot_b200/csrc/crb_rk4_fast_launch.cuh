@@ -45,9 +45,15 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
       }                                                                                                        \
     }                                                                                                          \
     if constexpr (PM) {                                                                                        \
-      if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV>, bytes, "crb_rk4")) return rc;      \
-      crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
-                                                                                               Y_out, save_every, stage_off, stage_stride); \
+      if (Y_out) {                                                                                             \
+        if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV, true>, bytes, "crb_rk4")) return rc; \
+        crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(       \
+            P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);                            \
+      } else {                                                                                                 \
+        if (int rc = set_smem(crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV, false>, bytes, "crb_rk4")) return rc; \
+        crb_rk4_lin2_kernel<M, LV, UCV, IMPV, PM, NCV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(      \
+            P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);                            \
+      }                                                                                                        \
     } else {                                                                                                   \
       return 1; /* rows not 16-byte aligned: general kernel */                                                 \
     }                                                                                                          \
@@ -59,9 +65,15 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
     if constexpr (!PM) {
 #define CRB_FASTG(IMPV, NCV)                                                                                  \
   {                                                                                                           \
-    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, IMPV, true, NCV>, bytes, "crb_rk4")) return rc;          \
-    crb_rk4_fast_kernel<M, LV, IMPV, true, NCV><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, \
-                                                                                          Y_out, save_every, stage_off, stage_stride); \
+    if (Y_out) {                                                                                              \
+      if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, IMPV, true, NCV, true>, bytes, "crb_rk4")) return rc;  \
+      crb_rk4_fast_kernel<M, LV, IMPV, true, NCV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(           \
+          P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);                             \
+    } else {                                                                                                  \
+      if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, IMPV, true, NCV, false>, bytes, "crb_rk4")) return rc; \
+      crb_rk4_fast_kernel<M, LV, IMPV, true, NCV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(          \
+          P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);                             \
+    }                                                                                                         \
   }
       if (imp && nc) CRB_FASTG(true, true)
       else if (imp) CRB_FASTG(true, false)
@@ -91,11 +103,11 @@ static int launch(const crb_plan_t* plan, const crb_system_t* sys, double* X, do
   } else if (uc) {
     return 1;  // the stage-by-stage fast kernel has no constant-force path: use the general kernel
   } else if (imp) {
-    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, true, false, false, true>, bytes, "crb_rk4")) return rc;
+    crb_rk4_fast_kernel<M, LV, true, false, false, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);
   } else {
-    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false>, bytes, "crb_rk4")) return rc;
-    crb_rk4_fast_kernel<M, LV, false><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);
+    if (int rc = set_smem(crb_rk4_fast_kernel<M, LV, false, false, false, true>, bytes, "crb_rk4")) return rc;
+    crb_rk4_fast_kernel<M, LV, false, false, false, true><<<grid, CRB_FAST_THREADS, bytes, stream>>>(P, *sys, X, t0, h, nsteps, Y_out, save_every, stage_off, stage_stride);
   }
 #undef CRB_LIN2
 #undef CRB_LIN2N
