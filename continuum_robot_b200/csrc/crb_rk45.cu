@@ -19,9 +19,9 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   const unsigned need = crb_needed_features(plan, sys);
   unsigned prof = crb_pick_profile(need);
   if (prof == CRB_F_PROFILE_C) prof = CRB_F_ALL;  // the reduced-vector feedback path is compiled into the generic RK45 kernel only
-  // shared memory: [mass factors][per-member scratch][stage accelerations 21 m doubles per thread]
+  // shared memory: [mass factors][per-member scratch][stage accelerations (+ committed state with CRB_RK45_QVS) 3 m doubles per vector and thread]
   auto total_bytes = [&](const SmemLayout& L, int m) {
-    return sizeof(double) * ((size_t)L.mfac_doubles + (size_t)L.scratch_doubles * mpb + (size_t)21 * m * 32 * WPB);
+    return sizeof(double) * ((size_t)L.mfac_doubles + (size_t)L.scratch_doubles * mpb + (size_t)3 * CRB_RK45_STAGE_VECTORS * m * 32 * WPB);
   };
 #define CRB_RK45_LAUNCH(MM, PROF, LL, PMV)                                                                 \
   {                                                                                                        \
@@ -33,7 +33,7 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
 #define CRB_RK45_CASE(MM, LL)                                                                             \
   if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                          \
     if (sys->mass_shared) {                                                                                \
-      if (prof == CRB_F_PROFILE_A) SL = smem_layout_compact(plan, sys, &bytes);                            \
+      if (prof == CRB_F_PROFILE_A || CRB_RK45_UMS_ALL) SL = smem_layout_compact(plan, sys, &bytes);        \
       if (prof == CRB_F_PROFILE_A) CRB_RK45_LAUNCH(MM, CRB_F_PROFILE_A, LL, false)                         \
       else CRB_RK45_LAUNCH(MM, CRB_F_PROFILE_B, LL, false)                                                 \
     } else {                                                                                               \

@@ -113,6 +113,13 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 #ifndef CRB_RK45_MINBLOCKS
 #define CRB_RK45_MINBLOCKS 1  // resident blocks per SM the register allocation is sized for (1: no cap)
 #endif
+#ifndef CRB_RK45_QVS
+#define CRB_RK45_QVS 0  // 1: the committed state (q, v) lives in shared memory next to the stage accelerations
+#endif
+#define CRB_RK45_STAGE_VECTORS (CRB_RK45_QVS ? 9 : 7)  // shared-memory vectors of 3M doubles per thread
+#ifndef CRB_RK45_UMS_ALL
+#define CRB_RK45_UMS_ALL 1  // the nonlinear profile uses the compact mass solve too (4 KB of factors per block instead of 28: measured 8.08 -> 7.78 ms on config 4)
+#endif
 template <int M, unsigned FEAT, int LV, int WPB, bool PM = false>
 __global__ void __launch_bounds__(32 * WPB, CRB_RK45_MINBLOCKS)
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
@@ -122,7 +129,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
   // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
   // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
-  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || PM);
+  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || PM || CRB_RK45_UMS_ALL);
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g, mpw = 32 / G;
@@ -151,8 +158,30 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   auto KV = [&](int s, int j, int d) -> double& { return kvs[((s * M + j) * 3 + d) * THREADS]; };
   const double inv_size = 1.0 / (2.0 * L.n);
 
-  double q[M][3], v[M][3], qs[M][3], vs[M][3], a[M][3];
-  load_state<M>(L, A.X, q, v);
+  constexpr bool QVS = CRB_RK45_QVS != 0;
+  double qreg[QVS ? 1 : M][3], vreg[QVS ? 1 : M][3], qs[M][3], vs[M][3], a[M][3];
+  auto Qr = [&](int j, int d) -> double& { return QVS ? KV(7, j, d) : qreg[QVS ? 0 : j][d]; };
+  auto Vr = [&](int j, int d) -> double& { return QVS ? KV(8, j, d) : vreg[QVS ? 0 : j][d]; };
+  {
+    double q0[M][3], v0[M][3];
+    load_state<M>(L, A.X, q0, v0);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Qr(j, d) = q0[j][d];
+        Vr(j, d) = v0[j][d];
+      }
+  }
+  auto state_copy = [&](double (&qo)[M][3], double (&vo)[M][3]) {
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        qo[j][d] = Qr(j, d);
+        vo[j][d] = Vr(j, d);
+      }
+  };
   double t = A.t[L.member];
   double h_abs = A.h_abs[L.member];
   const double tb = A.t_bound, rtol = A.rtol, atol = A.atol;
@@ -163,7 +192,9 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   while (ie < A.n_eval && A.t_eval[ie] < t) ++ie;  // outputs before the current time are not ours
   if (ie < A.n_eval && A.t_eval[ie] == t && running) {
     // SciPy emits t_eval == t0 from the first step's interpolant at x = 0, i.e. y_old itself
-    store_frame<M>(L, S, A.Y_eval, ie, q, v);
+    double q0[M][3], v0[M][3];
+    state_copy(q0, v0);
+    store_frame<M>(L, S, A.Y_eval, ie, q0, v0);
     ++ie;
   }
 
@@ -181,8 +212,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      qs[j][d] = q[j][d];
-      vs[j][d] = v[j][d];
+      qs[j][d] = Qr(j, d);
+      vs[j][d] = Vr(j, d);
     }
 
   // stage inputs of stage s from the stored accelerations (position rows use the squared tableau).
@@ -202,8 +233,9 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
           sv = fma(T.a[s][l], k, sv);
           sq = fma(T.a2[s][l], k, sq);
         }
-        vs[j][d] = fma(h, sv, v[j][d]);
-        qs[j][d] = fma(h2, sq, fma(hc, v[j][d], q[j][d]));
+        const double vv = Vr(j, d);
+        vs[j][d] = fma(h, sv, vv);
+        qs[j][d] = fma(h2, sq, fma(hc, vv, Qr(j, d)));
       }
     ts = t + T.c[s] * h;
   };
@@ -257,9 +289,10 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
 #pragma unroll
         for (int d = 0; d < 3; ++d)
           if (L.ri[j][d] >= 0) {
-            const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
-            const double yq = q[j][d] / scq, yv = v[j][d] / scv;
-            const double fq = v[j][d] / scq, fv = a[j][d] / scv;
+            const double qq = Qr(j, d), vv = Vr(j, d);
+            const double scq = fma(fabs(qq), rtol, atol), scv = fma(fabs(vv), rtol, atol);
+            const double yq = qq / scq, yv = vv / scv;
+            const double fq = vv / scq, fv = a[j][d] / scv;
             s0 += yq * yq + yv * yv;
             s1 += fq * fq + fv * fv;
           }
@@ -272,8 +305,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
       for (int j = 0; j < M; ++j)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          qs[j][d] = fma(h0, v[j][d], q[j][d]);
-          vs[j][d] = fma(h0, a[j][d], v[j][d]);
+          qs[j][d] = fma(h0, Vr(j, d), Qr(j, d));
+          vs[j][d] = fma(h0, a[j][d], Vr(j, d));
         }
       ts = t + h0;
       phase = 1;
@@ -286,8 +319,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
 #pragma unroll
         for (int d = 0; d < 3; ++d)
           if (L.ri[j][d] >= 0) {
-            const double scq = fma(fabs(q[j][d]), rtol, atol), scv = fma(fabs(v[j][d]), rtol, atol);
-            const double dq = (vs[j][d] - v[j][d]) / scq, dv = (a[j][d] - KV(0, j, d)) / scv;
+            const double scq = fma(fabs(Qr(j, d)), rtol, atol), scv = fma(fabs(Vr(j, d)), rtol, atol);
+            const double dq = (vs[j][d] - Vr(j, d)) / scq, dv = (a[j][d] - KV(0, j, d)) / scv;
             s2 += dq * dq + dv * dv;
           }
       const double d2 = sqrt(group_sum(s2, G) * inv_size) / hsel_h0;
@@ -328,8 +361,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
             ev = fma(T.e[l], k, ev);
             if (l < 6) eq = fma(T.e2[l], k, eq);
           }
-          const double scq = fma(fmax(fabs(q[j][d]), fabs(qs[j][d])), rtol, atol);
-          const double scv = fma(fmax(fabs(v[j][d]), fabs(vs[j][d])), rtol, atol);
+          const double scq = fma(fmax(fabs(Qr(j, d)), fabs(qs[j][d])), rtol, atol);
+          const double scv = fma(fmax(fabs(Vr(j, d)), fabs(vs[j][d])), rtol, atol);
           const double rq = eq * h2 / scq, rv = ev * h / scv;
           se += rq * rq + rv * rv;
         }
@@ -363,7 +396,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
                 }
               }
               const double wcs = fma(T.pcs[0], x, fma(T.pcs[1], x2, fma(T.pcs[2], x3, T.pcs[3] * x4)));
-              frame_put(S.out_sel_inv, out, L.n, r, fma(h, fma(h, pq, wcs * v[j][d]), q[j][d]), fma(h, pv, v[j][d]));
+              frame_put(S.out_sel_inv, out, L.n, r, fma(h, fma(h, pq, wcs * Vr(j, d)), Qr(j, d)), fma(h, pv, Vr(j, d)));
             }
           ++ie;
         }
@@ -372,8 +405,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
         for (int j = 0; j < M; ++j)
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            q[j][d] = qs[j][d];
-            v[j][d] = vs[j][d];
+            Qr(j, d) = qs[j][d];
+            Vr(j, d) = vs[j][d];
             KV(0, j, d) = KV(6, j, d);  // FSAL
           }
         t = t_new;
@@ -391,7 +424,9 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   }
 
   if (L.active) {
-    store_state<M>(L, A.X, q, v);
+    double q0[M][3], v0[M][3];
+    state_copy(q0, v0);
+    store_state<M>(L, A.X, q0, v0);
     if (L.g == 0) {
       A.t[L.member] = t;
       A.h_abs[L.member] = h_abs;

@@ -559,6 +559,10 @@ class BatchedDynamicEulerBernoulliBeam:
         if self.n_param_sets not in (1, B):
             raise ValueError(f"state batch has {B} members but the ensemble was built with {self.n_param_sets} parameter sets")
 
+    def _plan_key(self):
+        pl = self._plan
+        return (int(pl.n_elements), int(pl.n_free), int(pl.m), int(pl.g), int(pl.p), int(pl.contiguous), id(self._d_mfac))
+
     def make_system(self, B: int, *, drag: Optional[FluidDragForce] = None, gravity: Optional[GravityForce] = None,
                     u_const=None, impulse: Optional[TipImpulse] = None, gain=None, ref=None, f_ext=None,
                     member_range=None, time_inputs=()):
@@ -571,6 +575,7 @@ class BatchedDynamicEulerBernoulliBeam:
         n = self.n_free
         keep = []
         s = _lib.CrbSystem()
+        s._crb_plan_key = self._plan_key()  # which lane layout the device arrays of this struct were assembled for
         lo, hi = member_range if member_range is not None else (0, B)
         if not 0 <= lo < hi <= B:
             raise ValueError(f"bad member_range {member_range} for {B} members")

@@ -54,6 +54,15 @@ def with_selection(beam, system, out_sel):
     return s2, keep
 
 
+def _check_system_owner(beam, sysm):
+    """A prebuilt crb_system_t carries device arrays in ONE beam's lane layout (e.g. ``beam.with_slots(2)`` is a
+    different layout than ``beam``): using it with another beam would read mfac / kcoef / red_index wrongly."""
+    key = getattr(sysm, "_crb_plan_key", None)
+    if key is not None and key != beam._plan_key():
+        raise ValueError("this prebuilt system was made by another beam object (different lane layout / factor arrays); "
+                         "build it with the beam it is used with")
+
+
 def _with_selection(beam, sysm, keep, out_sel):
     """Copy of the crb_system_t with the lean-recording table of ``out_sel`` (state indices) attached."""
     import torch
@@ -65,6 +74,8 @@ def _with_selection(beam, sysm, keep, out_sel):
     inv[np.asarray(idx, dtype=np.int64)] = np.arange(len(idx), dtype=np.int32)
     d_inv = torch.from_numpy(inv).to(beam.device)
     s2 = type(sysm).from_buffer_copy(sysm)
+    if hasattr(sysm, "_crb_plan_key"):
+        s2._crb_plan_key = sysm._crb_plan_key
     s2.out_sel_inv = d_inv.data_ptr()
     s2.out_n_sel = len(idx)
     return s2, list(keep) + [d_inv], len(idx)
@@ -116,6 +127,7 @@ def rk4_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: float, ns
     elif u is not None or controller is not None:
         raise ValueError("rk4_steps: `u` / `controller` are part of a prebuilt `system`; pass one or the other")
     sysm, _keep = system
+    _check_system_owner(beam, sysm)
     if out_sel is not None:
         sysm, _keep, width = _with_selection(beam, sysm, _keep, out_sel)
         if Y_out is not None and (Y_out.shape[-1] != width or not Y_out.is_contiguous()):
@@ -152,6 +164,7 @@ def midpoint_steps(beam: BatchedDynamicEulerBernoulliBeam, X, t0: float, h: floa
         if u is not None:
             raise ValueError("midpoint_steps: `u` is part of a prebuilt `system`; pass one or the other")
         sysm, _keep = system
+        _check_system_owner(beam, sysm)
     if out_sel is not None:
         sysm, _keep, width = _with_selection(beam, sysm, _keep, out_sel)
         if Y_out is not None and (Y_out.shape[-1] != width or not Y_out.is_contiguous()):

@@ -188,3 +188,7 @@ def test_prebuilt_system_rejects_extra_inputs():
     system = beam.make_system(2)
     with pytest.raises(ValueError, match="prebuilt"):
         rk4_steps(beam, X, 0.0, 1e-5, 1, u=torch.zeros(2, beam.n_free, dtype=torch.float64, device="cuda"), system=system)
+    # a system built by the 2-slots-per-lane sibling carries another lane layout: refused, not mis-read
+    with pytest.raises(ValueError, match="another beam"):
+        rk4_steps(beam, X, 0.0, 1e-5, 1, system=beam.with_slots(2).make_system(2))
+    rk4_steps(beam, X, 0.0, 1e-5, 1, system=system)
