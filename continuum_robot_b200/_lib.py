@@ -123,6 +123,7 @@ _SIGNATURES = {
     "crb_gain_fragments": (C.c_int64, [C.POINTER(CrbPlan), C.c_void_p, C.c_void_p]),
     "crb_shared_operator": (C.c_int64, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p,
                                         C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p]),
+    "crb_shared_sparse_masks": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p]),
     "crb_dense_matrices": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_char_p, C.c_char_p,
                                      C.c_void_p, C.c_void_p]),
     "crb_dense_matrices_batched": (C.c_int, [C.POINTER(CrbPlan), C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p,

@@ -291,6 +291,13 @@ int64_t crb_shared_operator(const crb_plan_t* plan, const double* params_host, c
                             const uint8_t* bc_host, const double* gain_host, const double* ref_host,
                             double gx, double gy, int32_t gravity_on, int32_t imp_dof, double* out_host);
 
+/* Host only.  The operator blob ends with the internal DOF order crb_shared_operator chose (int32[4 KQ]) and the masks
+ * of the operator tiles that hold a nonzero (uint32[5]: Wq, Wv, P, Gc, Gs).  The rollout kernel carries, per (KQ, GKP),
+ * one code path compiled for the tile masks of the reference's LQR example (straight FIXED-root beam, gain without
+ * axial / bending coupling, gravity along y: examples/lqr_control.py:26-84) next to the all-tiles path; a blob whose
+ * masks are a subset of out5 runs the former.  Returns 0 or a negative error code. */
+int crb_shared_sparse_masks(int32_t KQ, int32_t GKP, uint32_t* out5);
+
 /* Dense BC-reduced matrices for one parameter set (host convenience for LQR synthesis;
  * replaces get_mass_matrix / get_stiffness_matrix, euler_bernoulli_beam.py:357-361,422-511).
  * params_host [N,7]; M_out, K_out host [n,n] row-major (K_out may be NULL). */

@@ -264,8 +264,10 @@ def test_gain_fragments_layout():
     assert lib.crb_gain_fragments(C.byref(p2), None, None) < 0 and b"4 lanes" in lib.crb_last_error()
 
 
-@pytest.mark.parametrize("N,bc0,gravity,with_ref,imp", [(6, 1, True, True, True), (3, 2, True, False, False), (8, 1, False, True, True), (1, 1, True, False, True)])
-def test_shared_operator_blob_matches_numpy(N, bc0, gravity, with_ref, imp):
+@pytest.mark.parametrize("N,bc0,gravity,with_ref,imp,decoupled", [
+    (6, 1, True, True, True, False), (3, 2, True, False, False, False), (8, 1, False, True, True, False), (1, 1, True, False, True, False),
+    (6, 1, True, True, True, True), (5, 2, True, False, True, True), (8, 1, False, False, False, True)])
+def test_shared_operator_blob_matches_numpy(N, bc0, gravity, with_ref, imp, decoupled):
     """crb_shared_operator (host only): de-tile the mma B fragments and compare W, c0, M^-1 e_k and the
     gravity operators with a NumPy restatement built from the oracle's M, K (dynamic_beam_model.py:256-272,
     full_state_linear.py:58, gravity_forces.py:97-146)."""
@@ -284,9 +286,15 @@ def test_shared_operator_blob_matches_numpy(N, bc0, gravity, with_ref, imp):
     et = bytes(int(t) for t in spec.elem_type)
     bcb = bytes(int(b) for b in list(spec.bc) + [0])
     gain = rng.standard_normal((n, 2 * n))
+    if decoupled:
+        # a gain designed on a straight beam does not couple axial and bending DOFs (examples/lqr_control.py:46-84):
+        # zero those blocks exactly, as SciPy's CARE solution has them (tests/golden/cfg5_samples.npz)
+        axial = _axial_mask(spec.bc, N)
+        cross = axial[:, None] != axial[None, :]
+        gain[np.concatenate([cross, cross], axis=1)] = 0.0
     ref = rng.standard_normal(2 * n) if with_ref else None
     imp_dof = n - 2 if imp and n >= 2 else (0 if imp else -1)
-    gx, gy = 1.5, -9.81
+    gx, gy = (0.0, -9.81) if decoupled else (1.5, -9.81)
     args = (C.byref(plan), par.ctypes.data_as(C.c_void_p), et, bcb, gain.ctypes.data_as(C.c_void_p),
             ref.ctypes.data_as(C.c_void_p) if with_ref else None, gx, gy, int(gravity), imp_dof)
     cnt = lib.crb_shared_operator(*args, None)
@@ -295,36 +303,57 @@ def test_shared_operator_blob_matches_numpy(N, bc0, gravity, with_ref, imp):
     assert lib.crb_shared_operator(*args, blob.ctypes.data_as(C.c_void_p)) == cnt
     KQ, NT, GKP = int(blob[2]), int(blob[3]), int(blob[4])
     assert (int(blob[1]), KQ, NT, GKP, int(blob[7])) == (n, (n + 3) // 4, ((n + 3) // 4 + 1) // 2, (N + 3) // 4 if gravity else 0, cnt)
+    tail = blob[cnt - 2 * KQ - 4:].view(np.int32)
+    order, masks = tail[:4 * KQ], tail[4 * KQ:4 * KQ + 5]
+    assert sorted(order[order >= 0].tolist()) == list(range(n))  # a permutation of the reduced DOFs plus padding
     o = 8
     wq = blob[o:o + 32 * KQ * NT].reshape(KQ, NT, 32); o += 32 * KQ * NT
     wv = blob[o:o + 32 * KQ * NT].reshape(KQ, NT, 32); o += 32 * KQ * NT
     pf = blob[o:o + 32 * KQ].reshape(KQ, 32); o += 32 * KQ
     gc = blob[o:o + 32 * GKP * NT].reshape(GKP, NT, 32); o += 32 * GKP * NT
     gs = blob[o:o + 32 * GKP * NT].reshape(GKP, NT, 32); o += 32 * GKP * NT
-    c0 = blob[o:o + 4 * KQ][:n]; o += 4 * KQ
-    mi = blob[o:o + 4 * KQ][:n]
-    # de-tile: lane -> (k = lane % 4, column 2 jo + e = lane // 4); output DOF 4 (2 nt + e) + jo
+    c0i = blob[o:o + 4 * KQ]; o += 4 * KQ
+    mii = blob[o:o + 4 * KQ]
+    c0 = np.zeros(n); mi = np.zeros(n)
+    c0[order[order >= 0]] = c0i[order >= 0]
+    mi[order[order >= 0]] = mii[order >= 0]
+    assert not c0i[order < 0].any() and not mii[order < 0].any()
+    # de-tile: lane -> (k = lane % 4, column 2 jo + e = lane // 4); internal output index 4 (2 nt + e) + jo; internal index
+    # r stands for reduced DOF order[r]
     W = np.zeros((n, 2 * n)); P = np.zeros((N, n)); Gc = np.zeros((n, N)); Gs = np.zeros((n, N))
+    ordx = np.concatenate([order, -np.ones(8, dtype=np.int32)])
     for lane in range(32):
         k, ncol = lane % 4, lane // 4
         jo, e = ncol // 2, ncol % 2
         for i in range(KQ):
-            c = 4 * i + k
+            c = ordx[4 * i + k]
             for nt in range(NT):
-                out = 4 * (2 * nt + e) + jo
-                if out < n and c < n:
+                out = ordx[4 * (2 * nt + e) + jo]
+                if out >= 0 and c >= 0:
                     W[out, c], W[out, n + c] = wq[i, nt, lane], wv[i, nt, lane]
                 else:
                     assert wq[i, nt, lane] == 0 and wv[i, nt, lane] == 0
             seg = 4 * e + jo
-            if seg < N and c < n:
+            if seg < N and c >= 0:
                 P[seg, c] = pf[i, lane]
         for p in range(GKP):
             seg = 4 * p + k
             for nt in range(NT):
-                out = 4 * (2 * nt + e) + jo
-                if seg < N and out < n:
+                out = ordx[4 * (2 * nt + e) + jo]
+                if seg < N and out >= 0:
                     Gc[out, seg], Gs[out, seg] = gc[p, nt, lane], gs[p, nt, lane]
+    # the tile masks name exactly the tiles that hold a nonzero
+    for name, frag, mask in (("wq", wq, masks[0]), ("wv", wv, masks[1]), ("gc", gc, masks[3]), ("gs", gs, masks[4])):
+        nz = frag.reshape(-1, 32).any(axis=1)
+        assert [bool(mask >> b & 1) for b in range(len(nz))] == nz.tolist(), name
+    assert [bool(masks[2] >> b & 1) for b in range(KQ)] == pf.any(axis=1).tolist()
+    n_tiles = sum(bin(int(m) & 0xFFFFFFFF).count("1") for m in masks)
+    if decoupled:
+        assert n_tiles < 2 * KQ * NT + (KQ + 2 * GKP * NT if gravity else 0)  # the chosen order leaves whole tiles empty
+        if (N, bc0, gravity) == (6, 1, True):
+            assert n_tiles == 24  # config 5's shape: 16 (W) + 2 (P) + 4 (cos) + 2 (sin) of 47
+    else:
+        assert np.array_equal(order[:n], np.arange(n))  # a dense gain keeps the natural order
     orc = bo.BeamOracle(spec, bo.ForceSpec(gravity_vector=(gx, gy, 0.0), enable_gravity_effects=gravity))
     K = np.zeros((n, n))
     for j in range(n):
@@ -349,6 +378,53 @@ def test_shared_operator_blob_matches_numpy(N, bc0, gravity, with_ref, imp):
     # argument errors are reported, not raised
     assert lib.crb_shared_operator(C.byref(plan), None, et, bcb, None, None, gx, gy, 0, -1, blob.ctypes.data_as(C.c_void_p)) < 0
     assert lib.crb_shared_operator(C.byref(plan), par.ctypes.data_as(C.c_void_p), et, bcb, None, None, gx, gy, 0, n, None) < 0
+
+
+def _axial_mask(bc, N):
+    """True for the axial (u) entries of the BC-reduced DOF vector (euler_bernoulli_beam.py:221-298: node i keeps
+    [u, w, phi] when free, [phi] when pinned, nothing when fixed)."""
+    out = []
+    for b in list(bc) + [0]:
+        if b == 0:
+            out += [True, False, False]
+        elif b == 2:
+            out += [False]
+    return np.array(out)
+
+
+@pytest.mark.parametrize("N", [3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("gravity", [False, True])
+def test_shared_operator_of_the_lqr_example_fits_the_compiled_tile_pattern(N, gravity):
+    """The straight FIXED-root beam of examples/lqr_control.py:26-84 (gain without axial / bending coupling, gravity
+    along y): the tile masks crb_shared_operator writes are a subset of the masks the rollout kernel's specialised
+    path is compiled for (crb_shared_sparse_masks), i.e. that path is the one that runs -- and it skips tiles."""
+    lib = _lib().load()
+    spec = bo.BeamSpec.uniform(N)
+    rc, plan = _plan(N, [1] + [0] * N)
+    assert rc == 0
+    n = plan.n_free
+    par = np.ascontiguousarray(np.stack([spec.length, spec.elastic_modulus, spec.moment_inertia, spec.density, spec.cross_area,
+                                         np.ones(N), np.ones(N)], axis=1))
+    et = bytes(int(t) for t in spec.elem_type)
+    bcb = bytes([1] + [0] * N)
+    gain = np.random.default_rng(N).standard_normal((n, 2 * n))
+    axial = _axial_mask(spec.bc, N)
+    cross = axial[:, None] != axial[None, :]
+    gain[np.concatenate([cross, cross], axis=1)] = 0.0
+    args = (C.byref(plan), par.ctypes.data_as(C.c_void_p), et, bcb, gain.ctypes.data_as(C.c_void_p), None, 0.0, -9.81, int(gravity), n - 2)
+    cnt = lib.crb_shared_operator(*args, None)
+    blob = np.zeros(cnt)
+    assert lib.crb_shared_operator(*args, blob.ctypes.data_as(C.c_void_p)) == cnt
+    KQ, NT, GKP = int(blob[2]), int(blob[3]), int(blob[4])
+    masks = blob[cnt - 2 * KQ - 4:].view(np.uint32)[4 * KQ:4 * KQ + 5]
+    compiled = np.zeros(5, dtype=np.uint32)
+    assert lib.crb_shared_sparse_masks(KQ, GKP, compiled.ctypes.data_as(C.c_void_p)) == 0
+    assert compiled[0] != 0xFFFFFFFF, "no specialised path for this shape"
+    assert not (masks & ~compiled).any(), (masks, compiled)
+    full = 2 * KQ * NT + (KQ + 2 * GKP * NT if gravity else 0)
+    used = sum(bin(int(m)).count("1") for m in compiled)
+    assert used < full
+    assert lib.crb_shared_sparse_masks(0, 0, compiled.ctypes.data_as(C.c_void_p)) < 0
 
 
 def test_shared_operator_size_limits():
