@@ -196,6 +196,9 @@ def run(names, slots=0, reps=3):
         if name == "cfg4":  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
             B = 4096
             e = ens.config4(B)
+            if os.environ.get("CRB_CFG4_UNIFORM"):  # experiments: identical members (same number of attempts everywhere)
+                e.E[:] = e.E[0]
+                e.impulse_amp[:] = e.impulse_amp[0]
             beam = BatchedDynamicEulerBernoulliBeam({"params": params(e, B), "type": ["nonlinear"] * 64},
                                                     ForceParams(fluid_density=1000.0, enable_fluid_effects=True, enable_gravity_effects=True),
                                                     max_slots_per_lane=a.slots)

@@ -8,6 +8,9 @@
 // GST: one gain PER MEMBER (crb_system_t.gain_stride != 0) staged in shared memory, one warp per block (a member's
 // n x 2n gain is 5 KB for the 6-element LQR example: 16 members per warp fill 83 KB); without it the gains are
 // re-read from L2 at every RHS evaluation.
+#ifndef CRB_RK4_UMS_ALL
+#define CRB_RK4_UMS_ALL 0  // 1: the nonlinear profile uses the compact mass solve too
+#endif
 template <int M, unsigned FEAT, int LV, bool PM = false, bool GST = false>
 __global__ void __launch_bounds__(GST ? 32 : CRB_THREADS)
 crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, double t0, double h,
@@ -17,7 +20,7 @@ crb_rk4_kernel(KPlan P, crb_system_t S, SmemLayout SL, double* __restrict__ X, d
   // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
   // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
   // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
-  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || FEAT == CRB_F_PROFILE_C || PM);
+  constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || FEAT == CRB_F_PROFILE_C || PM || CRB_RK4_UMS_ALL);
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Gk = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g;
@@ -142,7 +145,7 @@ int crb_launch_rk4_general(const crb_plan_t* plan, const crb_system_t* sys, doub
 #define CRB_RK4_CASE(MM, LL)                                                                                       \
   if (plan->m == MM && plan->levels == LL && prof != CRB_F_ALL) {                                                   \
     if (sys->mass_shared) {                                                                                         \
-      const SmemLayout SL = prof != CRB_F_PROFILE_B ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
+      const SmemLayout SL = (prof != CRB_F_PROFILE_B || CRB_RK4_UMS_ALL) ? smem_layout_compact(plan, sys, &bytes) : smem_layout(plan, sys, &bytes); \
       if (prof == CRB_F_PROFILE_A) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_A, LL, false)                                   \
       else if (prof == CRB_F_PROFILE_C) CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_C, LL, false)                              \
       else CRB_RK4_LAUNCH(MM, CRB_F_PROFILE_B, LL, false)                                                           \

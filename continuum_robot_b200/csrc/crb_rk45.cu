@@ -1,11 +1,14 @@
 // crb_rk45.cu -- launcher of the adaptive Dormand-Prince kernel.
+#include <cstdlib>
+
 #include "crb_internal.h"
 #include "crb_rk45.cuh"
 
 int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t, double* h_abs,
                     double t_bound, double rtol, double atol, const double* t_eval, int n_eval, double* Y_eval,
                     int* status, long long* counters, int max_attempts, cudaStream_t stream) {
-  constexpr int WPB = 2;  // warps per block of the adaptive kernels (see crb_rk45.cuh)
+  constexpr int WPB = CRB_RK45_WPB;  // warps per block of the adaptive kernels (see crb_rk45.cuh)
+  static const size_t pad_bytes = getenv("CRB_RK45_PAD_SMEM") ? (size_t)strtoul(getenv("CRB_RK45_PAD_SMEM"), nullptr, 10) : 0;  // occupancy experiments only
   size_t bytes;
   SmemLayout SL = smem_layout(plan, sys, &bytes);
   const int mpb = WPB * (32 / plan->g);
@@ -21,7 +24,7 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   if (prof == CRB_F_PROFILE_C) prof = CRB_F_ALL;  // the reduced-vector feedback path is compiled into the generic RK45 kernel only
   // shared memory: [mass factors][per-member scratch][stage accelerations (+ committed state with CRB_RK45_QVS) 3 m doubles per vector and thread]
   auto total_bytes = [&](const SmemLayout& L, int m) {
-    return sizeof(double) * ((size_t)L.mfac_doubles + (size_t)L.scratch_doubles * mpb + (size_t)3 * CRB_RK45_STAGE_VECTORS * m * 32 * WPB);
+    return sizeof(double) * ((size_t)L.mfac_doubles + (size_t)L.scratch_doubles * mpb + (size_t)3 * CRB_RK45_STAGE_VECTORS * m * 32 * WPB) + pad_bytes;
   };
 #define CRB_RK45_LAUNCH(MM, PROF, LL, PMV)                                                                 \
   {                                                                                                        \

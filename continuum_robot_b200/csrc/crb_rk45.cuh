@@ -117,11 +117,25 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 #define CRB_RK45_QVS 0  // 1: the committed state (q, v) lives in shared memory next to the stage accelerations
 #endif
 #define CRB_RK45_STAGE_VECTORS (CRB_RK45_QVS ? 9 : 7)  // shared-memory vectors of 3M doubles per thread
+#ifndef CRB_RK45_WPB
+#define CRB_RK45_WPB 2
+#endif
+#ifndef CRB_RK45_LOCKSTEP
+#define CRB_RK45_LOCKSTEP 0  // 1: the warps of a block start every attempt together (block barrier): they then walk through the same code at about the same time and share its instruction-cache lines
+#endif
+#ifndef CRB_RK45_ROLLED
+#define CRB_RK45_ROLLED 1  // 1: stage inputs by one rolled loop over the earlier stages (8 KB less code; measured 7.84 -> 7.03 ms on config 4) instead of six unrolled copies
+#endif
 #ifndef CRB_RK45_UMS_ALL
 #define CRB_RK45_UMS_ALL 1  // the nonlinear profile uses the compact mass solve too (4 KB of factors per block instead of 28: measured 8.08 -> 7.78 ms on config 4)
 #endif
+#ifdef CRB_RK45_MAXNREG
+#define CRB_RK45_BOUNDS __maxnreg__(CRB_RK45_MAXNREG)  // register cap chosen directly (occupancy experiments)
+#else
+#define CRB_RK45_BOUNDS __launch_bounds__(32 * WPB, CRB_RK45_MINBLOCKS)
+#endif
 template <int M, unsigned FEAT, int LV, int WPB, bool PM = false>
-__global__ void __launch_bounds__(32 * WPB, CRB_RK45_MINBLOCKS)
+__global__ void CRB_RK45_BOUNDS
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   constexpr int THREADS = 32 * WPB;
   extern __shared__ __align__(16) double smem[];
@@ -239,7 +253,44 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
       }
     ts = t + T.c[s] * h;
   };
+  // Rolled form (CRB_RK45_ROLLED): one loop over the earlier stages, tableau entries read from the constant bank by index.
+  // The kernel is instruction-fetch limited (ncu: 20 % of the stall samples are "no instruction", the attempt loop walks
+  // through ~60 KB of SASS against a 32 KB instruction cache), and the six unrolled copies are 24 KB of it.
+  auto prep_stage_rolled = [&](int s) {
+    double sv[M][3], sq[M][3];
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sv[j][d] = sq[j][d] = 0.0;
+    const double* kl = kvs;
+#pragma unroll 1
+    for (int l = 0; l < s; ++l, kl += 3 * M * THREADS) {
+      const double al = T.a[s][l], a2l = T.a2[s][l];
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double k = kl[(j * 3 + d) * THREADS];
+          sv[j][d] = fma(al, k, sv[j][d]);
+          sq[j][d] = fma(a2l, k, sq[j][d]);
+        }
+    }
+    const double cs = T.c[s], hc = h * cs;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double vv = Vr(j, d);
+        vs[j][d] = fma(h, sv[j][d], vv);
+        qs[j][d] = fma(h2, sq[j][d], fma(hc, vv, Qr(j, d)));
+      }
+    ts = t + cs * h;
+  };
   auto prep_stage = [&](int s) {
+    if (CRB_RK45_ROLLED) {
+      prep_stage_rolled(s);
+      return;
+    }
     switch (s) {
       case 1: prep_stage_c(std::integral_constant<int, 1>{}); break;
       case 2: prep_stage_c(std::integral_constant<int, 2>{}); break;
@@ -251,7 +302,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   };
   // start of an attempt (rk.py:111-140); returns false when the warp is done or out of budget
   auto begin_attempt = [&]() -> bool {
-    if (!__any_sync(CRB_FULL_MASK, running)) return false;
+    if (CRB_RK45_LOCKSTEP ? !__syncthreads_or(running) : !__any_sync(CRB_FULL_MASK, running)) return false;
     if (attempts >= A.max_attempts) {
       if (running) status = 1;
       return false;
