@@ -126,7 +126,7 @@ class BatchedLinearQuadraticRegulator:
                    2: "Failed to solve LQR problem: no stabilising Riccati solution",
                    3: "LQR solution results in unstable closed-loop system"}
 
-    def __init__(self, K_beam, M_beam, Q, R, refine_passes: int = 1):
+    def __init__(self, K_beam, M_beam, Q, R, refine_passes: int = 1, decouple: bool = True):
         import torch
 
         for name, a in (("K_beam", K_beam), ("M_beam", M_beam), ("Q", Q), ("R", R)):
@@ -151,11 +151,28 @@ class BatchedLinearQuadraticRegulator:
             if a.shape[0] not in (1, self.B):
                 raise ValueError(f"{name} has {a.shape[0]} members, expected 1 or {self.B}")
         self.refine_passes = int(refine_passes)
+        self.decouple = bool(decouple)  # solve DOF groups that nothing couples as separate, smaller problems
         self._K = self._S = self.status = self.residual = None
 
-    def compute_gain_matrix(self):
-        if self._K is not None:
-            return self._K
+    def _components(self):
+        """Groups of position DOFs that M, K (of any member), R and the four n x n blocks of Q do not couple with each
+        other.  The Riccati equation of such a design is reducible: S and the gain are block diagonal over the groups
+        (a dense CARE solver returns exact zeros there, tests/golden/cfg5_samples.npz), and every group is a smaller
+        synthesis problem.  A straight beam always splits into its axial and its bending DOFs with the diagonal weights
+        of examples/lqr_control.py:61-66: 4n x 4n Hamiltonian -> one of 4n/3 and one of 8n/3, a third of the work."""
+        import torch
+        from scipy.sparse.csgraph import connected_components
+
+        n = self.n
+        P = (self.M_beam != 0).any(0) | (self.K_beam != 0).any(0) | (self.R != 0)
+        for blk in (self.Q[:n, :n], self.Q[:n, n:], self.Q[n:, :n], self.Q[n:, n:]):
+            P |= blk != 0
+        ncomp, labels = connected_components((P | P.T).cpu().numpy(), directed=False)
+        dev = self.M_beam.device
+        return [torch.from_numpy((labels == c).nonzero()[0]).to(dev) for c in range(ncomp)]
+
+    def _solve(self, M_beam, K_beam, Q, R):
+        """crb_lqr_gains on one (sub-)problem: gain [B,k,2k], S [B,2k,2k], residual [B], status [B]."""
         import ctypes as C
 
         import torch
@@ -163,21 +180,46 @@ class BatchedLinearQuadraticRegulator:
         from . import _lib
 
         lib = _lib.load()
-        dev, n, B = self.M_beam.device, self.n, self.B
+        dev, n, B = M_beam.device, int(M_beam.shape[-1]), self.B
         need = C.c_size_t(0)
+        _lib.check(lib.crb_lqr_workspace_bytes(n, B, C.byref(need)), ValueError)
+        ws = torch.empty((need.value + 7) // 8, dtype=torch.float64, device=dev)
+        gain = torch.empty((B, n, 2 * n), dtype=torch.float64, device=dev)
+        S = torch.empty((B, 2 * n, 2 * n), dtype=torch.float64, device=dev)
+        resid = torch.empty(B, dtype=torch.float64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        rc = lib.crb_lqr_gains(
+            n, B, M_beam.data_ptr(), int(M_beam.shape[0] == 1), K_beam.data_ptr(), int(K_beam.shape[0] == 1),
+            Q.data_ptr(), R.data_ptr(), self.refine_passes, gain.data_ptr(), S.data_ptr(), resid.data_ptr(),
+            status.data_ptr(), ws.data_ptr(), need.value, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, ValueError)
+        return gain, S, resid, status
+
+    def compute_gain_matrix(self):
+        if self._K is not None:
+            return self._K
+        import torch
+
+        dev, n, B = self.M_beam.device, self.n, self.B
         with torch.cuda.device(dev):
-            _lib.check(lib.crb_lqr_workspace_bytes(n, B, C.byref(need)), ValueError)
-            ws = torch.empty((need.value + 7) // 8, dtype=torch.float64, device=dev)
-            gain = torch.empty((B, n, 2 * n), dtype=torch.float64, device=dev)
-            S = torch.empty((B, 2 * n, 2 * n), dtype=torch.float64, device=dev)
-            resid = torch.empty(B, dtype=torch.float64, device=dev)
-            status = torch.empty(B, dtype=torch.int32, device=dev)
-            rc = lib.crb_lqr_gains(
-                n, B, self.M_beam.data_ptr(), int(self.M_beam.shape[0] == 1), self.K_beam.data_ptr(),
-                int(self.K_beam.shape[0] == 1), self.Q.data_ptr(), self.R.data_ptr(), self.refine_passes,
-                gain.data_ptr(), S.data_ptr(), resid.data_ptr(), status.data_ptr(), ws.data_ptr(), need.value,
-                torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(rc, ValueError)
+            comps = self._components() if self.decouple else []
+            if len(comps) < 2:
+                gain, S, resid, status = self._solve(self.M_beam, self.K_beam, self.Q, self.R)
+            else:
+                gain = torch.zeros((B, n, 2 * n), dtype=torch.float64, device=dev)
+                S = torch.zeros((B, 2 * n, 2 * n), dtype=torch.float64, device=dev)
+                status = torch.zeros(B, dtype=torch.int32, device=dev)
+                res2 = torch.zeros(B, dtype=torch.float64, device=dev)
+                for idx in comps:
+                    idx2 = torch.cat([idx, idx + n])
+                    sub = lambda a, i: a[:, i][:, :, i].contiguous()
+                    Qc = self.Q[idx2][:, idx2].contiguous()
+                    g, s, r, st = self._solve(sub(self.M_beam, idx), sub(self.K_beam, idx), Qc, self.R[idx][:, idx].contiguous())
+                    gain[:, idx[:, None], idx2[None, :]] = g
+                    S[:, idx2[:, None], idx2[None, :]] = s
+                    status = torch.maximum(status, st)
+                    res2 += (r * torch.linalg.matrix_norm(Qc)) ** 2  # residuals are relative to ||Q_c||_F
+                resid = torch.sqrt(res2) / torch.linalg.matrix_norm(self.Q)
             bad = torch.nonzero(status).flatten()
         self.status, self.residual = status, resid
         if bad.numel():

@@ -96,6 +96,41 @@ def test_lqr_gain_of_config5_design_matches_golden_gain():
     assert float(lqr.residual[0]) < 1e-6
 
 
+@pytest.mark.parametrize("N,bc0", [(6, 1), (5, 2), (12, 1)])
+def test_lqr_reducible_designs_are_solved_group_by_group(N, bc0):
+    """Axial and bending DOFs of a straight beam are not coupled by M, K or the diagonal weights of
+    examples/lqr_control.py:61-66: the host class solves the two groups as separate, smaller problems
+    (`decouple=True`, default).  Same gains and S as the one 4n x 4n solve to solver accuracy, exact zeros in the
+    cross blocks (as SciPy's CARE has them), same closeness to the oracle; a Q that couples the groups falls back."""
+    from continuum_robot_b200 import BatchedLinearQuadraticRegulator
+    from oracle import beam_oracle as bo
+
+    par, et, bc = design_ensemble(5, N, seed=40 + N, bc0=bc0)
+    beam = make_gpu_beam(par, et, bc)
+    n = beam.n_free
+    Q, R, Qd, Rd = weights(n)
+    Md, Kd = beam.dense_matrices()
+    split = BatchedLinearQuadraticRegulator(Kd, Md, Qd, Rd)
+    groups = split._components()
+    assert len(groups) == 2 and sorted(int(g.numel()) for g in groups) == sorted([N, n - N])
+    whole = BatchedLinearQuadraticRegulator(Kd, Md, Qd, Rd, decouple=False)
+    Gs, Gw = split.compute_gain_matrix().cpu().numpy(), whole.compute_gain_matrix().cpu().numpy()
+    Ss, Sw = split.get_S().cpu().numpy(), whole.get_S().cpu().numpy()
+    assert np.abs(Gs - Gw).max() <= TOL_VS_REFINED * np.abs(Gw).max()
+    assert np.abs(Ss - Sw).max() <= 1e-9 * np.abs(Sw).max()
+    ax = np.zeros(n, dtype=bool)
+    ax[groups[0].cpu().numpy() if groups[0].numel() == N else groups[1].cpu().numpy()] = True
+    cross = ax[:, None] != ax[None, :]
+    assert not Gs[:, np.concatenate([cross, cross], axis=1)].any()  # exact zeros, e.g. for the tile-skipping rollout kernel
+    assert float(split.residual.max()) < 1e-6 and int(split.status.abs().sum()) == 0
+    for i in range(5):
+        kr = bo.lqr_gain_refined(Kd[i].cpu().numpy(), Md[i].cpu().numpy(), Q, R)
+        assert np.abs(Gs[i] - kr).max() <= TOL_VS_REFINED * np.abs(kr).max()
+    Qc = Qd.clone()
+    Qc[0, 1] = Qc[1, 0] = 1.0  # couples u and w of the first node: one group, one solve
+    assert len(BatchedLinearQuadraticRegulator(Kd, Md, Qc, Rd)._components()) == 1
+
+
 def test_lqr_shared_mass_and_refinement_passes():
     """One mass matrix shared by the ensemble (m_shared), per-member stiffness; 0 / 1 / 2 correction passes."""
     from continuum_robot_b200 import BatchedLinearQuadraticRegulator
@@ -134,7 +169,7 @@ def test_lqr_failures_raise_like_the_reference():
         BatchedLinearQuadraticRegulator(Kd, Md, Qd, Qd)
     with pytest.raises(TypeError):
         BatchedLinearQuadraticRegulator(Kd.cpu(), Md, Qd, Rd)
-    big = torch.eye(97, dtype=torch.float64, device="cuda")
+    big = torch.eye(97, dtype=torch.float64, device="cuda") + 0.01  # one coupled group of 97 DOFs
     with pytest.raises(ValueError, match="exceed the limit"):
         BatchedLinearQuadraticRegulator(big, big, torch.eye(194, dtype=torch.float64, device="cuda"), big).compute_gain_matrix()
 
