@@ -302,6 +302,8 @@ def secondary_measurements():
         if cfg in pipes:
             entry["ncu"] = pipes[cfg]
         out[cfg] = entry
+    if "captured_on" in pipes:  # which build the `ncu` pipe shares were measured on
+        out["ncu_captured_on"] = {k: pipes["captured_on"].get(k) for k in ("commit", "date", "round")}
     return out
 
 

@@ -193,8 +193,8 @@ def run(names, slots=0, reps=3):
             ms = timed(lambda: rk4_steps(beam, X, 0.0, e.h, steps))
             yield {"config": "cfg3 with per-member mass (paired fast kernel, per-member factor sets in shared memory)",
                               "element_steps_per_s": B * 32 * steps / (ms * 1e-3), "ms": ms}
-        if name == "cfg4":  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
-            B = 4096
+        if name in ("cfg4", "cfg4x4"):  # nonlinear 64-element, drag + gravity, adaptive RK45 to 3 ms
+            B = 4096 if name == "cfg4" else 16384  # x4: BASELINE's 4096 members are 3.5 waves of warps on a B200; four times as many show the rate without the partial last wave
             e = ens.config4(B)
             if os.environ.get("CRB_CFG4_UNIFORM"):  # experiments: identical members (same number of attempts everywhere)
                 e.E[:] = e.E[0]
@@ -214,7 +214,7 @@ def run(names, slots=0, reps=3):
             ms = timed(run, reps=2)
             r = out["r"]
             att = (r.naccept + r.nreject).double()
-            yield {"config": "cfg4 4096 x 64 nonlinear RK45 to 3 ms", "m": beam._plan.m, "g": beam._plan.g, "ms": ms,
+            yield {"config": "cfg4 %d x 64 nonlinear RK45 to 3 ms" % B, "m": beam._plan.m, "g": beam._plan.g, "ms": ms,
                               "attempts_mean": float(att.mean()), "attempts_max": float(att.max()),
                               "element_attempts_per_s": float(att.sum()) * 64 / (ms * 1e-3), "success": r.success}
         if name == "cfg5":  # LQR rollout, shared N = 6 design, 131072 members per GPU

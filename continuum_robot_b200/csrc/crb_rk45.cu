@@ -30,6 +30,8 @@ int crb_launch_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, 
   {                                                                                                        \
     const size_t total = total_bytes(SL, MM);                                                              \
     if (int rc = set_smem(crb_rk45_kernel<MM, PROF, LL, WPB, PMV>, total, "crb_rk45")) return rc;          \
+    /* the driver's default carve-out (168 KB here) holds 4 blocks of the 64-element shape; the registers allow 5 */ \
+    cudaFuncSetAttribute(crb_rk45_kernel<MM, PROF, LL, WPB, PMV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
     crb_rk45_kernel<MM, PROF, LL, WPB, PMV><<<grid, 32 * WPB, total, stream>>>(P, *sys, SL, A, T);         \
     return 0;                                                                                              \
   }
