@@ -8,6 +8,8 @@
 // (three streams, PCIe is full duplex), and consecutive calls on the same buffers overlap chunk
 // by chunk (the only cross-call ordering is "chunk c is not uploaded before its previous result
 // has been downloaded"), so a sequence of calls runs at max(copy-in, compute, copy-out).
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "crb_internal.h"
@@ -22,6 +24,7 @@ struct crb_pipeline {
   const double* last_dev = nullptr;
   long long last_members = 0;
   int last_chunk = 0, last_row = 0;
+  int last_trace_chunks = 0;
   bool pending = false;
 };
 
@@ -31,12 +34,18 @@ struct crb_pipeline {
     if (e_ != cudaSuccess) return crb_fail(CRB_E_CUDA, "%s: %s: %s", who, #call, cudaGetErrorString(e_)); \
   } while (0)
 
+static bool pipeline_trace() {  // CRB_PIPELINE_TRACE=1: events carry time stamps, crb_pipeline_synchronize prints the chunk timeline of the last call
+  static const bool on = getenv("CRB_PIPELINE_TRACE") != nullptr;
+  return on;
+}
+
 static int ensure_events(crb_pipeline* p, size_t n) {
+  const unsigned flags = pipeline_trace() ? cudaEventDefault : cudaEventDisableTiming;
   while (p->ev_in.size() < n) {
     cudaEvent_t a, b, c;
-    CRB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "crb_pipeline");
-    CRB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "crb_pipeline");
-    CRB_CUDA(cudaEventCreateWithFlags(&c, cudaEventDisableTiming), "crb_pipeline");
+    CRB_CUDA(cudaEventCreateWithFlags(&a, flags), "crb_pipeline");
+    CRB_CUDA(cudaEventCreateWithFlags(&b, flags), "crb_pipeline");
+    CRB_CUDA(cudaEventCreateWithFlags(&c, flags), "crb_pipeline");
     p->ev_in.push_back(a);
     p->ev_cmp.push_back(b);
     p->ev_out.push_back(c);
@@ -51,7 +60,7 @@ static int pipeline_build(crb_pipeline* p) {
   CRB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking), "crb_pipeline_create");
   CRB_CUDA(cudaStreamCreateWithFlags(&p->s_cmp, cudaStreamNonBlocking), "crb_pipeline_create");
   CRB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking), "crb_pipeline_create");
-  CRB_CUDA(cudaEventCreateWithFlags(&p->ev_entry, cudaEventDisableTiming), "crb_pipeline_create");
+  CRB_CUDA(cudaEventCreateWithFlags(&p->ev_entry, pipeline_trace() ? cudaEventDefault : cudaEventDisableTiming), "crb_pipeline_create");
   CRB_CUDA(cudaEventCreateWithFlags(&p->ev_all_out, cudaEventDisableTiming), "crb_pipeline_create");
   return 0;
 }
@@ -93,6 +102,16 @@ extern "C" int crb_pipeline_synchronize(crb_pipeline_t* p) {
   CRB_CUDA(cudaStreamSynchronize(p->s_in), "crb_pipeline_synchronize");
   CRB_CUDA(cudaStreamSynchronize(p->s_cmp), "crb_pipeline_synchronize");
   CRB_CUDA(cudaStreamSynchronize(p->s_out), "crb_pipeline_synchronize");
+  if (pipeline_trace() && p->pending && p->last_trace_chunks > 0) {
+    fprintf(stderr, "[crb pipeline] chunk: copy-in done / kernel done / copy-out done (ms after the call's entry)\n");
+    for (int c = 0; c < p->last_trace_chunks; ++c) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, p->ev_entry, p->ev_in[c]);
+      cudaEventElapsedTime(&b, p->ev_entry, p->ev_cmp[c]);
+      cudaEventElapsedTime(&d, p->ev_entry, p->ev_out[c]);
+      fprintf(stderr, "[crb pipeline] %2d: %.3f %.3f %.3f\n", c, a, b, d);
+    }
+  }
   p->pending = false;
   return 0;
 }
@@ -194,6 +213,7 @@ extern "C" int crb_rk4_host(crb_pipeline_t* p, const crb_plan_t* plan, const crb
   p->last_members = B;
   p->last_chunk = chunk;
   p->last_row = row;
+  p->last_trace_chunks = (int)nchunks;
   p->pending = true;
   return 0;
 }
