@@ -458,14 +458,21 @@ def test_lqr_rollout_config5_banded_path():
     assert max(block_err(got[i], g["Y"][i, 0], n) for i in range(B)) < 1e-9
 
 
-@pytest.mark.parametrize("N,bc0,gravity,with_ref,with_imp", [
-    (6, 1, True, False, True), (6, 1, False, True, False), (3, 1, True, True, True), (8, 1, True, False, False),
-    (4, 2, True, True, True), (1, 1, True, False, True), (5, 1, False, False, False),
+@pytest.mark.parametrize("N,bc0,gravity,with_ref,with_imp,decoupled", [
+    (6, 1, True, False, True, False), (6, 1, False, True, False, False), (3, 1, True, True, True, False),
+    (8, 1, True, False, False, False), (4, 2, True, True, True, False), (1, 1, True, False, True, False),
+    (5, 1, False, False, False, False),
+    (6, 1, True, True, True, True), (3, 1, True, False, True, True), (4, 1, True, True, False, True),
+    (5, 1, True, False, True, True), (7, 1, True, True, True, True), (8, 1, False, True, True, True),
+    (4, 2, True, True, True, True), (2, 1, True, False, False, True),
 ])
-def test_shared_operator_path_matches_banded_path_and_oracle(N, bc0, gravity, with_ref, with_imp):
+def test_shared_operator_path_matches_banded_path_and_oracle(N, bc0, gravity, with_ref, with_imp, decoupled):
     """Shared-operator RK4 (dense FP64 tensor-core contraction, crb_shared_operator) vs the banded
     per-member kernel and vs the CPU oracle: gains with a non-zero reference, FIXED and PINNED roots,
-    gravity on/off, impulse on/off, 1..8 elements (<= 1e-9 block inf-norm over 300 steps)."""
+    gravity on/off, impulse on/off, 1..8 elements (<= 1e-9 block inf-norm over 300 steps).
+    `decoupled`: a gain without axial / bending coupling and gravity along -y, as in examples/lqr_control.py --
+    the operator's DOFs are reordered and the kernel's tile-skipping code path runs (where one is compiled for the
+    shape; tests/test_host_api.py checks which)."""
     from continuum_robot_b200 import FullStateLinear, TipImpulse
     from continuum_robot_b200 import ensembles as ens
     from continuum_robot_b200.integrate import rk4_steps
@@ -479,10 +486,15 @@ def test_shared_operator_path_matches_banded_path_and_oracle(N, bc0, gravity, wi
     par[0, :, 5], par[0, :, 6] = m["wetted_area"], m["drag_coef"]
     bc = np.array([bc0] + [0] * N)
     et = np.zeros(N, dtype=int)
-    beam = make_gpu_beam(par, et, bc, 0.0, gravity, (1.5, -9.81, 0.0))
+    gvec = (0.0, -9.81, 0.0) if decoupled else (1.5, -9.81, 0.0)
+    beam = make_gpu_beam(par, et, bc, 0.0, gravity, gvec)
     n, B, h, steps = beam.n_free, 37, 2e-6, 300
     # (stiffness-like and damping-like feedback small enough that the closed loop stays tame over the run)
     gain = np.concatenate([50.0 * rng.standard_normal((n, n)), 0.05 * rng.standard_normal((n, n))], axis=1)
+    if decoupled:
+        axial = np.array(sum(([True, False, False] if b == 0 else ([False] if b == 2 else []) for b in bc), []))
+        cross = axial[:, None] != axial[None, :]
+        gain[np.concatenate([cross, cross], axis=1)] = 0.0
     ref = 1e-3 * rng.standard_normal(2 * n) if with_ref else None
     ctrl = FullStateLinear(torch.from_numpy(gain).cuda(), reference=torch.from_numpy(ref).cuda() if with_ref else None)
     amp = rng.uniform(1.0, 5.0, B)
@@ -498,7 +510,7 @@ def test_shared_operator_path_matches_banded_path_and_oracle(N, bc0, gravity, wi
     assert not np.array_equal(gs, gb)  # two different kernels really ran
     assert max(block_err(gs[i], gb[i], n) for i in range(B)) < 1e-9
     spec = bo.BeamSpec(par[0, :, 0], par[0, :, 1], par[0, :, 2], par[0, :, 3], par[0, :, 4], et, bc, par[0, :, 5], par[0, :, 6])
-    orc = bo.BeamOracle(spec, bo.ForceSpec(gravity_vector=(1.5, -9.81, 0.0), enable_gravity_effects=gravity))
+    orc = bo.BeamOracle(spec, bo.ForceSpec(gravity_vector=gvec, enable_gravity_effects=gravity))
     r = np.zeros(2 * n) if ref is None else ref
     for i in (0, B - 1):
         def f(t, x, i=i):
