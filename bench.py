@@ -519,8 +519,8 @@ def main():
     ap.add_argument("--members", type=int, default=65536)
     ap.add_argument("--elements", type=int, default=32)
     ap.add_argument("--steps-per-launch", type=int, default=50)
-    ap.add_argument("--cpu-steps", type=int, default=2000, help="RK4 steps per member in the oracle-port sample")
-    ap.add_argument("--cpu-ref-steps", type=int, default=300, help="RK4 steps per member in the reference sample")
+    ap.add_argument("--cpu-steps", type=int, default=6000, help="RK4 steps per member in the oracle-port sample")
+    ap.add_argument("--cpu-ref-steps", type=int, default=1000, help="RK4 steps per member in the reference sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--e2e-chunk-members", type=int, default=0, help="members per pipelined chunk (0 = two kernel waves)")
