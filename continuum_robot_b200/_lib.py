@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 CRB_MAX_SLOTS = 256
-CRB_VERSION = 106
+CRB_VERSION = 107
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRB_LIB", os.path.join(_HERE, "libcrb.so"))  # CRB_LIB: kernel-variant experiments
@@ -77,6 +77,7 @@ class CrbSystem(C.Structure):
         ("tile_counter", C.c_void_p),
         ("out_sel_inv", C.c_void_p),
         ("out_n_sel", C.c_int32),
+        ("member_order", C.c_void_p),
     ]
 
 

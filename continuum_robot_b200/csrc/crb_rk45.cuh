@@ -148,7 +148,8 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = LV >= 0 ? (1 << (LV >= 0 ? LV : 0)) : P.g, mpw = 32 / G;
   const int mloc = warp * mpw + lane / G;
-  const int member = blockIdx.x * (WPB * mpw) + mloc;
+  const int slot_member = blockIdx.x * (WPB * mpw) + mloc;  // launch slot; S.member_order names the member it integrates
+  const int member = slot_member < S.n_members ? (S.member_order ? S.member_order[slot_member] : slot_member) : S.n_members;
   LaneCtx<M> L;
   const int mpb = WPB * mpw;
   load_lane_ctx<M>(L, P, S, member, lane % G, mf,
@@ -198,6 +199,10 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   };
   double t = A.t[L.member];
   double h_abs = A.h_abs[L.member];
+  // resuming after a budget stop (status 1 on entry): h_abs < 0 carries "the last attempt was rejected"
+  const bool resumed = L.active && A.status[L.member] == 1;
+  const bool resumed_rejected = resumed && h_abs < 0.0;
+  if (resumed) h_abs = fabs(h_abs);
   const double tb = A.t_bound, rtol = A.rtol, atol = A.atol;
   long long nfev = 0, nacc = 0, nrej = 0;
   int status = 0;
@@ -205,10 +210,13 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   int ie = 0;
   while (ie < A.n_eval && A.t_eval[ie] < t) ++ie;  // outputs before the current time are not ours
   if (ie < A.n_eval && A.t_eval[ie] == t && running) {
-    // SciPy emits t_eval == t0 from the first step's interpolant at x = 0, i.e. y_old itself
-    double q0[M][3], v0[M][3];
-    state_copy(q0, v0);
-    store_frame<M>(L, S, A.Y_eval, ie, q0, v0);
+    // SciPy emits t_eval == t0 from the first step's interpolant at x = 0, i.e. y_old itself (a resumed member has
+    // written this frame already, from the interpolant of the step that ended at t)
+    if (!resumed) {
+      double q0[M][3], v0[M][3];
+      state_copy(q0, v0);
+      store_frame<M>(L, S, A.Y_eval, ie, q0, v0);
+    }
     ++ie;
   }
 
@@ -219,7 +227,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   // Every lane of the warp is always in the same phase / stage; members differ only in
   // `running`, t, h and the accept / reject outcome (predicated).
   double hsel_h0 = 0.0, hsel_d1 = 0.0;
-  bool step_rejected = false, new_step = true;
+  bool step_rejected = resumed_rejected, new_step = !resumed_rejected;
   int attempts = 0, phase = 0, st = 0;
   double h = 0.0, h2 = 0.0, t_new = t, ts = t;
 #pragma unroll
@@ -329,7 +337,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   while (true) {
     beam_accel<M, FEAT, false, (UMS ? LV : -1)>(L, S, F, qs, vs, ts, a);
     if (phase == 0) {
-      nfev += 1;
+      if (!resumed) nfev += 1;  // a resumed member counted this evaluation in the launch that computed it first
 #pragma unroll
       for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -481,7 +489,7 @@ crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
     store_state<M>(L, A.X, q0, v0);
     if (L.g == 0) {
       A.t[L.member] = t;
-      A.h_abs[L.member] = h_abs;
+      A.h_abs[L.member] = (status == 1 && step_rejected) ? -h_abs : h_abs;
       A.status[L.member] = status;
       A.counters[3ll * L.member + 0] += nfev;
       A.counters[3ll * L.member + 1] += nacc;

@@ -398,10 +398,26 @@ def _rk45_unfused(beam, X, t0, tf, rtol, atol, u, controller, te, Y_eval, max_at
     return t, h_abs, status, counters
 
 
+def _pilot_attempts(beam, B: int, requested, max_attempts: int) -> int:
+    """Attempts of the pilot launch of an adaptive solve (0: one launch in natural order).  ``requested`` None: a pilot
+    of 8 attempts when the ensemble is more than one and at most 64 waves of the device's resident warps (one wave
+    starts everything at once, and the tail of a very long launch is short relative to its length);
+    CRB_RK45_PILOT overrides."""
+    import torch
+
+    if requested is None and os.environ.get("CRB_RK45_PILOT") is not None:
+        requested = int(os.environ["CRB_RK45_PILOT"])
+    if requested is not None:
+        return max(0, min(int(requested), int(max_attempts) - 1))
+    slots = 8 * torch.cuda.get_device_properties(beam.device).multi_processor_count  # resident warps of the adaptive kernel
+    warps = -(-B * int(beam._plan.g) // 32)
+    return 8 if slots < warps <= 64 * slots and max_attempts > 8 else 0
+
+
 def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[float], X0, *, method: str = "RK45",
                    h: Optional[float] = None, t_eval=None, rtol: float = 1e-3, atol: float = 1e-6, u=None,
                    controller=None, save_every: Optional[int] = None, max_attempts: int = 10_000_000,
-                   first_step: Optional[float] = None, outputs="state") -> EnsembleResult:
+                   first_step: Optional[float] = None, outputs="state", pilot_attempts: Optional[int] = None) -> EnsembleResult:
     """Integrate every member of the ensemble over ``t_span``.
 
     RK4: ``h`` is required; ``nsteps = round((tf - t0) / h)``; outputs are stored every
@@ -413,6 +429,10 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
     ``"shape"``, ``"shape_velocity"`` or a list of state indices (``outputs.output_selection``): the kernels
     then store only those rows (``.y`` is ``[B, len(selection), T]``, ``.rows`` names them) instead of
     materialising the whole trajectory; ``.x_final`` always holds the full final state.
+
+    ``pilot_attempts`` (RK45, fused path): attempts of the pilot launch that orders the members longest-first for
+    the main launch (``_pilot_attempts``; None = automatic, 0 = one launch in natural order).  Results do not
+    depend on it: every member takes the same step sequence either way.
     """
     import torch
 
@@ -514,13 +534,31 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
         t, hh, status, counters = _rk45_unfused(beam, X, t0, tf, rtol, atol, u, controller, te if Y is not None else None,
                                                 Y, int(max_attempts), first_step)
     else:
-        with torch.cuda.device(dev):
-            rc = _lib.load().crb_rk45(
-                C.byref(beam._plan), C.byref(sysm), X.data_ptr(), t.data_ptr(), hh.data_ptr(), tf, float(rtol), float(atol),
-                d_te.data_ptr() if d_te is not None else None, len(te), Y.data_ptr() if Y is not None else None,
-                status.data_ptr(), counters.data_ptr(), int(max_attempts), beam._stream(),
-            )
-        _lib.check(rc)
+        def launch(budget):
+            with torch.cuda.device(dev):
+                rc = _lib.load().crb_rk45(
+                    C.byref(beam._plan), C.byref(sysm), X.data_ptr(), t.data_ptr(), hh.data_ptr(), tf, float(rtol), float(atol),
+                    d_te.data_ptr() if d_te is not None else None, len(te), Y.data_ptr() if Y is not None else None,
+                    status.data_ptr(), counters.data_ptr(), int(budget), beam._stream(),
+                )
+            _lib.check(rc)
+
+        # Longest members first.  Members take different numbers of attempts (config 4: 92 on average, 178 at most) and
+        # a launch ends with its stragglers; when the ensemble is a few waves of warps, a PILOT launch of a few attempts
+        # per member (no work is repeated: the second launch resumes every member exactly where the budget stopped it)
+        # tells how many steps each member still wants, (tf - t) / h, and the second launch hands the members out in
+        # that order (crb_system_t.member_order).
+        pilot = _pilot_attempts(beam, B, pilot_attempts, max_attempts)
+        if pilot > 0:
+            launch(pilot)
+            remaining = torch.where(status == 1, (tf - t) / hh.abs().clamp_min(1e-300), torch.zeros_like(t))
+            order = torch.argsort(remaining, descending=True).to(torch.int32)
+            sysm.member_order = order.data_ptr()
+            keep = list(keep) + [order]
+            launch(int(max_attempts) - pilot)
+            hh.abs_()
+        else:
+            launch(max_attempts)
     if Y is not None:
         if needs_unfused and sel is not None:
             Y = Y[:, :, d_sel]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CRB_VERSION 106
+#define CRB_VERSION 107
 #define CRB_MAX_SLOTS 256      /* node slots per member handled by one lane group */
 #define CRB_MAX_LEVELS 5       /* log2(32) scan levels */
 #define CRB_LQR_MAX_ELEMENTS 128 /* crb_dense_matrices_batched: elements per beam */
@@ -149,6 +149,11 @@ typedef struct crb_system_t {
    * crb_rk4 / crb_midpoint (Y_out) and crb_rk45 (Y_eval) are then [T, B, out_n_sel] instead of [T, B, 2n]. */
   const int32_t* out_sel_inv;
   int32_t out_n_sel;
+  /* crb_rk45 only.  Launch order of the members: device int32 [B], a permutation of 0 .. B-1, or NULL for the natural
+   * order.  Members of an adaptive run take different numbers of attempts and a member cannot be split, so the launch
+   * ends with its longest stragglers; the hardware hands blocks out in launch order, and "longest first" fills the
+   * tail with short members (solve_ensemble orders by the time each member covered in a short pilot launch). */
+  const int32_t* member_order;
 } crb_system_t;
 
 /* library version (CRB_VERSION of the build) */
@@ -244,8 +249,12 @@ int crb_midpoint(const crb_plan_t* plan, const crb_system_t* sys, const double* 
  * examples/pyodide_example/pyodide_example.py:69-75 and throughout the reference's tests.
  *   t [B] in/out current time, h_abs [B] in/out next step size (<= 0: select_initial_step),
  *   t_eval [n_eval] ascending output times (dense output), Y_eval [n_eval, B, 2n],
- *   status [B]: 0 running/finished at t_bound, -1 step size too small, 1 attempt budget hit
- *   counters [B,3]: nfev, accepted, rejected.  max_attempts bounds the work of one launch. */
+ *   status [B] in/out: 0 running/finished at t_bound, -1 step size too small, 1 attempt budget hit
+ *   counters [B,3]: nfev, accepted, rejected.  max_attempts bounds the work of one launch.
+ * Resuming: a member whose status is 1 ON ENTRY continues exactly where the budget stopped it -- same step sequence,
+ * same counters as an uninterrupted run: f(t, y) is re-evaluated without being counted, and h_abs < 0 on entry means
+ * "|h_abs| is the next step size and the last attempt was rejected" (rk.py:160-176: the growth factor of the next
+ * accepted step is capped at 1), which is how a budget stop writes it. */
 int crb_rk45(const crb_plan_t* plan, const crb_system_t* sys, double* X, double* t,
              double* h_abs, double t_bound, double rtol, double atol, const double* t_eval,
              int32_t n_eval, double* Y_eval, int32_t* status, int64_t* counters,

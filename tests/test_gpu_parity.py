@@ -410,6 +410,40 @@ def test_rhs_random_topologies_match_oracle(seed):
         assert block_err(Y[i], b.rhs(0.1, X[i], U[i]), n) < 1e-10, (seed, i, N, list(bc), list(et))
 
 
+def test_rk45_pilot_launch_and_member_order_change_nothing():
+    """solve_ensemble(method="RK45") may split the run into a pilot launch (attempt budget) and a main launch that
+    resumes every member and hands the members out longest-first (crb_system_t.member_order).  A resumed member takes
+    exactly the step sequence of an uninterrupted run: final state, time, step size, counters and dense output are
+    bitwise equal for pilots of 1, 5 and 12 attempts -- also when the pilot ends on a rejected attempt."""
+    from continuum_robot_b200 import ForceParams, TipImpulse, solve_ensemble
+    from continuum_robot_b200 import ensembles as ens
+
+    B = 192
+    e = ens.config4(B, seed=9)
+    m = ens.material()
+    par = np.empty((B, 64, 7))
+    par[:, :, 0], par[:, :, 2], par[:, :, 3], par[:, :, 4] = m["length"], m["I"], m["rho"], m["A"]
+    par[:, :, 1] = e.E
+    par[:, :, 5], par[:, :, 6] = m["wetted_area"], m["drag_coef"]
+    from continuum_robot_b200 import BatchedDynamicEulerBernoulliBeam
+
+    beam = BatchedDynamicEulerBernoulliBeam({"params": par, "type": ["nonlinear"] * 64},
+                                            ForceParams(fluid_density=1000.0, enable_fluid_effects=True, enable_gravity_effects=True))
+    beam.create_system_func(); beam.create_input_func()
+    imp = TipImpulse(torch.from_numpy(e.impulse_amp).cuda())
+    X0 = torch.zeros(B, 384, dtype=torch.float64, device="cuda")
+    te = np.linspace(0.0, 1e-3, 6)
+    runs = {}
+    for pilot in (0, 1, 5, 12):
+        r = solve_ensemble(beam, (0.0, 1e-3), X0, method="RK45", rtol=1e-6, atol=1e-9, u=imp, t_eval=te, pilot_attempts=pilot)
+        assert r.success
+        runs[pilot] = (r.x_final.clone(), r.y.clone(), r.nfev.clone(), r.naccept.clone(), r.nreject.clone(), r.t_final.clone(), r.h_last.clone())
+    assert int(runs[0][4].sum()) > 0  # some attempts are rejected in this ensemble
+    for pilot in (1, 5, 12):
+        for a, b in zip(runs[0], runs[pilot]):
+            assert torch.equal(a, b), pilot
+
+
 def test_rk45_step_sequence_equals_scipy_controller():
     """GPU RK45 vs the oracle's restated SciPy controller on the same beam: identical accepted /
     rejected step counts and nfev, outputs equal to ~1e-9 of the tolerance band."""

@@ -545,7 +545,8 @@ def test_lqr_entry_points_validate_arguments_on_the_host():
     pb, sb = C.c_int32(), C.c_int32()
     assert lib.crb_abi_sizes(C.byref(pb), C.byref(sb)) == 0
     assert (pb.value, sb.value) == (C.sizeof(L.CrbPlan), C.sizeof(L.CrbSystem))
-    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.out_sel_inv.offset == C.sizeof(L.CrbSystem) - 16
+    assert C.sizeof(L.CrbSystem) % 8 == 0 and L.CrbSystem.out_sel_inv.offset == C.sizeof(L.CrbSystem) - 24
+    assert L.CrbSystem.member_order.offset == C.sizeof(L.CrbSystem) - 8
     assert L.CrbSystem.member_op.offset == L.CrbSystem.gain_stride.offset + 8 == L.CrbSystem.u_sin_amp.offset - 8
 
 
