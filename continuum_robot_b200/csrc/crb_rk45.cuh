@@ -123,6 +123,9 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 #ifndef CRB_RK45_LOCKSTEP
 #define CRB_RK45_LOCKSTEP 0  // 1: the warps of a block start every attempt together (block barrier): they then walk through the same code at about the same time and share its instruction-cache lines
 #endif
+#ifndef CRB_RK45_168
+#define CRB_RK45_168 1
+#endif
 #ifndef CRB_RK45_ROLLED
 #define CRB_RK45_ROLLED 1  // 1: stage inputs by one rolled loop over the earlier stages (8 KB less code; measured 7.84 -> 7.03 ms on config 4) instead of six unrolled copies
 #endif
@@ -132,7 +135,10 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 #ifdef CRB_RK45_MAXNREG
 #define CRB_RK45_BOUNDS __maxnreg__(CRB_RK45_MAXNREG)  // register cap chosen directly (occupancy experiments)
 #else
-#define CRB_RK45_BOUNDS __launch_bounds__(32 * WPB, CRB_RK45_MINBLOCKS)
+// The 64-element shape (2 slots per lane, 32 lanes per member) fits 168 registers without spills, which is what a
+// THIRD warp per scheduler needs (16 K registers per sub-partition / (3 warps x 32 lanes) = 170): 10 resident warps per
+// SM (5 blocks; shared memory allows no sixth) instead of 8.  Other shapes keep their allocation.
+#define CRB_RK45_BOUNDS __maxnreg__((M == 2 && LV == 5 && WPB == 2 && CRB_RK45_168) ? 168 : 255)
 #endif
 template <int M, unsigned FEAT, int LV, int WPB, bool PM = false>
 __global__ void CRB_RK45_BOUNDS
