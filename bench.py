@@ -173,7 +173,10 @@ def run_reference(args):
     # member-step, so K is capped to keep the arm within a few minutes
     cap = 2000 if kind == "reference" else 4000
     steps = min(max(1, args.steps), cap)
-    val, cores, sample = cpu_throughput(kind, steps, members_per_core=1, warmup=min(max(args.warmup, 1), 20))
+    # ... and with few steps several members per core, so that the timed sample is about a second of stepping per core
+    # rather than a few milliseconds (20 steps of one member are 30 ms)
+    per_core = max(1, min(64, -(-600 // steps)))
+    val, cores, sample = cpu_throughput(kind, steps, members_per_core=per_core, warmup=min(max(args.warmup, 1), 20))
     ms = 1e3 * (cores * 32) / val
     line = {
         "impl": "reference", "metric": "beam-element RK4 steps/sec", "value": val, "unit": "element-steps/s",
