@@ -141,6 +141,7 @@ extern "C" int crb_system_slice(const crb_plan_t* plan, const crb_system_t* sys,
   }
   if (sys->gain && sys->gain_stride) out->gain = sys->gain + lo * sys->gain_stride;
   if (sys->member_op) out->member_op = sys->member_op + lo * n * (3 * n + 1);
+  out->member_order = nullptr;  // a launch order of the whole ensemble does not carry over to a sub-range
   return 0;
 }
 
