@@ -542,15 +542,27 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
 // (< 1 ulp on [-pi/4, pi/4]); about 25 FP64 instructions instead of a call into the library routine
 // with its large-argument path (the gravity term evaluates one per segment and RHS,
 // gravity_forces.py:117-125).  |x| >= 1e5 (never a beam rotation) falls back to the library.
+// SMALL_PATH: a warp vote skips the reduction and the quadrant selects when |x| <= pi/4 on every active lane (same
+// polynomials on the same argument: bitwise the same result).  Worth it only where the sincos is a large share of a
+// short right-hand side: the shared-operator kernel gains 4 % (8.18 -> 7.87 ms on config 5); in the banded kernels
+// the extra branch costs more than it saves (config 1 -8 %, config 4 -6 %, dense rollout -8 %: measured), so it is opt-in.
+template <bool SMALL_PATH = false>
 __device__ __forceinline__ void crb_sincos(double x, double& sn, double& cs) {
   if (!(fabs(x) < 1.0e5)) {
     sincos(x, &sn, &cs);
     return;
   }
-  const double n = rint(x * 6.36619772367581382433e-01);
-  double r = fma(-n, 1.57079632679489655800e+00, x);
-  r = fma(-n, 6.12323399573676603587e-17, r);
-  const int q = (int)n;
+  // |x| <= pi/4 on every active lane (beam rotations: the common case): the reduction below would find n = 0, r = x
+  // and quadrant 0
+  const bool small = SMALL_PATH && __all_sync(__activemask(), fabs(x) <= 0.78539816339744828);
+  double n = 0.0, r = x;
+  int q = 0;
+  if (!small) {
+    n = rint(x * 6.36619772367581382433e-01);
+    r = fma(-n, 1.57079632679489655800e+00, x);
+    r = fma(-n, 6.12323399573676603587e-17, r);
+    q = (int)n;
+  }
   const double z = r * r;
   double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
   ps = fma(z, ps, 2.75573137070700676789e-06);
@@ -564,6 +576,11 @@ __device__ __forceinline__ void crb_sincos(double x, double& sn, double& cs) {
   pc = fma(z, pc, -1.38888888888741095749e-03);
   pc = fma(z, pc, 4.16666666666666019037e-02);
   const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+  if (small) {
+    sn = s0;
+    cs = c0;
+    return;
+  }
   const double a = (q & 1) ? c0 : s0, b = (q & 1) ? s0 : c0;
   sn = (q & 2) ? -a : a;
   cs = ((q + 1) & 2) ? -b : b;
