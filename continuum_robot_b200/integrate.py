@@ -398,7 +398,7 @@ def _rk45_unfused(beam, X, t0, tf, rtol, atol, u, controller, te, Y_eval, max_at
     return t, h_abs, status, counters
 
 
-def _pilot_attempts(beam, B: int, requested, max_attempts: int) -> int:
+def _pilot_attempts(beam, B: int, requested, max_attempts: int, sm_count: Optional[int] = None) -> int:
     """Attempts of the pilot launch of an adaptive solve (0: one launch in natural order).  ``requested`` None: a pilot
     of 8 attempts when the ensemble is more than one and at most 64 waves of the device's resident warps (one wave
     starts everything at once, and the tail of a very long launch is short relative to its length);
@@ -409,7 +409,9 @@ def _pilot_attempts(beam, B: int, requested, max_attempts: int) -> int:
         requested = int(os.environ["CRB_RK45_PILOT"])
     if requested is not None:
         return max(0, min(int(requested), int(max_attempts) - 1))
-    slots = 8 * torch.cuda.get_device_properties(beam.device).multi_processor_count  # resident warps of the adaptive kernel
+    if sm_count is None:
+        sm_count = torch.cuda.get_device_properties(beam.device).multi_processor_count
+    slots = 8 * sm_count  # resident warps of the adaptive kernel
     warps = -(-B * int(beam._plan.g) // 32)
     return 8 if slots < warps <= 64 * slots and max_attempts > 8 else 0
 

@@ -579,3 +579,31 @@ def test_header_is_plain_c_and_the_library_serves_a_c_client(tmp_path):
     assert float(vals["trace_M"]) == serial(M) and float(vals["trace_K"]) == serial(K)
     assert float(vals["asym_K"]) == 0.0
     assert vals["bad_bc"].startswith("rc -1") and int(vals["bad_bc"].split()[-1]) > 10
+
+
+def test_rk45_pilot_launch_policy(monkeypatch):
+    """Host logic of solve_ensemble's pilot launch (integrate._pilot_attempts): on for ensembles of more than one and
+    at most 64 waves of resident warps, off otherwise; an explicit request or CRB_RK45_PILOT wins; never the whole
+    attempt budget."""
+    from types import SimpleNamespace
+
+    from continuum_robot_b200.integrate import _pilot_attempts
+
+    monkeypatch.delenv("CRB_RK45_PILOT", raising=False)
+    beam = SimpleNamespace(_plan=SimpleNamespace(g=32), device="cuda:0")  # one member per warp
+    slots = 8 * 148
+    assert _pilot_attempts(beam, slots, None, 10**6, sm_count=148) == 0          # one wave: everything starts at once
+    assert _pilot_attempts(beam, slots + 1, None, 10**6, sm_count=148) == 8
+    assert _pilot_attempts(beam, 4096, None, 10**6, sm_count=148) == 8           # BASELINE config 4
+    assert _pilot_attempts(beam, 64 * slots, None, 10**6, sm_count=148) == 8
+    assert _pilot_attempts(beam, 64 * slots + 1, None, 10**6, sm_count=148) == 0  # the tail is short against the launch
+    assert _pilot_attempts(beam, 4096, None, 8, sm_count=148) == 0                # budget too small to split
+    half = SimpleNamespace(_plan=SimpleNamespace(g=16), device="cuda:0")          # two members per warp
+    assert _pilot_attempts(half, 2 * slots, None, 10**6, sm_count=148) == 0
+    assert _pilot_attempts(half, 2 * slots + 2, None, 10**6, sm_count=148) == 8
+    assert _pilot_attempts(beam, 10, 5, 10**6, sm_count=148) == 5                 # explicit request
+    assert _pilot_attempts(beam, 4096, 0, 10**6, sm_count=148) == 0
+    assert _pilot_attempts(beam, 4096, 50, 20, sm_count=148) == 19                # at least one attempt is left for the main launch
+    monkeypatch.setenv("CRB_RK45_PILOT", "3")
+    assert _pilot_attempts(beam, 10, None, 10**6, sm_count=148) == 3
+    assert _pilot_attempts(beam, 10, 7, 10**6, sm_count=148) == 7                 # the argument wins over the environment
