@@ -558,9 +558,9 @@ def solve_ensemble(beam: BatchedDynamicEulerBernoulliBeam, t_span: Sequence[floa
             sysm.member_order = order.data_ptr()
             keep = list(keep) + [order]
             launch(int(max_attempts) - pilot)
-            hh.abs_()
         else:
             launch(max_attempts)
+        hh.abs_()  # (a budget stop after a rejected attempt leaves -h: the C ABI's resume flag, of no use to the caller here)
     if Y is not None:
         if needs_unfused and sel is not None:
             Y = Y[:, :, d_sel]
