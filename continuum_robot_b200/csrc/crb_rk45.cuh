@@ -110,9 +110,8 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 // slowest member, so the adaptive kernel runs with small blocks (2 warps; the hardware block scheduler
 // then balances the ragged ensemble) where the fixed-step kernels use 4.
 // PM: per-member mass factors (shape-specialised kernels): compact solve on per-member shared-memory regions.
-#ifndef CRB_RK45_MINBLOCKS
-#define CRB_RK45_MINBLOCKS 1  // resident blocks per SM the register allocation is sized for (1: no cap)
-#endif
+// Compile-time switches below: the defaults are the measured best on config 4; the others are kept as the record of what
+// was measured (benchmarks/build_variant.sh, profiles/r2_rk45_experiments.json).
 #ifndef CRB_RK45_QVS
 #define CRB_RK45_QVS 0  // 1: the committed state (q, v) lives in shared memory next to the stage accelerations
 #endif
@@ -124,13 +123,13 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 #define CRB_RK45_LOCKSTEP 0  // 1: the warps of a block start every attempt together (block barrier): they then walk through the same code at about the same time and share its instruction-cache lines
 #endif
 #ifndef CRB_RK45_168
-#define CRB_RK45_168 1
+#define CRB_RK45_168 1  // 1: 168-register cap for the 64-element shape (see CRB_RK45_BOUNDS)
 #endif
 #ifndef CRB_RK45_ROLLED
 #define CRB_RK45_ROLLED 1  // 1: stage inputs by one rolled loop over the earlier stages (8 KB less code; measured 7.84 -> 7.03 ms on config 4) instead of six unrolled copies
 #endif
 #ifndef CRB_RK45_UMS_ALL
-#define CRB_RK45_UMS_ALL 1  // the nonlinear profile uses the compact mass solve too (4 KB of factors per block instead of 28: measured 8.08 -> 7.78 ms on config 4)
+#define CRB_RK45_UMS_ALL 1  // the nonlinear profile uses the compact mass solve too (17 KB of factors per block instead of 28: measured 8.08 -> 7.78 ms on config 4)
 #endif
 #ifdef CRB_RK45_MAXNREG
 #define CRB_RK45_BOUNDS __maxnreg__(CRB_RK45_MAXNREG)  // register cap chosen directly (occupancy experiments)
@@ -145,10 +144,10 @@ __global__ void CRB_RK45_BOUNDS
 crb_rk45_kernel(KPlan P, crb_system_t S, SmemLayout SL, Rk45Args A, DpTab T) {
   constexpr int THREADS = 32 * WPB;
   extern __shared__ __align__(16) double smem[];
-  // Shape-specialised LINEAR kernels (profile A) use the compact mass solve (fast_solve_r) on the compact
-  // factor copy: measured +30 % on config 3's shape (shared-memory bound with the stored-spike solve).
-  // The nonlinear profile keeps the stored spikes: it is latency-bound and the compact solve's four
-  // dependent sweeps measured 3-5 % slower there than two sweeps plus independent corrections.
+  // Shape-specialised kernels use the compact mass solve (fast_solve_r) on the compact factor copy: +30 % on config
+  // 3's shape (shared-memory bound with the stored-spike solve), and here also for the nonlinear profile
+  // (CRB_RK45_UMS_ALL: 17 KB of factors per block instead of 28 for 32 lanes per member; 8.08 -> 7.78 ms on config 4) --
+  // the fixed-step nonlinear kernel keeps the stored spikes (compact solve 2 % slower there, crb_rk4.cu).
   constexpr bool UMS = LV >= 0 && (FEAT == CRB_F_PROFILE_A || PM || CRB_RK45_UMS_ALL);
   const double* mf = UMS ? smem : stage_mfac(S, P, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
