@@ -175,3 +175,52 @@ def test_guard_detects_a_stray_write():
     g2 = Guarded((5,), torch.int32, 0)
     g2.buf[PAD - 1] = 0
     assert not g2.intact()
+
+
+@pytest.mark.parametrize("B,N", [(1, 6), (13, 6), (5, 14), (3, 20)])
+def test_lqr_and_rhs_entry_points_write_only_their_arrays(B, N):
+    """crb_dense_matrices_batched, crb_lqr_gains (shared-memory and workspace paths), crb_member_operators, crb_rhs and
+    crb_forces through the C ABI on guarded outputs (the workspace is guarded too)."""
+    import ctypes as C
+
+    from continuum_robot_b200 import _lib
+
+    rng = np.random.default_rng(B + N)
+    par = _params(B, N, rng, vary_mass=True)
+    et, bc = np.zeros(N, dtype=int), np.array([1] + [0] * N)
+    beam = make_gpu_beam(par, et, bc, 1000.0, True)
+    n = beam.n_free
+    lib = _lib.load()
+    dpar = torch.from_numpy(par).cuda()
+    M, K = Guarded((B, n, n)), Guarded((B, n, n))
+    with torch.cuda.device(beam.device):
+        _lib.check(lib.crb_dense_matrices_batched(C.byref(beam._plan), dpar.data_ptr(), B, bytes(int(t) for t in et), bytes(int(b) for b in bc),
+                                                  M.t.data_ptr(), K.t.data_ptr(), beam._stream()))
+        torch.cuda.synchronize()
+        assert M.intact() and K.intact()
+        Q = torch.diag(torch.cat([torch.full((n,), 100.0), torch.full((n,), 10.0)])).to("cuda", torch.float64)
+        R = torch.eye(n, dtype=torch.float64, device="cuda")
+        need = C.c_size_t(0)
+        _lib.check(lib.crb_lqr_workspace_bytes(n, B, C.byref(need)))
+        ws = Guarded(((need.value + 7) // 8,))
+        gain, S, resid, status = Guarded((B, n, 2 * n)), Guarded((B, 2 * n, 2 * n)), Guarded((B,)), Guarded((B,), torch.int32, 0)
+        _lib.check(lib.crb_lqr_gains(n, B, M.t.data_ptr(), 0, K.t.data_ptr(), 0, Q.data_ptr(), R.data_ptr(), 1, gain.t.data_ptr(),
+                                     S.t.data_ptr(), resid.t.data_ptr(), status.t.data_ptr(), ws.t.data_ptr(), need.value, beam._stream()))
+        torch.cuda.synchronize()
+        for g in (M, K, ws, gain, S, resid, status):
+            assert g.intact(), (B, N)
+        assert int(status.t.abs().sum()) == 0 and bool(torch.isfinite(gain.t).all())
+        if n <= 32:
+            op, st = Guarded((B, n, 3 * n + 1)), Guarded((B,), torch.int32, 0)
+            _lib.check(lib.crb_member_operators(n, B, M.t.data_ptr(), 0, K.t.data_ptr(), 0, gain.t.data_ptr(), None, op.t.data_ptr(),
+                                                st.t.data_ptr(), beam._stream()))
+            torch.cuda.synchronize()
+            assert op.intact() and st.intact() and gain.intact()
+        drag, grav, _ = beam._active_forces()
+        sysm, keep = beam.make_system(B, drag=drag, gravity=grav)
+        X = _state(B, n, rng)
+        dX, F = Guarded((B, 2 * n)), Guarded((B, n))
+        _lib.check(lib.crb_rhs(C.byref(beam._plan), C.byref(sysm), X.t.data_ptr(), 0.0, dX.t.data_ptr(), beam._stream()))
+        _lib.check(lib.crb_forces(C.byref(beam._plan), C.byref(sysm), X.t.data_ptr(), F.t.data_ptr(), beam._stream()))
+        torch.cuda.synchronize()
+        assert X.intact() and dX.intact() and F.intact() and bool(torch.isfinite(dX.t).all())
