@@ -607,3 +607,15 @@ def test_rk45_pilot_launch_policy(monkeypatch):
     monkeypatch.setenv("CRB_RK45_PILOT", "3")
     assert _pilot_attempts(beam, 10, None, 10**6, sm_count=148) == 3
     assert _pilot_attempts(beam, 10, 7, 10**6, sm_count=148) == 7                 # the argument wins over the environment
+
+
+def test_integration_md_stub_mirrors_the_struct():
+    """The ctypes stub shown in INTEGRATION.md lists the fields of crb_system_t in the order of the product's mirror."""
+    import os
+    import re
+
+    L = _lib()
+    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    blk = txt[txt.index("class CrbSystem(C.Structure)"):]
+    blk = blk[:blk.index("]\n", blk.index("member_order"))]
+    assert re.findall(r'\("(\w+)",', blk) == [f[0] for f in L.CrbSystem._fields_]
