@@ -537,6 +537,13 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
   L.mc.g = g;
 }
 
+// fdlibm kernel polynomial coefficients of crb_sincos (sin: S6..S1, cos: C6..C1, -1/2)
+static __constant__ double kSinCos[13] = {
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02, -0.5};
+
 // sin and cos of a rotation angle, inlinable and branch-free on the common path: two-constant FMA
 // Cody-Waite reduction by pi/2 (x - n c1 is exact in an FMA) and the fdlibm kernel polynomials
 // (< 1 ulp on [-pi/4, pi/4]); about 25 FP64 instructions instead of a call into the library routine
@@ -546,7 +553,7 @@ __device__ __forceinline__ void load_lane_ctx(LaneCtx<M>& L, const KPlan& P, con
 // polynomials on the same argument: bitwise the same result).  Worth it only where the sincos is a large share of a
 // short right-hand side: the shared-operator kernel gains 4 % (8.18 -> 7.87 ms on config 5); in the banded kernels
 // the extra branch costs more than it saves (config 1 -8 %, config 4 -6 %, dense rollout -8 %: measured), so it is opt-in.
-template <bool SMALL_PATH = false>
+template <bool SMALL_PATH = false, bool CONST_COEF = false>
 __device__ __forceinline__ void crb_sincos(double x, double& sn, double& cs) {
   if (!(fabs(x) < 1.0e5)) {
     sincos(x, &sn, &cs);
@@ -564,18 +571,24 @@ __device__ __forceinline__ void crb_sincos(double x, double& sn, double& cs) {
     q = (int)n;
   }
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  // CONST_COEF: coefficients as constant-bank operands instead of literals.  A literal costs two uniform moves, which
+  // the compiler hoists out of a step loop when it has uniform registers to spare: the banded gravity kernel (config 1)
+  // is 9 % FASTER with literals, the shared-operator kernel 4 % and the dense per-member kernel 1.5 % faster with the
+  // constant bank (229 -> 149 UMOV in the shared-operator kernel's SASS); config 4 does not care.  Measured, so opt-in.
+#define CRB_SC(i, lit) (CONST_COEF ? kSinCos[i] : (lit))
+  double ps = fma(z, CRB_SC(0, 1.58969099521155010221e-10), CRB_SC(1, -2.50507602534068634195e-08));
+  ps = fma(z, ps, CRB_SC(2, 2.75573137070700676789e-06));
+  ps = fma(z, ps, CRB_SC(3, -1.98412698298579493134e-04));
+  ps = fma(z, ps, CRB_SC(4, 8.33333333332248946124e-03));
+  ps = fma(z, ps, CRB_SC(5, -1.66666666666666324348e-01));
   const double s0 = fma(r * z, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
-  const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+  double pc = fma(z, CRB_SC(6, -1.13596475577881948265e-11), CRB_SC(7, 2.08757232129817482790e-09));
+  pc = fma(z, pc, CRB_SC(8, -2.75573143513906633035e-07));
+  pc = fma(z, pc, CRB_SC(9, 2.48015872894767294178e-05));
+  pc = fma(z, pc, CRB_SC(10, -1.38888888888741095749e-03));
+  pc = fma(z, pc, CRB_SC(11, 4.16666666666666019037e-02));
+  const double c0 = fma(z * z, pc, fma(CRB_SC(12, -0.5), z, 1.0));
+#undef CRB_SC
   if (small) {
     sn = s0;
     cs = c0;
@@ -587,9 +600,10 @@ __device__ __forceinline__ void crb_sincos(double x, double& sn, double& cs) {
 }
 
 // Gravity contribution of one pseudo-segment (gravity_forces.py:117-125).
+template <bool CONST_COEF = false>
 __device__ __forceinline__ void grav_pair(double phi, double hm, double gx, double gy, double& fa, double& ft) {
   double sn, cs;
-  crb_sincos(phi, sn, cs);
+  crb_sincos<false, CONST_COEF>(phi, sn, cs);
   fa = fma(cs, gx, sn * gy) * hm;
   ft = fma(-sn, gx, cs * gy) * hm;
 }

@@ -394,7 +394,7 @@ __device__ __forceinline__ void shared_steps(const SharedArgs& A, const double* 
 #pragma unroll
         for (int p = 0; p < GKP; ++p) {
           double sn, cs;
-          crb_sincos<true>(ph[p], sn, cs);
+          crb_sincos<true, true>(ph[p], sn, cs);
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             if (MGC >> (p * NT + nt) & 1) dmma884(acc[nt][0], acc[nt][1], cs, Gc[(p * NT + nt) * 32]);
